@@ -1,0 +1,137 @@
+/* navtex_b200.h -- C ABI of the batched, B200-native NAVTEX receive chain.
+ *
+ * One engine = one GPU = S independent 252 kS/s zero-IF IQ streams, each carrying the 518 kHz
+ * (+14 kHz) and 490 kHz (-14 kHz) channels.  It replaces, for all S streams at once, the
+ * reference's per-sample push chain (all citations relative to receiver/ in bartelvdh/Navtex):
+ *
+ *   init_fir_filter1()            fir1cpp.h:2   -> nvx_engine_create / nvx_engine_reset
+ *   init_fir2_wrapper()           nav_sched.h:1 -> nvx_engine_create / nvx_engine_reset
+ *   sample_in_1(double I,double Q) fir1cpp.h:3, called per sample at capt_sched.c:511
+ *                                               -> nvx_engine_push_* (a whole [S][n] block per call)
+ *   fir_filter3::sample_in        fir3cpp.h:100 -> stage taps via nvx_engine_read_y3
+ *   decoder::sample_in            decoder.h:85  -> bit taps via nvx_engine_read_bits
+ *   byte_state_machine::receive_bit nav_b_sm.h:127 -> events, nvx_engine_read_events
+ *   add_message(bbbb,message,freq) nav_b_sm.C:4, message_store.h:7
+ *                                               -> nvx_engine_poll_messages / nvx_message_cb
+ *
+ * The legacy symbol names themselves are provided by libnavtex_compat.so (navtex_compat.h), a
+ * one-stream adapter over this ABI, so a host written against the reference headers relinks
+ * unchanged.  There is no CPU fallback: every entry point needs a CUDA device and fails with
+ * NVX_ERR_CUDA otherwise.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every buffer it passes; the engine
+ * owns all device state; one caller thread per engine; return 0 on success, negative nvx_status
+ * otherwise (nvx_last_error() gives a message).  Sample blocks are stream-major:
+ * element (s, k) of a block of n samples per stream is at base[(s * n + k) * 2 + {0 = I, 1 = Q}].
+ * n must be a multiple of NVX_BLOCK_ALIGN (280 = 4*7*10, one 900 Hz output).
+ */
+#ifndef NAVTEX_B200_H
+#define NAVTEX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVX_BLOCK_ALIGN 280
+#define NVX_FS_HZ 252000
+
+typedef enum {
+    NVX_OK = 0,
+    NVX_ERR_ARG = -1,      /* bad argument (null, misaligned n, wrong engine state) */
+    NVX_ERR_CUDA = -2,     /* CUDA runtime/driver failure, including "no device" */
+    NVX_ERR_NOMEM = -3,
+    NVX_ERR_OVERFLOW = -4  /* a per-block output buffer was too small; results up to that point are valid */
+} nvx_status;
+
+typedef struct nvx_engine nvx_engine;
+
+typedef struct {
+    int device;                 /* CUDA device ordinal */
+    int n_streams;              /* S */
+    long long max_block;        /* largest n a push will carry (samples per stream) */
+    int freq_tag[2];            /* tags handed to add_message for channel 0 (+14 kHz) / 1 (-14 kHz); 0,0 = 518,490 */
+    /* optional replacement tap sets of the reference lengths 37 / 47 / 71 (NULL = reference taps) */
+    const double *h1, *h2, *h3;
+    int keep_bits;              /* record 'B'/'Y' decisions and discriminator sums for nvx_engine_read_bits */
+    int first_stream_id;        /* global id of stream 0 (multi-GPU sharding; only used to label messages) */
+} nvx_config;
+
+typedef struct {
+    int stream;                 /* global stream id */
+    int freq;                   /* 518 / 490 */
+    char bbbb[8];               /* B1B2B3B4, NUL terminated */
+    const char *text;           /* message text, NUL terminated; valid until the next poll/destroy */
+    size_t text_len;
+} nvx_message;
+
+/* add_message-shaped callback (nav_b_sm.C:4): strings are borrowed for the duration of the call */
+typedef int (*nvx_message_cb)(void *user, int stream, char *bbbb, char *message, int freq);
+
+void nvx_default_config(nvx_config *cfg);
+const char *nvx_last_error(void);
+
+int nvx_engine_create(const nvx_config *cfg, nvx_engine **out);
+void nvx_engine_destroy(nvx_engine *e);
+/* back to the state right after create (zero FIR history, decoder INIT, phasing search) */
+int nvx_engine_reset(nvx_engine *e);
+
+/* ---- ingest: n samples for every stream.  Host variants copy H2D (pinned or pageable) ----- */
+int nvx_engine_push_host_f32(nvx_engine *e, const float *iq, long long n);
+int nvx_engine_push_host_s16(nvx_engine *e, const int16_t *iq, long long n);   /* SDRplay / WAV sample format */
+/* device-resident float2 block [S][n], 16-byte aligned; processed in place, asynchronously on the
+ * engine's stream (ordered after everything previously queued on it) */
+int nvx_engine_push_device_f32(nvx_engine *e, const void *d_iq, long long n);
+int nvx_engine_push_device_s16(nvx_engine *e, const void *d_iq, long long n);
+/* wait for everything pushed so far and run the host-side message assembly */
+int nvx_engine_sync(nvx_engine *e);
+
+/* ---- results -------------------------------------------------------------------------------- */
+/* messages completed since the previous poll (implies sync); pointers valid until the next poll */
+int nvx_engine_poll_messages(nvx_engine *e, const nvx_message **msgs, size_t *count);
+/* alternatively deliver them through an add_message-shaped callback during sync/poll */
+int nvx_engine_set_message_callback(nvx_engine *e, nvx_message_cb cb, void *user);
+
+/* taps of the LAST pushed block (imply sync).  y3: [S][2][n/280] float pairs (I,Q) at 900 Hz */
+int nvx_engine_read_y3(nvx_engine *e, float *out, size_t cap_floats, size_t *n_per_channel);
+/* bits decided during the last block for (stream, ch): 'B'/'Y'; sums = 4 floats per bit (BR BI YR YI), may be NULL */
+int nvx_engine_read_bits(nvx_engine *e, int stream, int ch, char *bits, float *sums, size_t cap, size_t *count);
+/* character / '\n' (line complete) / 0x18 (abort) events of the last block for (stream, ch) */
+int nvx_engine_read_events(nvx_engine *e, int stream, int ch, char *ev, size_t cap, size_t *count);
+
+/* ---- measurement hooks (bench.py) --------------------------------------------------------- */
+typedef struct {
+    double cascade_ms;          /* sum of fused-FIR kernel time since the last call, CUDA events on the engine stream */
+    double demod_ms;            /* same for the demod/bit-sync/FSM kernel */
+    long long cascade_launches;
+    long long demod_launches;
+    long long aux_launches;     /* tail carry, s16 -> f32 conversion */
+    long long samples;          /* IQ samples (all streams) pushed */
+} nvx_stats;
+int nvx_engine_enable_timing(nvx_engine *e, int on);
+int nvx_engine_get_stats(nvx_engine *e, nvx_stats *out, int reset);
+/* the CUDA stream everything is queued on (cudaStream_t as void*), for callers that produce input on the device */
+void *nvx_engine_stream(nvx_engine *e);
+
+/* host-only helper (no GPU needed): run the line / ZCZC / NNNN / abort assembly of nav_b_sm.C:44-97 over one
+ * channel's event bytes; calls cb once per completed message and returns their number */
+int nvx_host_assemble(const unsigned char *events, size_t n, int stream, int freq, nvx_message_cb cb, void *user);
+
+/* ---- synthetic captures on the device (bench / tests): SITOR-B FSK + AWGN, int16-valued float2 - */
+typedef struct {
+    const uint8_t *bits;        /* host: concatenated per-stream bit strings (1 = 'Y'), 100 baud */
+    const long long *bit_off;   /* host: [S+1] offsets into bits */
+    const float *offset_hz;     /* host: [S] channel offset (+14000 / -14000) */
+    const float *start_s;       /* host: [S] emission start time */
+    const float *amplitude;     /* host: [S] */
+    const float *noise_sigma;   /* host: [S] per-component AWGN sigma (0 = none) */
+    unsigned long long seed;
+} nvx_synth_desc;
+/* fill d_iq ([S][n] float2, device) with samples [t0, t0+n) of every stream's capture */
+int nvx_synth_fill_device(int device, const nvx_synth_desc *d, int n_streams, long long t0, long long n,
+                          void *d_iq, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,523 @@
+// engine.cu -- the C ABI of include/navtex_b200.h: per-GPU engine that owns the carried state of
+// S independent streams and queues, per pushed block, the fused FIR cascade, the tail carry, the
+// demod/bit-sync/FSM kernel and the event download; host side it runs the message assembler.
+//
+// Call contract it replaces: capt_sched.c:552-555 (init_dsp), :612 (init_fir2_wrapper) and the
+// consumer loop :484-528 that calls sample_in_1 once per IQ pair.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/navtex_b200.h"
+#include "demod.cuh"
+#include "fir_cascade.cuh"
+#include "message_assembler.h"
+
+namespace nvx {
+size_t cascade_smem_bytes();
+cudaError_t cascade_upload_constants(const double* h1, const double* h2, const double* h3, cudaStream_t stream);
+cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, cudaStream_t stream);
+int cascade_target_warps(int device);
+}  // namespace nvx
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(NVX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int load_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(NVX_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
+}
+
+// float32 view [rows][2 * cols] of a stream-major float2 array; box = one step (56 floats) x 32 rows
+int encode_rows(CUtensorMap* map, const void* base, long long cols, long long rows) {
+    if (int rc = load_encode()) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)(2 * cols), (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(cols * 8)};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * nvx::kStepIn), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NVX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%lld rows=%lld", (int)r, cols, rows);
+    return 0;
+}
+
+// new_tail[s] = last kHalo samples of (old_tail[s] ++ x[s][0..n))
+__global__ void tail_carry_kernel(const float2* __restrict__ old_tail, const float2* __restrict__ x, float2* __restrict__ new_tail,
+                                  int streams, long long n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 = 2 samples
+    const long long per = nvx::kHalo / 2;
+    if (idx >= per * streams) return;
+    const int s = (int)(idx / per);
+    const long long k = (idx % per) * 2;
+    const long long p = n - nvx::kHalo + k;                                      // n and kHalo are even
+    const float4* src = p >= 0 ? reinterpret_cast<const float4*>(x + (size_t)s * n + p)
+                               : reinterpret_cast<const float4*>(old_tail + (size_t)s * nvx::kHalo + (nvx::kHalo + p));
+    *reinterpret_cast<float4*>(new_tail + (size_t)s * nvx::kHalo + k) = *src;
+}
+
+// interleaved int16 I,Q -> float2, the (double)short of capt_sched.c:511 (exact in float)
+__global__ void s16_to_f32_kernel(const short2* __restrict__ in, float2* __restrict__ out, long long count) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < count; i += stride) {
+        const int4 v = *reinterpret_cast<const int4*>(in + i);                   // 4 IQ pairs
+        const short2 a = *reinterpret_cast<const short2*>(&v.x), b = *reinterpret_cast<const short2*>(&v.y);
+        const short2 c = *reinterpret_cast<const short2*>(&v.z), d = *reinterpret_cast<const short2*>(&v.w);
+        float4* o = reinterpret_cast<float4*>(out + i);
+        o[0] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+        o[1] = make_float4((float)c.x, (float)c.y, (float)d.x, (float)d.y);
+    }
+}
+
+}  // namespace
+
+struct nvx_engine {
+    nvx_config cfg;
+    int S = 0, P_max = 0, channels = 0;
+    cudaStream_t stream = nullptr;
+    float2* tail[2] = {nullptr, nullptr};
+    CUtensorMap map_tail[2];
+    int tail_cur = 0;
+    float2* y3 = nullptr;
+    nvx::ChannelState* chstate = nullptr;
+    uint8_t* d_events = nullptr; int* d_ev_count = nullptr; int ev_cap = 0;
+    char* d_bits = nullptr; float* d_disc = nullptr; int* d_bit_count = nullptr; int bit_cap = 0;
+    uint8_t* h_events = nullptr; int* h_ev_count = nullptr;
+    float2* stage_f32 = nullptr; size_t stage_f32_samples = 0;
+    short2* stage_s16 = nullptr; size_t stage_s16_samples = 0;
+    long long sb_abs = 0;
+    int last_P = 0;
+    bool events_pending = false, custom_taps = false;
+    int target_warps = 1184;
+    nvx::MessageAssembler assembler;
+    std::vector<nvx::AssembledMessage> ready, handed;
+    std::vector<nvx_message> view;
+    nvx_message_cb cb = nullptr; void* cb_user = nullptr;
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Span { int a, b, kind; };
+    std::vector<Span> spans;
+    size_t ev_used = 0;
+    nvx_stats stats = {};
+};
+
+namespace {
+
+int free_engine(nvx_engine* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->y3); cudaFree(e->chstate);
+    cudaFree(e->d_events); cudaFree(e->d_ev_count); cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
+    cudaFree(e->stage_f32); cudaFree(e->stage_s16);
+    cudaFreeHost(e->h_events); cudaFreeHost(e->h_ev_count);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+int reset_state(nvx_engine* e) {
+    CU_TRY(cudaMemsetAsync(e->tail[0], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
+    CU_TRY(cudaMemsetAsync(e->tail[1], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
+    CU_TRY(nvx::demod_init_state(e->chstate, e->channels, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->tail_cur = 0;
+    e->sb_abs = 0;
+    e->last_P = 0;
+    e->events_pending = false;
+    e->assembler.reset();
+    e->ready.clear();
+    return 0;
+}
+
+cudaEvent_t next_event(nvx_engine* e) {
+    if (e->ev_used == e->ev_pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->ev_pool.push_back(ev);
+    }
+    return e->ev_pool[e->ev_used++];
+}
+
+// host half: run after the stream is idle
+int drain_events(nvx_engine* e) {
+    if (e->timing && !e->spans.empty()) {
+        for (const auto& sp : e->spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e->ev_pool[sp.a], e->ev_pool[sp.b]);
+            if (sp.kind == 0) e->stats.cascade_ms += ms; else e->stats.demod_ms += ms;
+        }
+        e->spans.clear();
+        e->ev_used = 0;
+    }
+    if (!e->events_pending) return 0;
+    e->events_pending = false;
+    int rc = 0;
+    for (int ch = 0; ch < e->channels; ++ch) {
+        int n = e->h_ev_count[ch];
+        if (n > e->ev_cap) { n = e->ev_cap; rc = fail(NVX_ERR_OVERFLOW, "event buffer overflow on channel %d", ch); }
+        if (n > 0)
+            e->assembler.feed(ch, e->cfg.first_stream_id + ch / 2, e->cfg.freq_tag[ch & 1], e->h_events + (size_t)ch * e->ev_cap,
+                              (size_t)n, &e->ready);
+    }
+    if (e->cb) {
+        for (auto& m : e->ready) {
+            std::string b = m.bbbb, t = m.text;
+            e->cb(e->cb_user, m.stream, &b[0], &t[0], m.freq);
+        }
+        e->ready.clear();
+    }
+    return rc;
+}
+
+int sync_engine(nvx_engine* e) {
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return drain_events(e);
+}
+
+int process_block(nvx_engine* e, const float2* d_x, long long n) {
+    using namespace nvx;
+    if (n <= 0 || n % kSuper != 0) return fail(NVX_ERR_ARG, "block length %lld is not a positive multiple of %d", n, kSuper);
+    if (n > e->cfg.max_block) return fail(NVX_ERR_ARG, "block length %lld exceeds max_block %lld", n, e->cfg.max_block);
+    if (((uintptr_t)d_x & 15) != 0) return fail(NVX_ERR_ARG, "device block is not 16-byte aligned");
+    if (e->events_pending) {
+        int rc = sync_engine(e);
+        if (rc && rc != NVX_ERR_OVERFLOW) return rc;
+    }
+    CascadeArgs ca;
+    if (int rc = encode_rows(&ca.map_x, d_x, n, e->S)) return rc;
+    ca.map_tail = e->map_tail[e->tail_cur];
+    const int n_super = (int)(n / kSuper);
+    const int groups = (e->S + 31) / 32;
+    // time segments: enough warps to fill the machine once, but keep the 7-superblock warm-up small
+    int segs = (e->target_warps + groups / 2) / groups;
+    const int min_seg = 63;
+    if (segs > n_super / min_seg) segs = n_super / min_seg;
+    if (segs < 1) segs = 1;
+    const int seg_super = (n_super + segs - 1) / segs;
+    segs = (n_super + seg_super - 1) / seg_super;
+    ca.y3 = e->y3;
+    ca.n = n;
+    ca.streams = e->S;
+    ca.segs = segs;
+    ca.seg_super = seg_super;
+    ca.n_super = n_super;
+    ca.sb_phase = (int)(e->sb_abs % kNcoPeriod);
+    ca.y3_pitch = e->P_max;
+    ca.y3_off = 0;
+
+    cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
+    if (e->timing) {
+        const int base = (int)e->ev_used;
+        t0 = next_event(e); t1 = next_event(e); t2 = next_event(e); t3 = next_event(e);
+        e->spans.push_back({base, base + 1, 0});
+        e->spans.push_back({base + 2, base + 3, 1});
+        CU_TRY(cudaEventRecord(t0, e->stream));
+    }
+    CU_TRY(cascade_launch(ca, e->custom_taps, e->stream));
+    if (e->timing) CU_TRY(cudaEventRecord(t1, e->stream));
+
+    const int nxt = e->tail_cur ^ 1;
+    {
+        const long long work = (long long)e->S * (kHalo / 2);
+        tail_carry_kernel<<<(unsigned)((work + 255) / 256), 256, 0, e->stream>>>(e->tail[e->tail_cur], d_x, e->tail[nxt], e->S, n);
+        CU_TRY(cudaGetLastError());
+    }
+    e->tail_cur = nxt;
+
+    DemodArgs da;
+    da.y3 = e->y3; da.y3_pitch = e->P_max; da.y3_off = 0;
+    da.n_new = n_super; da.channels = e->channels; da.state = e->chstate;
+    da.events = e->d_events; da.ev_count = e->d_ev_count; da.ev_cap = e->ev_cap;
+    da.bits = e->d_bits; da.disc = e->d_disc; da.bit_count = e->d_bit_count; da.bit_cap = e->bit_cap;
+    if (e->timing) CU_TRY(cudaEventRecord(t2, e->stream));
+    CU_TRY(demod_launch(da, e->stream));
+    if (e->timing) CU_TRY(cudaEventRecord(t3, e->stream));
+
+    CU_TRY(cudaMemcpyAsync(e->h_ev_count, e->d_ev_count, sizeof(int) * e->channels, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->h_events, e->d_events, (size_t)e->channels * e->ev_cap, cudaMemcpyDeviceToHost, e->stream));
+    e->events_pending = true;
+    e->sb_abs += n_super;
+    e->last_P = n_super;
+    e->stats.cascade_launches++;
+    e->stats.demod_launches++;
+    e->stats.aux_launches++;
+    e->stats.samples += n * e->S;
+    return 0;
+}
+
+int ensure_stage_f32(nvx_engine* e, size_t samples) {
+    if (e->stage_f32_samples >= samples) return 0;
+    cudaFree(e->stage_f32);
+    e->stage_f32 = nullptr; e->stage_f32_samples = 0;
+    CU_TRY(cudaMalloc(&e->stage_f32, samples * sizeof(float2)));
+    e->stage_f32_samples = samples;
+    return 0;
+}
+int ensure_stage_s16(nvx_engine* e, size_t samples) {
+    if (e->stage_s16_samples >= samples) return 0;
+    cudaFree(e->stage_s16);
+    e->stage_s16 = nullptr; e->stage_s16_samples = 0;
+    CU_TRY(cudaMalloc(&e->stage_s16, samples * sizeof(short2)));
+    e->stage_s16_samples = samples;
+    return 0;
+}
+
+int convert_and_process(nvx_engine* e, const short2* d_in, long long n) {
+    const size_t total = (size_t)e->S * (size_t)n;
+    if (int rc = ensure_stage_f32(e, total)) return rc;
+    s16_to_f32_kernel<<<148 * 8, 256, 0, e->stream>>>(d_in, e->stage_f32, (long long)total);
+    CU_TRY(cudaGetLastError());
+    e->stats.aux_launches++;
+    return process_block(e, e->stage_f32, n);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nvx_last_error(void) { return g_err; }
+
+void nvx_default_config(nvx_config* cfg) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->n_streams = 1;
+    cfg->max_block = 252000;
+    cfg->freq_tag[0] = 518;   // nav_sched.C:10-11
+    cfg->freq_tag[1] = 490;
+}
+
+int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
+    if (!cfg || !out) return fail(NVX_ERR_ARG, "null argument");
+    if (cfg->n_streams <= 0 || cfg->max_block <= 0 || cfg->max_block % nvx::kSuper != 0)
+        return fail(NVX_ERR_ARG, "n_streams must be > 0 and max_block a positive multiple of %d", nvx::kSuper);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+        return fail(NVX_ERR_CUDA, "no usable CUDA device %d (%d visible): this library has no CPU path", cfg->device, ndev);
+    CU_TRY(cudaSetDevice(cfg->device));
+    nvx_engine* e = new nvx_engine();
+    e->cfg = *cfg;
+    if (e->cfg.freq_tag[0] == 0 && e->cfg.freq_tag[1] == 0) { e->cfg.freq_tag[0] = 518; e->cfg.freq_tag[1] = 490; }
+    e->cfg.h1 = e->cfg.h2 = e->cfg.h3 = nullptr;    // copied to the device below, not retained
+    e->S = cfg->n_streams;
+    e->channels = 2 * e->S;
+    e->P_max = (int)(cfg->max_block / nvx::kSuper);
+    e->custom_taps = cfg->h1 || cfg->h2 || cfg->h3;
+    // per block and channel: at most one character plus one abort per 14 bits ... generous bound
+    e->ev_cap = 2 * (e->P_max / 63 + 2) + 8;
+    e->bit_cap = cfg->keep_bits ? e->P_max / 9 + 2 : 0;
+#define CREATE_TRY(expr)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            fail(NVX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));                              \
+            free_engine(e);                                                                                   \
+            return e__ == cudaErrorMemoryAllocation ? NVX_ERR_NOMEM : NVX_ERR_CUDA;                           \
+        }                                                                                                     \
+    } while (0)
+    CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const size_t tail_bytes = (size_t)e->S * nvx::kHalo * sizeof(float2);
+    CREATE_TRY(cudaMalloc(&e->tail[0], tail_bytes));
+    CREATE_TRY(cudaMalloc(&e->tail[1], tail_bytes));
+    CREATE_TRY(cudaMalloc(&e->y3, (size_t)e->channels * e->P_max * sizeof(float2)));
+    CREATE_TRY(cudaMalloc(&e->chstate, (size_t)e->channels * sizeof(nvx::ChannelState)));
+    CREATE_TRY(cudaMalloc(&e->d_events, (size_t)e->channels * e->ev_cap));
+    CREATE_TRY(cudaMalloc(&e->d_ev_count, sizeof(int) * e->channels));
+    CREATE_TRY(cudaMemset(e->d_ev_count, 0, sizeof(int) * e->channels));
+    if (cfg->keep_bits) {
+        CREATE_TRY(cudaMalloc(&e->d_bits, (size_t)e->channels * e->bit_cap));
+        CREATE_TRY(cudaMalloc(&e->d_disc, (size_t)e->channels * e->bit_cap * 4 * sizeof(float)));
+        CREATE_TRY(cudaMalloc(&e->d_bit_count, sizeof(int) * e->channels));
+        CREATE_TRY(cudaMemset(e->d_bit_count, 0, sizeof(int) * e->channels));
+    }
+    CREATE_TRY(cudaMallocHost(&e->h_events, (size_t)e->channels * e->ev_cap));
+    CREATE_TRY(cudaMallocHost(&e->h_ev_count, sizeof(int) * e->channels));
+    CREATE_TRY(nvx::cascade_upload_constants(cfg->h1, cfg->h2, cfg->h3, e->stream));
+#undef CREATE_TRY
+    for (int k = 0; k < 2; ++k)
+        if (int rc = encode_rows(&e->map_tail[k], e->tail[k], nvx::kHalo, e->S)) { free_engine(e); return rc; }
+    e->target_warps = nvx::cascade_target_warps(cfg->device);
+    e->assembler.resize(e->channels);
+    if (int rc = reset_state(e)) { free_engine(e); return rc; }
+    *out = e;
+    return 0;
+}
+
+void nvx_engine_destroy(nvx_engine* e) { free_engine(e); }
+
+int nvx_engine_reset(nvx_engine* e) {
+    if (!e) return fail(NVX_ERR_ARG, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return reset_state(e);
+}
+
+int nvx_engine_push_device_f32(nvx_engine* e, const void* d_iq, long long n) {
+    if (!e || !d_iq) return fail(NVX_ERR_ARG, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    return process_block(e, static_cast<const float2*>(d_iq), n);
+}
+
+int nvx_engine_push_device_s16(nvx_engine* e, const void* d_iq, long long n) {
+    if (!e || !d_iq) return fail(NVX_ERR_ARG, "null argument");
+    if (((uintptr_t)d_iq & 15) != 0) return fail(NVX_ERR_ARG, "device block is not 16-byte aligned");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    return convert_and_process(e, static_cast<const short2*>(d_iq), n);
+}
+
+int nvx_engine_push_host_f32(nvx_engine* e, const float* iq, long long n) {
+    if (!e || !iq) return fail(NVX_ERR_ARG, "null argument");
+    if (n <= 0 || n % nvx::kSuper != 0 || n > e->cfg.max_block) return fail(NVX_ERR_ARG, "bad block length %lld", n);
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const size_t total = (size_t)e->S * (size_t)n;
+    if (int rc = ensure_stage_f32(e, total)) return rc;
+    CU_TRY(cudaMemcpyAsync(e->stage_f32, iq, total * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+    return process_block(e, e->stage_f32, n);
+}
+
+int nvx_engine_push_host_s16(nvx_engine* e, const int16_t* iq, long long n) {
+    if (!e || !iq) return fail(NVX_ERR_ARG, "null argument");
+    if (n <= 0 || n % nvx::kSuper != 0 || n > e->cfg.max_block) return fail(NVX_ERR_ARG, "bad block length %lld", n);
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const size_t total = (size_t)e->S * (size_t)n;
+    if (int rc = ensure_stage_s16(e, total)) return rc;
+    CU_TRY(cudaMemcpyAsync(e->stage_s16, iq, total * sizeof(short2), cudaMemcpyHostToDevice, e->stream));
+    return convert_and_process(e, e->stage_s16, n);
+}
+
+int nvx_engine_sync(nvx_engine* e) {
+    if (!e) return fail(NVX_ERR_ARG, "null engine");
+    return sync_engine(e);
+}
+
+int nvx_engine_poll_messages(nvx_engine* e, const nvx_message** msgs, size_t* count) {
+    if (!e || !msgs || !count) return fail(NVX_ERR_ARG, "null argument");
+    int rc = sync_engine(e);
+    e->handed.swap(e->ready);
+    e->ready.clear();
+    e->view.clear();
+    for (const auto& m : e->handed) {
+        nvx_message v;
+        v.stream = m.stream; v.freq = m.freq;
+        memset(v.bbbb, 0, sizeof v.bbbb);
+        strncpy(v.bbbb, m.bbbb.c_str(), sizeof v.bbbb - 1);
+        v.text = m.text.c_str(); v.text_len = m.text.size();
+        e->view.push_back(v);
+    }
+    *msgs = e->view.data();
+    *count = e->view.size();
+    return rc;
+}
+
+int nvx_engine_set_message_callback(nvx_engine* e, nvx_message_cb cb, void* user) {
+    if (!e) return fail(NVX_ERR_ARG, "null engine");
+    e->cb = cb; e->cb_user = user;
+    return 0;
+}
+
+int nvx_engine_read_y3(nvx_engine* e, float* out, size_t cap_floats, size_t* n_per_channel) {
+    if (!e || !out || !n_per_channel) return fail(NVX_ERR_ARG, "null argument");
+    int rc = sync_engine(e);
+    const size_t P = (size_t)e->last_P;
+    *n_per_channel = P;
+    if (cap_floats < (size_t)e->channels * P * 2) return fail(NVX_ERR_ARG, "y3 buffer too small");
+    if (P)
+        CU_TRY(cudaMemcpy2D(out, P * sizeof(float2), e->y3, (size_t)e->P_max * sizeof(float2), P * sizeof(float2), (size_t)e->channels,
+                            cudaMemcpyDeviceToHost));
+    return rc;
+}
+
+int nvx_engine_read_bits(nvx_engine* e, int stream, int ch, char* bits, float* sums, size_t cap, size_t* count) {
+    if (!e || !bits || !count || stream < 0 || stream >= e->S || ch < 0 || ch > 1) return fail(NVX_ERR_ARG, "bad argument");
+    if (!e->d_bits) return fail(NVX_ERR_ARG, "engine was created without keep_bits");
+    int rc = sync_engine(e);
+    const int c = stream * 2 + ch;
+    int n = 0;
+    CU_TRY(cudaMemcpy(&n, e->d_bit_count + c, sizeof n, cudaMemcpyDeviceToHost));
+    if (n > e->bit_cap) { n = e->bit_cap; rc = fail(NVX_ERR_OVERFLOW, "bit buffer overflow"); }
+    if ((size_t)n > cap) return fail(NVX_ERR_ARG, "bit buffer too small (%d needed)", n);
+    *count = (size_t)n;
+    if (n) {
+        CU_TRY(cudaMemcpy(bits, e->d_bits + (size_t)c * e->bit_cap, (size_t)n, cudaMemcpyDeviceToHost));
+        if (sums) CU_TRY(cudaMemcpy(sums, e->d_disc + (size_t)c * e->bit_cap * 4, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return rc;
+}
+
+int nvx_engine_read_events(nvx_engine* e, int stream, int ch, char* ev, size_t cap, size_t* count) {
+    if (!e || !ev || !count || stream < 0 || stream >= e->S || ch < 0 || ch > 1) return fail(NVX_ERR_ARG, "bad argument");
+    int rc = sync_engine(e);
+    const int c = stream * 2 + ch;
+    int n = e->h_ev_count[c];
+    if (n > e->ev_cap) n = e->ev_cap;
+    if ((size_t)n > cap) return fail(NVX_ERR_ARG, "event buffer too small (%d needed)", n);
+    memcpy(ev, e->h_events + (size_t)c * e->ev_cap, (size_t)n);
+    *count = (size_t)n;
+    return rc;
+}
+
+int nvx_engine_enable_timing(nvx_engine* e, int on) {
+    if (!e) return fail(NVX_ERR_ARG, "null engine");
+    int rc = sync_engine(e);
+    e->timing = on != 0;
+    return rc;
+}
+
+int nvx_engine_get_stats(nvx_engine* e, nvx_stats* out, int reset) {
+    if (!e || !out) return fail(NVX_ERR_ARG, "null argument");
+    int rc = sync_engine(e);
+    *out = e->stats;
+    if (reset) e->stats = nvx_stats{};
+    return rc;
+}
+
+void* nvx_engine_stream(nvx_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int nvx_host_assemble(const unsigned char* events, size_t n, int stream, int freq, nvx_message_cb cb, void* user) {
+    if ((!events && n) || !cb) return fail(NVX_ERR_ARG, "null argument");
+    nvx::MessageAssembler as;
+    as.resize(1);
+    std::vector<nvx::AssembledMessage> out;
+    as.feed(0, stream, freq, events, n, &out);
+    for (auto& m : out) {
+        std::string b = m.bbbb, t = m.text;
+        cb(user, m.stream, &b[0], &t[0], m.freq);
+    }
+    return (int)out.size();
+}
+
+}  // extern "C"

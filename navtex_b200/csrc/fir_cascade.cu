@@ -1,0 +1,159 @@
+// fir_cascade.cu -- kernel + launcher for the fused FIR cascade (see fir_cascade.cuh).
+#define NVX_CASCADE_DEVICE_CODE
+#include "fir_cascade.cuh"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace nvx {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kStages = 3;
+
+template <bool kImm>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* const wbase = smem + (size_t)warp * (kStages * kStageBytes);
+    const uint32_t wbase_s = smem_u32(wbase);
+    const uint32_t bar0 = smem_u32(smem + (size_t)kWarpsPerCta * kStages * kStageBytes) + warp * kStages * 8;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // warp -> (group of 32 consecutive streams, time segment); lane -> stream inside the group
+    const int groups = (a.streams + 31) >> 5;
+    const long long wg = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (wg >= (long long)groups * a.segs) return;
+    const int seg = (int)(wg / groups);
+    const int strm0 = (int)(wg % groups) * 32;
+    const int strm = strm0 + lane;
+    const int first_sb = seg * a.seg_super;
+    int my_super = a.n_super - first_sb;
+    my_super = my_super > a.seg_super ? a.seg_super : my_super;
+    if (strm >= a.streams) my_super = 0;          // padding lanes compute on TMA zero fill, store nothing
+
+    const int warp_steps = (kWarmSuper + a.seg_super) * kStepsPerSuper;
+    // first input sample of this segment's warm-up, relative to the chunk start (negative = carried tail)
+    const long long pos0 = ((long long)first_sb - kWarmSuper) * kSuper;
+
+    auto issue = [&](int t, int stage) {
+        if (lane == 0) {
+            const uint32_t bar = bar0 + 8 * stage;
+            const long long p = pos0 + (long long)t * kStepIn;
+            mbar_arrive_expect_tx(bar, kStageBytes);
+            if (p < 0) tma_load_2d(wbase_s + stage * kStageBytes, &a.map_tail, (int)(2 * (p + kHalo)), strm0, bar);
+            else       tma_load_2d(wbase_s + stage * kStageBytes, &a.map_x, (int)(2 * p), strm0, bar);
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+        if (s < warp_steps) issue(s, s);
+
+    CascadeState st;
+#pragma unroll
+    for (int j = 0; j < kLive1; ++j) st.a1[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int j = 0; j < kLive2; ++j) st.a2[c][j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kLive3; ++j) st.a3[c][j] = make_float2(0.f, 0.f);
+    }
+
+    // NCO phase of the first stage-1 output of a step: (70 sb_abs + 7 r10) mod 9, sb_abs = absolute
+    // superblock index; identical for every lane (same time position, all streams share the chunk clock).
+    int phase = (7 * ((a.sb_phase + first_sb + 9 * kWarmSuper - kWarmSuper) % kNcoPeriod)) % kNcoPeriod;
+    int stage = 0;
+    uint32_t parity = 0;
+    float2* const y3row = a.y3 + (size_t)strm * 2 * a.y3_pitch + a.y3_off + first_sb;
+
+    float2 y3[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    int r10 = 0, out = -kWarmSuper;
+    for (int t = 0; t < warp_steps; ++t) {
+        mbar_wait(bar0 + 8 * stage, parity);
+        const float4* rowp = reinterpret_cast<const float4*>(wbase + stage * kStageBytes + lane * kRowBytes);
+        cascade_step<kImm>(st, rowp, phase, r10, y3);
+        __syncwarp();
+        if (t + kStages < warp_steps) issue(t + kStages, stage);
+        if (++stage == kStages) { stage = 0; parity ^= 1; }
+        phase += 7;
+        if (phase >= kNcoPeriod) phase -= kNcoPeriod;
+        if (++r10 == kStepsPerSuper) {
+            r10 = 0;
+            if (out >= 0 && out < my_super) {
+                y3row[out] = y3[0];
+                y3row[a.y3_pitch + out] = y3[1];
+            }
+            ++out;
+        }
+    }
+}
+
+size_t cascade_smem_bytes() { return (size_t)kWarpsPerCta * kStages * kStageBytes + kWarpsPerCta * kStages * 8; }
+
+static void fill_constants(const double* h1, const double* h2, const double* h3, TapSet* t, NcoTable* n) {
+    static const double d1[NVX_T1] = {NVX_H1_VALUES};
+    static const double d2[NVX_T2] = {NVX_H2_VALUES};
+    static const double d3[NVX_T3] = {NVX_H3_VALUES};
+    if (!h1) h1 = d1;
+    if (!h2) h2 = d2;
+    if (!h3) h3 = d3;
+    for (int i = 0; i < NVX_T1; ++i) t->h1[i] = (float)h1[i];
+    for (int i = 0; i < NVX_T2; ++i) t->h2[i] = (float)h2[i];
+    for (int r = 0; r < NVX_D3; ++r)
+        for (int j = 0; j < 8; ++j) {
+            const int i = 10 * j + 9 - r;
+            t->h3t[r][j] = i < NVX_T3 ? (float)h3[i] : 0.f;
+        }
+    for (int i = 0; i < kNcoPeriod + NVX_D2; ++i) {
+        const int k = i % kNcoPeriod;
+        // same expression as fir2cpp.C:105-106, rounded once to float
+        n->w[i].x = (float)cos((2 * M_PI * k * 14000) / 63000);
+        n->w[i].y = (float)-sin((2 * M_PI * k * 14000) / 63000);
+    }
+}
+
+cudaError_t cascade_upload_constants(const double* h1, const double* h2, const double* h3, cudaStream_t stream) {
+    TapSet t = {};
+    NcoTable n = {};
+    fill_constants(h1, h2, h3, &t, &n);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_taps, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbolAsync(c_nco, &n, sizeof n, 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(stream);
+}
+
+// warps that are resident at once across the device: the host sizes the grid to one full wave
+int cascade_target_warps(int device) {
+    int sms = 148, per_sm = 2;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaFuncSetAttribute(fir_cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cascade_smem_bytes());
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_cascade_kernel<true>, kWarpsPerCta * 32,
+                                                      cascade_smem_bytes()) != cudaSuccess || per_sm < 1)
+        per_sm = 2;
+    return sms * per_sm * kWarpsPerCta;
+}
+
+cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, cudaStream_t stream) {
+    static bool attr_set[2] = {false, false};
+    const size_t smem = cascade_smem_bytes();
+    auto kern = custom_taps ? fir_cascade_kernel<false> : fir_cascade_kernel<true>;
+    if (!attr_set[custom_taps]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set[custom_taps] = true;
+    }
+    const long long warps = (long long)((a.streams + 31) / 32) * a.segs;
+    const unsigned grid = (unsigned)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
+    kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace nvx

@@ -1,0 +1,186 @@
+// fir_cascade.cuh -- fused stage-1 FIR (/4) -> NCO mix (two channels) -> stage-2 FIR (/7) ->
+// stage-3 FIR (/10) for batches of independent IQ streams, sm_100a.
+//
+// Replaces, for [streams x samples] at once, the reference's per-sample push chain
+//   sample_in_1   receiver/fir1cpp.C:80-136   (37 taps, /4)
+//   sample_in_2   receiver/fir2cpp.C:112-128  (mix by e^{-+j 2 pi k 2/9})
+//   fir_in_2 / fir_in_2_490   fir2cpp.C:131-215 (47 taps, /7, per channel)
+//   fir_filter3::sample_in    fir3cpp.C:22-60   (71 taps, /10, per channel)
+// and emits the 900 Hz complex samples that decoder::sample_in (decoder.C:42) consumes.
+//
+// Mapping (B200-first, not the reference's ring buffers):
+//   * one THREAD owns one (stream, time-segment) "row"; a warp is 32 rows.  Every FIR stage
+//     runs in transposed (scatter) polyphase form: an arriving sample is multiply-added into
+//     the few output accumulators it belongs to, so the whole cascade state is 9 + 2*6 + 2*7
+//     complex partial sums in registers and no intermediate (63 kHz, 9 kHz) sample ever
+//     touches shared memory or HBM.
+//   * I and Q ride in one 64-bit register pair and every tap is one FFMA2 (fma.rn.f32x2) with
+//     the tap as a 32-bit immediate / uniform operand: 2 FMAs per lane per issue slot.
+//   * a warp's 32 rows are 32 consecutive streams at the same time segment, so the 28 samples
+//     each of them needs for one step form a [32 streams x 224 B] box of the stream-major
+//     input: ONE TMA tensor copy (cp.async.bulk.tensor.2d -> UTMALDG) per warp per step into
+//     a per-warp ring of shared-memory stages, completion tracked by one mbarrier per stage.
+//     Each lane then reads its own 224-byte row with LDS.128.
+//   * time segments are made independent by recomputing a 7-superblock (1960-sample) warm-up
+//     from the raw input that precedes the segment (previous segment, or the carried tail of
+//     the previous chunk); since every 900 Hz output depends on exactly 2181 inputs
+//      the results are bit-identical to an unsegmented pass.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/navtex_taps.h"
+
+namespace nvx {
+
+constexpr int kSuper = NVX_D1 * NVX_D2 * NVX_D3;   // 280 inputs per 900 Hz output
+constexpr int kStepIn = NVX_D1 * NVX_D2;           // 28 inputs per 9 kHz output ("step")
+constexpr int kStepsPerSuper = NVX_D3;             // 10
+constexpr int kWarmSuper = 7;                      // ceil(1901 / 280)
+constexpr int kHalo = kWarmSuper * kSuper;         // 1960 carried input samples per stream
+constexpr int kNcoPeriod = 9;                      // fir2cpp.C:12-14
+constexpr int kRowBytes = kStepIn * 8;             // 224 (the TMA box is dense: row pitch = row bytes)
+constexpr int kStageBytes = 32 * kRowBytes;        // 7168 per warp per stage
+constexpr int kLive1 = 9, kLive2 = 6, kLive3 = 8;  // partial sums carried between steps
+
+__device__ constexpr double kH1[NVX_T1] = {NVX_H1_VALUES};
+__device__ constexpr double kH2[NVX_T2] = {NVX_H2_VALUES};
+
+// runtime tap sets of the reference lengths (constant bank, uniform operands)
+struct TapSet {
+    float h1[NVX_T1 + 3];
+    float h2[NVX_T2 + 1];
+    // stage-3 taps regrouped per step position: h3t[r][j] = h3[10 j + 9 - r] (0 where that index is > 70),
+    // so the 8 taps one step needs are two aligned 16-byte uniform loads
+    float h3t[NVX_D3][8];
+};
+// (cos, -sin) of 2 pi k 14000 / 63000, k = 0..8, repeated so that [phase + q], q < 7 needs no wrap
+struct NcoTable { float2 w[kNcoPeriod + NVX_D2]; };
+
+
+struct CascadeArgs {
+    CUtensorMap map_x;    // float32 view [S][2 n] of this chunk (stream-major IQ), box 56 x 32
+    CUtensorMap map_tail; // float32 view [S][2 kHalo]: the kHalo samples that preceded the chunk (zeros at start)
+    float2* y3;           // [S][2][y3_pitch] 900 Hz output; this chunk's samples start at y3_off
+    long long n;          // samples per stream in this chunk (multiple of kSuper)
+    int streams;
+    int segs;             // time segments per stream
+    int seg_super;        // superblocks per segment (last one may be short)
+    int n_super;          // n / kSuper
+    int sb_phase;         // (absolute superblock index of chunk start) mod 9
+    long long y3_pitch;
+    long long y3_off;
+};
+
+#ifdef NVX_CASCADE_DEVICE_CODE
+__constant__ TapSet c_taps;
+__constant__ NcoTable c_nco;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <bool kImm> __device__ __forceinline__ float tap1(int i) { return kImm ? (float)kH1[i] : c_taps.h1[i]; }
+template <bool kImm> __device__ __forceinline__ float tap2(int i) { return kImm ? (float)kH2[i] : c_taps.h2[i]; }
+
+__device__ __forceinline__ float2 fma2(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+
+struct CascadeState {
+    float2 a1[kLive1];
+    float2 a2[2][kLive2];
+    float2 a3[2][kLive3];
+};
+
+// One step: 28 inputs of one row -> 7 stage-1 outputs -> mix -> one stage-2 output per channel ->
+// scattered into the stage-3 partial sums.  r10 = position of this step inside its superblock.
+// y3 is written when r10 == 9 completed a 900 Hz sample.
+template <bool kImm>
+__device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __restrict__ row, int nco_phase,
+                                             const int r10, float2 (&y3)[2]) {
+    float2 w[kLive1 + NVX_D2];
+#pragma unroll
+    for (int j = 0; j < kLive1; ++j) w[j] = st.a1[j];
+#pragma unroll
+    for (int j = kLive1; j < kLive1 + NVX_D2; ++j) w[j] = make_float2(0.f, 0.f);
+
+    float2 b[2][kLive2 + 1];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int j = 0; j < kLive2; ++j) b[c][j] = st.a2[c][j];
+        b[c][kLive2] = make_float2(0.f, 0.f);
+    }
+
+#pragma unroll
+    for (int q = 0; q < NVX_D2; ++q) {
+        // four inputs complete stage-1 output q of this step
+        const float4 v0 = row[2 * q], v1 = row[2 * q + 1];
+        const float2 xs[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y),
+                              make_float2(v1.z, v1.w)};
+#pragma unroll
+        for (int r = 0; r < NVX_D1; ++r) {
+#pragma unroll
+            for (int j = 0; 4 * j + 3 - r < NVX_T1; ++j) w[q + j] = fma2(xs[r], tap1<kImm>(4 * j + 3 - r), w[q + j]);
+        }
+        const float2 y1 = w[q];
+        // NCO mix (fir2cpp.C:115-124): ch0 = y1 * (re + j im), ch1 = y1 * (re - j im), (re, im) = (cos, -sin)
+        const float2 rot = c_nco.w[nco_phase + q];
+        const float ar = y1.x * rot.x, br = y1.y * rot.x;
+        float2 m[2];
+        m[0] = make_float2(fmaf(-y1.y, rot.y, ar), fmaf(y1.x, rot.y, br));
+        m[1] = make_float2(fmaf(y1.y, rot.y, ar), fmaf(-y1.x, rot.y, br));
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int j = 0; 7 * j + 6 - q < NVX_T2; ++j) b[c][j] = fma2(m[c], tap2<kImm>(7 * j + 6 - q), b[c][j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kLive1; ++j) st.a1[j] = w[j + NVX_D2];
+
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float2 y2 = b[c][0];
+#pragma unroll
+        for (int j = 0; j < kLive2; ++j) st.a2[c][j] = b[c][j + 1];
+        // stage 3: sample 10p + r10 feeds outputs p + j with tap 10 j + 9 - r10 (table row r10; j = 7 only
+        // carries a non-zero tap when r10 == 9)
+#pragma unroll
+        for (int j = 0; j < kLive3; ++j) st.a3[c][j] = fma2(y2, c_taps.h3t[r10][j], st.a3[c][j]);
+    }
+    if (r10 == NVX_D3 - 1) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            y3[c] = st.a3[c][0];
+#pragma unroll
+            for (int j = 1; j < kLive3; ++j) st.a3[c][j - 1] = st.a3[c][j];
+            st.a3[c][kLive3 - 1] = make_float2(0.f, 0.f);
+        }
+    }
+}
+
+#endif  // NVX_CASCADE_DEVICE_CODE
+
+}  // namespace nvx

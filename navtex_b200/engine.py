@@ -1,0 +1,216 @@
+"""ctypes binding of libnavtex_b200.so (include/navtex_b200.h).
+
+Python is only the harness language here (tests, bench): the product is the C ABI.  There is no
+CPU fallback: importing works anywhere, but creating an Engine needs the built library and a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnavtex_b200.so")
+BLOCK_ALIGN = 280
+FS = 252_000
+
+
+class NvxError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int), ("n_streams", C.c_int), ("max_block", C.c_longlong), ("freq_tag", C.c_int * 2),
+        ("h1", C.POINTER(C.c_double)), ("h2", C.POINTER(C.c_double)), ("h3", C.POINTER(C.c_double)),
+        ("keep_bits", C.c_int), ("first_stream_id", C.c_int),
+    ]
+
+
+class Message(C.Structure):
+    _fields_ = [("stream", C.c_int), ("freq", C.c_int), ("bbbb", C.c_char * 8), ("text", C.c_char_p), ("text_len", C.c_size_t)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("cascade_ms", C.c_double), ("demod_ms", C.c_double), ("cascade_launches", C.c_longlong),
+                ("demod_launches", C.c_longlong), ("aux_launches", C.c_longlong), ("samples", C.c_longlong)]
+
+
+class SynthDesc(C.Structure):
+    _fields_ = [("bits", C.POINTER(C.c_uint8)), ("bit_off", C.POINTER(C.c_longlong)), ("offset_hz", C.POINTER(C.c_float)),
+                ("start_s", C.POINTER(C.c_float)), ("amplitude", C.POINTER(C.c_float)), ("noise_sigma", C.POINTER(C.c_float)),
+                ("seed", C.c_ulonglong)]
+
+
+EXPORTS = (
+    "nvx_default_config", "nvx_last_error", "nvx_engine_create", "nvx_engine_destroy", "nvx_engine_reset",
+    "nvx_engine_push_host_f32", "nvx_engine_push_host_s16", "nvx_engine_push_device_f32", "nvx_engine_push_device_s16",
+    "nvx_engine_sync", "nvx_engine_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
+    "nvx_engine_read_bits", "nvx_engine_read_events", "nvx_engine_enable_timing", "nvx_engine_get_stats",
+    "nvx_engine_stream", "nvx_synth_fill_device", "nvx_host_assemble",
+)
+
+MESSAGE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int)
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NvxError(f"{LIB_PATH} is missing: run navtex_b200/build.sh (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.nvx_last_error.restype = C.c_char_p
+    L.nvx_default_config.argtypes = [C.POINTER(Config)]
+    L.nvx_engine_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.nvx_engine_destroy.argtypes = [C.c_void_p]
+    L.nvx_engine_destroy.restype = None
+    L.nvx_engine_reset.argtypes = [C.c_void_p]
+    for name in ("nvx_engine_push_host_f32", "nvx_engine_push_host_s16", "nvx_engine_push_device_f32", "nvx_engine_push_device_s16"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    L.nvx_engine_sync.argtypes = [C.c_void_p]
+    L.nvx_engine_poll_messages.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Message)), C.POINTER(C.c_size_t)]
+    L.nvx_engine_read_y3.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.nvx_engine_read_bits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.nvx_engine_read_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.nvx_engine_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    L.nvx_engine_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
+    L.nvx_engine_stream.argtypes = [C.c_void_p]
+    L.nvx_engine_stream.restype = C.c_void_p
+    L.nvx_synth_fill_device.argtypes = [C.c_int, C.POINTER(SynthDesc), C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]
+    L.nvx_host_assemble.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, MESSAGE_CB, C.c_void_p]
+    _lib = L
+    return L
+
+
+def host_assemble(events: bytes, stream: int = 0, freq: int = 518):
+    """Host-side message assembly of one channel's event bytes -> [(stream, freq, bbbb, text)]."""
+    out = []
+
+    def cb(_user, strm, bbbb, text, f):
+        out.append((strm, f, bbbb.decode("latin-1"), text.decode("latin-1")))
+        return 0
+
+    _check(min(0, load_library().nvx_host_assemble(events, len(events), stream, freq, MESSAGE_CB(cb), None)))
+    return out
+
+
+def _check(rc, allow_overflow=False):
+    if rc == 0 or (allow_overflow and rc == -4):
+        return rc
+    raise NvxError(f"nvx error {rc}: {load_library().nvx_last_error().decode()}")
+
+
+class Engine:
+    """One GPU, S streams.  Mirrors the reference's init / per-sample push / add_message flow, batched."""
+
+    def __init__(self, n_streams: int, max_block: int, device: int = 0, keep_bits: bool = False, taps=None,
+                 first_stream_id: int = 0):
+        L = load_library()
+        cfg = Config()
+        L.nvx_default_config(C.byref(cfg))
+        cfg.device, cfg.n_streams, cfg.max_block = device, n_streams, max_block
+        cfg.keep_bits, cfg.first_stream_id = int(keep_bits), first_stream_id
+        self._taps = None
+        if taps is not None:
+            self._taps = [np.ascontiguousarray(t, dtype=np.float64) for t in taps]
+            assert [len(t) for t in self._taps] == [37, 47, 71]
+            cfg.h1, cfg.h2, cfg.h3 = (t.ctypes.data_as(C.POINTER(C.c_double)) for t in self._taps)
+        self._h = C.c_void_p()
+        _check(L.nvx_engine_create(C.byref(cfg), C.byref(self._h)))
+        self.L, self.S, self.max_block, self.device = L, n_streams, max_block, device
+        self.last_n = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.L.nvx_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def reset(self):
+        _check(self.L.nvx_engine_reset(self._h))
+
+    def push_host(self, iq: np.ndarray):
+        """iq: [S, n, 2] (or [S, 2n]) float32 or int16, C-contiguous."""
+        iq = np.ascontiguousarray(iq)
+        n = iq.size // (2 * self.S)
+        fn = {np.dtype(np.float32): self.L.nvx_engine_push_host_f32, np.dtype(np.int16): self.L.nvx_engine_push_host_s16}[iq.dtype]
+        _check(fn(self._h, iq.ctypes.data_as(C.c_void_p), n))
+        self.last_n = n
+
+    def push_host_ptr(self, ptr: int, n: int, s16: bool):
+        fn = self.L.nvx_engine_push_host_s16 if s16 else self.L.nvx_engine_push_host_f32
+        _check(fn(self._h, C.c_void_p(ptr), n))
+        self.last_n = n
+
+    def push_device(self, ptr: int, n: int, s16: bool = False):
+        fn = self.L.nvx_engine_push_device_s16 if s16 else self.L.nvx_engine_push_device_f32
+        _check(fn(self._h, C.c_void_p(ptr), n))
+        self.last_n = n
+
+    def sync(self):
+        _check(self.L.nvx_engine_sync(self._h), allow_overflow=True)
+
+    def poll_messages(self):
+        msgs = C.POINTER(Message)()
+        cnt = C.c_size_t()
+        _check(self.L.nvx_engine_poll_messages(self._h, C.byref(msgs), C.byref(cnt)), allow_overflow=True)
+        return [(msgs[k].stream, msgs[k].freq, msgs[k].bbbb.decode("latin-1"), C.string_at(msgs[k].text, msgs[k].text_len).decode("latin-1"))
+                for k in range(cnt.value)]
+
+    def read_y3(self) -> np.ndarray:
+        """[S, 2, P] complex64 of the last block."""
+        P = self.last_n // BLOCK_ALIGN
+        out = np.empty((self.S, 2, P, 2), dtype=np.float32)
+        got = C.c_size_t()
+        _check(self.L.nvx_engine_read_y3(self._h, out.ctypes.data_as(C.c_void_p), out.size, C.byref(got)))
+        assert got.value == P
+        return out.view(np.complex64)[..., 0]
+
+    def read_bits(self, stream: int, ch: int):
+        cap = self.last_n // BLOCK_ALIGN // 9 + 4
+        bits = np.empty(cap, dtype=np.uint8)
+        sums = np.empty((cap, 4), dtype=np.float32)
+        got = C.c_size_t()
+        _check(self.L.nvx_engine_read_bits(self._h, stream, ch, bits.ctypes.data_as(C.c_void_p), sums.ctypes.data_as(C.c_void_p), cap, C.byref(got)))
+        return bits[: got.value].tobytes(), sums[: got.value].copy()
+
+    def read_events(self, stream: int, ch: int) -> bytes:
+        cap = self.last_n // BLOCK_ALIGN // 30 + 64
+        ev = np.empty(cap, dtype=np.uint8)
+        got = C.c_size_t()
+        _check(self.L.nvx_engine_read_events(self._h, stream, ch, ev.ctypes.data_as(C.c_void_p), cap, C.byref(got)))
+        return ev[: got.value].tobytes()
+
+    def enable_timing(self, on: bool = True):
+        _check(self.L.nvx_engine_enable_timing(self._h, int(on)), allow_overflow=True)
+
+    def stats(self, reset: bool = True) -> Stats:
+        st = Stats()
+        _check(self.L.nvx_engine_get_stats(self._h, C.byref(st), int(reset)), allow_overflow=True)
+        return st
+
+    @property
+    def stream(self) -> int:
+        return self.L.nvx_engine_stream(self._h) or 0
+
+
+def synth_fill_device(device: int, d_ptr: int, n_streams: int, t0: int, n: int, bits_per_stream, offset_hz, start_s,
+                      amplitude, noise_sigma, seed: int, cuda_stream: int = 0):
+    """Fill a device float2 [S][n] block with samples [t0, t0+n) of S synthetic captures (see synth.cu)."""
+    L = load_library()
+    off = np.zeros(n_streams + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(b) for b in bits_per_stream])
+    bits = np.concatenate([np.asarray(b, dtype=np.uint8) for b in bits_per_stream]) if off[-1] else np.zeros(1, np.uint8)
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (offset_hz, start_s, amplitude, noise_sigma)]
+    d = SynthDesc()
+    d.bits = bits.ctypes.data_as(C.POINTER(C.c_uint8))
+    d.bit_off = off.ctypes.data_as(C.POINTER(C.c_longlong))
+    d.offset_hz, d.start_s, d.amplitude, d.noise_sigma = (a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs)
+    d.seed = seed
+    _check(L.nvx_synth_fill_device(device, C.byref(d), n_streams, t0, n, C.c_void_p(d_ptr), C.c_void_p(cuda_stream)))

@@ -92,6 +92,7 @@ class Emission:
     amplitude: float = 8000.0
     n_phasing: int = 70
     n_tail: int = 6
+    stop_s: float | None = None   # transmitter drops out this many seconds after start_s
 
 
 def fsk_iq(
@@ -116,6 +117,8 @@ def fsk_iq(
         bits = message_bits(em.text, em.n_phasing, em.n_tail)
         start = int(round(em.start_s * FS))
         span = min(len(bits) * SAMPLES_PER_BIT, max(0, n - start))
+        if em.stop_s is not None:
+            span = min(span, int(round(em.stop_s * FS)))
         if span <= 0:
             continue
         tone = np.where(bits == 1, -FSK_SHIFT_HZ, FSK_SHIFT_HZ)       # Y = -85 Hz, B = +85 Hz

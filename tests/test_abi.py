@@ -1,0 +1,67 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, the host-side message assembly matches the oracle, and compute entry points fail loudly
+without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as ol
+from navtex_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:nvx_|init_fir|sample_in_|navtex_compat_)\w*)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = engine.load_library()
+    names = [n for n in declared("navtex_b200.h") if n != "nvx_message_cb"]
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(engine.EXPORTS) <= set(names)
+
+
+def test_compat_library_exports_reference_symbols():
+    path = os.path.join(ROOT, "navtex_b200", "libnavtex_compat.so")
+    L = C.CDLL(path)
+    for n in ("init_fir_filter1", "sample_in_1", "init_fir2_wrapper", "navtex_compat_flush", "navtex_compat_set_sink"):
+        assert hasattr(L, n), n
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine.NvxError, match="no usable CUDA device|CUDA"):
+        engine.Engine(1, 2800)
+
+
+@pytest.mark.parametrize("name", ["clean518", "weak518", "dropout"])
+def test_host_assembler_matches_oracle(name):
+    """Feeding the oracle's event stream through the product's host assembler reproduces the oracle's messages."""
+    iq = cases.build(name)
+    r = ol.run_oracle(iq, record_taps=False)
+    got = engine.host_assemble(r.events["518"], stream=7, freq=518)
+    want = [(7, f, b, t) for f, b, t in r.messages if f == 518]
+    assert got == want
+
+
+def test_host_assembler_quirks():
+    # a second ZCZC before NNNN keeps the first B1B2B3B4 (strncat onto a non-empty buffer, nav_b_sm.C:74-76)
+    ev = b"ZCZC AB12\nTEXT\nZCZC CD34\nMORE\nNNNN\n"
+    assert engine.host_assemble(ev) == [(0, 518, "AB12", "ZCZC CD34\nMORE\nNNNN\n")]
+    # one garbled character in the framing words is tolerated (regex alternatives)
+    assert engine.host_assemble(b"Z*ZC EF56\nX\nN*NN\n") == [(0, 518, "EF56", "Z*ZC EF56\nX\nN*NN\n")]
+    # abort stores the partial message, and nothing when none is in progress
+    assert engine.host_assemble(b"ZCZC GH78\nPART\x18") == [(0, 518, "GH78", "ZCZC GH78\n")]
+    assert engine.host_assemble(b"NOISE\x18NNNN\n") == []
