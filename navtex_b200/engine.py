@@ -126,9 +126,10 @@ class Engine:
         self.last_n = 0
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            self.L.nvx_engine_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.L.nvx_engine_destroy(h)
+            h.value = None
 
     __del__ = close
 

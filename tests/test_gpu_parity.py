@@ -100,7 +100,7 @@ def test_blocking_invariance(batch, block):
     y = np.concatenate(ys, axis=2)
     assert np.array_equal(y.view(np.uint64), y_ref.view(np.uint64))      # bit-identical, not just close
     if block != 280:
-        assert msgs == msgs_ref
+        assert sorted(msgs) == sorted(msgs_ref)      # same multiset; delivery order follows block boundaries
         for k in range(S):
             for c, tag in enumerate(ol.CHANNELS):
                 assert events[k][c] == oracle[k].events[tag]
