@@ -1,0 +1,353 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the NAVTEX receive chain (BASELINE.json metric:
+"IQ Msamples/s through FIR cascade + FSK demod at 1-8 B200; % HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the whole hot path (fused FIR cascade -> demod / bit-sync -> SITOR-B state
+machine -> host message assembly) over one block of BASELINE.json configs[1]: 1024 synthetic IQ
+streams per GPU (distinct SITOR-B bulletins, start times, channels and SNRs) x 10.28 s at 252 kS/s,
+resident in HBM (21 GB per GPU: far larger than the 126 MB L2, so nothing is cache-warm between
+steps).  Streams are independent: N GPUs = N x 1024 streams, no collective on the data path
+(weak scaling); the only cross-rank traffic is the barrier and the max-over-ranks timing.
+
+value  = samples processed by all ranks / max-over-ranks device time (CUDA events on the engine stream).
+e2e    = same metric through nvx_engine_push_host_s16 (the reference's own int16 sample format) with
+         pinned HOST buffers: H2D copy, int16->float conversion, both kernels, event download and
+         host message assembly all inside the timed region.
+--impl reference times the reference's own CPU chain (oracle/_ref/ref_chain, built unmodified from
+the reference sources) on all host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STREAMS_PER_GPU = 1024
+SUPER_PER_BLOCK = 9250              # 900 Hz outputs per stream per step -> n = 2,590,000 samples (10.28 s)
+BLOCK = SUPER_PER_BLOCK * 280
+E2E_BLOCK = 900 * 280               # 1.0 s per stream per host push (1.03 GB of int16 per step)
+BYTES_PER_SAMPLE = 8.0 + 16.0 / 280 # algorithmic HBM bytes per input IQ sample: float2 in, 2 x float2 per 280 out
+REF_CHAIN = os.path.join(ROOT, "oracle", "_ref", "ref_chain")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "cascade_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        inside = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in inside)]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in inside if num(r[0]) is not None]
+        pw = [num(r[2]) for r in inside if num(r[2]) is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(inside[0][1]), "power_w_max": max(pw) if pw else None,
+                "samples": len(inside), "reasons": reasons}
+
+
+def build_workload(torch, device, rank):
+    """1024 distinct synthetic captures for this rank, generated on the device (untimed)."""
+    import numpy as np
+    from navtex_b200 import engine, synth
+
+    S = STREAMS_PER_GPU
+    rng = np.random.default_rng(518490 + rank)
+    bits, off, start, amp, sigma, expect = [], [], [], [], [], []
+    for s in range(S):
+        while True:      # bulletins short enough to fit one 10.28 s block together with their start delay
+            text, bbbb = synth.random_message(rng, n_lines=1, words_per_line=3)
+            b = synth.message_bits(text, n_phasing=18, n_tail=5)
+            if len(b) * 2520 + 0.6 * 252000 < BLOCK:
+                break
+        bits.append(b)
+        ch = s % 2
+        off.append(14000.0 if ch == 0 else -14000.0)
+        start.append(0.05 + 0.4 * rng.random())
+        amp.append(3000.0 + 6000.0 * rng.random())
+        sigma.append(amp[-1] * 10 ** (rng.uniform(-6.0, 14.0) / 20) / np.sqrt(2))     # full-band SNR -14 .. +6 dB
+        expect.append((s + rank * S, 518 if ch == 0 else 490, bbbb, text))
+    x = torch.empty((S, BLOCK, 2), dtype=torch.float32, device=device)
+    engine.synth_fill_device(device.index, x.data_ptr(), S, 0, BLOCK, bits, off, start, amp, sigma, seed=518490 + rank)
+    return x, expect
+
+
+def run_reference_cpu(samples_i16, passes_warm, passes_timed, cores):
+    """Time the unmodified reference chain on `cores` host cores, one process (= one stream: its state is
+    global) per core, `passes` back-to-back passes each.  Returns aggregate samples/s over the timed passes."""
+    import numpy as np
+
+    n_streams = len(samples_i16)
+    with tempfile.TemporaryDirectory() as td:
+        paths = []
+        for k, iq in enumerate(samples_i16):
+            p = os.path.join(td, f"s{k}.s16")
+            np.ascontiguousarray(iq, dtype=np.int16).tofile(p)
+            paths.append(p)
+        procs = [subprocess.Popen([REF_CHAIN, "--s16", paths[k % n_streams], "--passes", str(passes_warm + passes_timed)],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for k in range(cores)]
+        outs = [p.communicate()[1] for p in procs]
+    per_pass = []
+    n = samples_i16[0].size // 2
+    for o in outs:
+        j = json.loads(o.strip().splitlines()[-1])
+        per_pass.append(j["pass_s"][passes_warm:])
+    # all processes run concurrently: pass k of the job ends when the slowest core finishes it
+    step_s = [max(pp[k] for pp in per_pass) for k in range(passes_timed)]
+    total = cores * n * passes_timed
+    return total / sum(step_s), sum(step_s) / passes_timed, n
+
+
+def impl_reference(args, rank, world):
+    if rank != 0:
+        return
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from navtex_b200 import synth
+
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(518490)
+    n_sample_streams = min(cores, 16)
+    streams = []
+    seconds = 4.0          # bounded sample: 4 s of each of up to 16 of the workload's streams
+    for s in range(n_sample_streams):
+        text, _ = synth.random_message(rng, n_lines=1, words_per_line=2)
+        em = synth.Emission(text, 14000.0 if s % 2 == 0 else -14000.0, start_s=0.1, n_phasing=12, n_tail=4)
+        streams.append(synth.quantise_s16(synth.fsk_iq([em], seconds, snr_db=float(rng.uniform(-14, 6)), seed=s)))
+    if os.path.exists(REF_CHAIN):
+        sps, step_s, n = run_reference_cpu(streams, args.warmup, args.steps, cores)
+        kind = "reference"
+    else:   # the compiled reference did not travel: time the C port instead
+        import oracle_lib as ol
+        t0 = time.time()
+        for k in range(args.steps):
+            ol.run_oracle(streams[k % len(streams)], record_taps=False)
+        step_s = (time.time() - t0) / args.steps
+        n, cores, kind = streams[0].size // 2, 1, "port"
+        sps = n / step_s
+    val = sps / 1e6
+    sample = f"{cores} processes x {n} samples ({seconds:.0f} s of one workload stream each) per step"
+    line = {
+        "impl": "reference", "metric": "iq_msamples_per_s", "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1024 synthetic IQ streams/GPU, fused FIR cascade + FSK demod + bit-sync + SITOR-B (CPU chain on host cores, bounded sample)",
+                   "streams_per_gpu": STREAMS_PER_GPU, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "realtime_streams": val / 0.252,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        impl_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from navtex_b200 import engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU chain)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    S = STREAMS_PER_GPU
+    x, expect = build_workload(torch, device, rank)
+    eng = engine.Engine(S, BLOCK, device=local, first_stream_id=rank * S)
+    es = torch.cuda.ExternalStream(eng.stream, device=device)
+
+    # ---- device-resident whole-job throughput ----------------------------------------------------
+    for _ in range(args.warmup):
+        eng.push_device(x.data_ptr(), BLOCK)
+    msgs_warm = eng.poll_messages()
+    eng.enable_timing(True)
+    eng.stats()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record(es)
+    for _ in range(args.steps):
+        eng.push_device(x.data_ptr(), BLOCK)
+    eng.sync()
+    ev1.record(es)
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    dev_ms = ev0.elapsed_time(ev1)
+    st = eng.stats()
+    msgs = eng.poll_messages()
+    eng.enable_timing(False)
+    # correctness of what was timed: each pass over the block re-decodes every stream's bulletin
+    got = {(m[0], m[1], m[2], m[3]) for m in msgs}
+    decoded_ok = sum(1 for e in expect if e in got)
+
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    total_samples = world * S * BLOCK * args.steps
+    value = total_samples / (max_ms * 1e-3) / 1e6                     # Msamples/s
+
+    # ---- end to end through the host-buffer C ABI --------------------------------------------------
+    ne = E2E_BLOCK
+    host = torch.empty((S, ne, 2), dtype=torch.int16).pin_memory()
+    host.copy_(x[:, :ne].round().to(torch.int16).cpu())
+    e2e_eng = engine.Engine(S, ne, device=local, first_stream_id=rank * S)
+    e2s = torch.cuda.ExternalStream(e2e_eng.stream, device=device)
+    for _ in range(max(3, args.warmup)):
+        e2e_eng.push_host_ptr(host.data_ptr(), ne, s16=True)
+        e2e_eng.poll_messages()
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    a0.record(e2s)
+    n_e2e_msgs = 0
+    for _ in range(args.steps):
+        e2e_eng.push_host_ptr(host.data_ptr(), ne, s16=True)
+        n_e2e_msgs += len(e2e_eng.poll_messages())                    # D2H of the events + host assembly: the step's result
+    a1.record(e2s)
+    barrier()
+    e2e_wall = time.time() - tw0
+    te = torch.tensor([max(a0.elapsed_time(a1) * 1e-3, e2e_wall)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * ne * args.steps / float(te.item()) / 1e6
+    ev_cap = 2 * (ne // 280 // 63 + 2) + 8
+    e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * ne * 4, "d2h_bytes_per_step": 2 * S * (ev_cap + 4),
+           "input": "int16 IQ in pinned host memory, [1024 streams][252000 samples] per step", "ms_per_step": float(te.item()) * 1e3 / args.steps}
+    e2e_eng.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused FIR cascade) -------------------------------------------
+    peak, peak_src = measured_peak()
+    casc_ms = st.cascade_ms / max(1, st.cascade_launches)
+    achieved = S * BLOCK * BYTES_PER_SAMPLE / (casc_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+                "kernel": "nvx::fir_cascade_kernel<true>", "kernel_ms": casc_ms, "demod_kernel_ms": st.demod_ms / max(1, st.demod_launches),
+                "algorithmic_bytes_per_launch": S * BLOCK * BYTES_PER_SAMPLE,
+                "kernel_gsamples_per_s": S * BLOCK / (casc_ms * 1e-3) / 1e9}
+
+    # ---- CPU baseline: the reference's own chain on the host cores, bounded sample ------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_cpu = 4 * 252000
+        sample = [x[k, :n_cpu].round().to(torch.int16).cpu().numpy().reshape(-1) for k in range(min(cores, 16))]
+        if os.path.exists(REF_CHAIN):
+            sps, step_s, n = run_reference_cpu(sample, 2, 10, cores)
+            kind = "reference"
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as ol
+            t0 = time.time()
+            for k in range(4):
+                ol.run_oracle(sample[k % len(sample)], record_taps=False)
+            sps, cores, kind = 4 * n_cpu / (time.time() - t0), 1, "port"
+        cpu = {"value": sps / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
+               "sample": f"first 4 s of {min(cores, 16)} of the workload's streams, one ref_chain process per core, 10 timed passes"}
+
+    line = {
+        "metric": "iq_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 1024 synthetic IQ streams per GPU through fused FIR cascade + FSK demod + bit-sync + SITOR-B",
+                   "streams_per_gpu": S, "samples_per_stream_per_step": BLOCK, "seconds_per_step": BLOCK / 252000,
+                   "input": "float2 IQ resident in HBM, 21.2 GB per GPU per step (larger than L2; no flush needed)",
+                   "parallelism": f"stream-sharded x{world}, no collectives"},
+        "realtime_streams": value / 0.252,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(st.cascade_launches + st.demod_launches + st.aux_launches),
+        "clocks": clocks,
+        "check": {"bulletins_expected_per_step": len(expect), "decoded_exact": decoded_ok, "messages_total": len(msgs),
+                  "e2e_messages": n_e2e_msgs},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,7 @@ int main(int argc, char **argv) {
     init_fir2_wrapper();     // capt_sched.c:612
 
     double best = 1e30, total = 0;
+    std::vector<double> pass_s;
     for (int p = 0; p < passes; ++p) {
         g_record = (p == 0) && out != nullptr;
         auto t0 = std::chrono::steady_clock::now();
@@ -185,9 +186,12 @@ int main(int argc, char **argv) {
         double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (dt < best) best = dt;
         total += dt;
+        pass_s.push_back(dt);
     }
-    fprintf(stderr, "{\"samples\": %zu, \"passes\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"msps_best\": %.3f, \"msps_mean\": %.3f, \"messages\": %zu}\n",
+    fprintf(stderr, "{\"samples\": %zu, \"passes\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"msps_best\": %.3f, \"msps_mean\": %.3f, \"messages\": %zu, \"pass_s\": [",
             n, passes, best, total / passes, n / best * 1e-6, n * passes / total * 1e-6, g_msgs.size());
+    for (size_t p = 0; p < pass_s.size(); ++p) fprintf(stderr, "%s%.6f", p ? ", " : "", pass_s[p]);
+    fprintf(stderr, "]}\n");
 
     if (out) {
         std::string o(out);
