@@ -1,25 +1,29 @@
 // demod.cu -- FSK discriminator, bit synchroniser, mark/space decision and SITOR-B byte state
-// machine for [channels] independent 900 Hz complex streams, one WARP per channel.
+// machine for [channels] independent 900 Hz complex streams.
 //
-// Replaces, per channel and per batch instead of per sample,
+// Replaces, per channel and per block instead of per sample,
 //   decoder::sample_in            receiver/decoder.C:42-59    (delay-conjugate product + atan2)
 //   decoder::bs_decoded_sample_in receiver/decoder.C:142-255  (bit-sync timing recovery)
 //   decoder::bd_decoded_sample_in receiver/decoder.C:73-137   (mark/space energy discriminator)
 //   byte_state_machine::receive_bit / receive_rxdx_byte / message_byte_out
 //                                 receiver/nav_b_sm.C:266-634, :150-262, :100-145
 // Line assembly, the ZCZC/NNNN regexes and add_message (nav_b_sm.C:56-97, :44-52) stay on the
-// host (message_assembler.cpp); this kernel emits the character/line/abort event stream they
+// host (message_assembler.cpp); the last kernel emits the character/line/abort event stream they
 // consume.
 //
-// Work split inside the warp, per batch of 32 consecutive 900 Hz samples (lane = sample):
-//   feed-forward part, all lanes in parallel: angle (FP64 atan2), 9-tap transition-mask
-//   correlation, and the 63-term per-offset sum, each in exactly the reference's operation order
-//   (the 567-deep ring is kept as a time-indexed history so every lane sees the ring "as of" its
-//   own sample);
-//   feedback part, 32 short uniform iterations: lanes 0..8 own the nine offset sums, the argmax is
-//   a shuffle reduction, then slew limiting, the WAIT/BIT_START/RECEIVING machine with the
-//   reference's mixed float/double accumulator arithmetic (explicit _rn intrinsics, no FMA
-//   contraction), and the byte state machine, evaluated redundantly by all lanes (no divergence).
+// The reference interleaves everything per sample, but almost all of it is feed-forward in time.
+// Three kernels per block:
+//   angle_corr_kernel   thread = sample: FP64 angle of y[n] conj(y[n-1]) and the 9-tap transition
+//                       mask correlation, in the reference's operation order;
+//   sum_decide_kernel   thread = sample: the 63-term per-offset sum "as the 567-ring stood at that
+//                       sample" (same ascending-slot summation order), the first-maximum arg max over
+//                       the nine sums at evaluation samples, and -- for EVERY possible bit start --
+//                       the mark/space decision of the 5-sample window starting there, with the
+//                       reference's mixed float/double accumulator arithmetic (_rn intrinsics, no
+//                       FMA contraction).  One byte per sample comes out;
+//   symbol_clock_kernel thread = channel: the only truly sequential part -- slew-limited offset
+//                       tracking, the WAIT/BIT_START/RECEIVING symbol clock (which merely selects
+//                       which precomputed decision is a bit), and the byte state machine.
 #include "demod.cuh"
 
 #include <math.h>
@@ -28,9 +32,9 @@ namespace nvx {
 
 namespace {
 
-constexpr int kWarps = 4;
+constexpr int kTile = 256;
 
-enum { DS_INIT = 0, DS_WAIT = 1, DS_BIT_START = 2, DS_RECEIVING = 3 };   // decoder.h:16-19
+enum { DS_INIT = 0, DS_WAIT = 1, DS_PENDING = 2 };   // decoder.h:16-19 (BIT_START / RECEIVING folded into PENDING)
 enum { BY_WAIT = 1, BY_GOT_DX = 2, BY_GOT_RX = 3 };                       // nav_b_sm.h:41-43
 
 __constant__ unsigned char c_ltrs[128];
@@ -48,7 +52,7 @@ struct Emit {
 };
 
 // byte_state_machine::init, nav_b_sm.C:16-42 (the error ring contents survive, only its counters reset)
-__device__ __forceinline__ void fsm_reset(ChannelScalars& s) {
+__device__ __forceinline__ void fsm_reset(ChannelState& s) {
     s.match = 0; s.byte_state = BY_WAIT; s.figures = 0; s.nbits = 0;
     s.dx_at = 0; s.dx_full = 0;
     s.err_count = 0; s.err_at = 0; s.err_full = 0;
@@ -57,7 +61,7 @@ __device__ __forceinline__ void fsm_reset(ChannelScalars& s) {
 }
 
 // message_byte_out, nav_b_sm.C:100-145; code 0 = "no valid copy" -> '*'
-__device__ __forceinline__ void fsm_char(ChannelScalars& s, Emit& e, int code) {
+__device__ __forceinline__ void fsm_char(ChannelState& s, Emit& e, int code) {
     if (code == 0) { e.put('*'); return; }
     const int l = c_ltrs[code];
     if (l == 'l') { s.figures = 0; return; }
@@ -68,13 +72,13 @@ __device__ __forceinline__ void fsm_char(ChannelScalars& s, Emit& e, int code) {
 }
 
 // message_abort, nav_b_sm.C:44-52: the host decides whether a message was in progress
-__device__ __forceinline__ void fsm_abort(ChannelScalars& s, Emit& e) {
+__device__ __forceinline__ void fsm_abort(ChannelState& s, Emit& e) {
     e.put(kEvAbort);
     fsm_reset(s);
 }
 
 // receive_rxdx_byte, nav_b_sm.C:150-262
-__device__ __forceinline__ void fsm_byte(ChannelScalars& s, Emit& e, int b) {
+__device__ __forceinline__ void fsm_byte(ChannelState& s, Emit& e, int b) {
     if (s.byte_state == BY_WAIT) {
         if (b == 0x07) s.byte_state = BY_GOT_RX;
         if (b == 0x4c) s.byte_state = BY_GOT_DX;
@@ -112,7 +116,7 @@ __device__ __forceinline__ void fsm_byte(ChannelScalars& s, Emit& e, int b) {
 }
 
 // receive_bit, nav_b_sm.C:266-634.  is_y: 'Y' (=1) else 'B'.
-__device__ __forceinline__ void fsm_bit(ChannelScalars& s, Emit& e, bool is_y) {
+__device__ __forceinline__ void fsm_bit(ChannelState& s, Emit& e, bool is_y) {
     if (s.enabled) {
         s.shift = ((s.shift << 1) | (is_y ? 1 : 0)) & 0x7f;
         if (++s.nbits == 7) {
@@ -135,183 +139,249 @@ __device__ __forceinline__ void fsm_bit(ChannelScalars& s, Emit& e, bool is_y) {
     }
 }
 
-__global__ void __launch_bounds__(kWarps * 32) demod_kernel(const DemodArgs a) {
-    __shared__ double s_corr[kWarps][kCorrRing];
-    __shared__ double s_ang[kWarps][40];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * kWarps + warp;
-    if (ch >= a.channels) return;
-    constexpr unsigned kAll = 0xffffffffu;
 
-    ChannelState& g = a.state[ch];
-    double* corr = s_corr[warp];
-    double* ang = s_ang[warp];
-    for (int k = lane; k < kCorrRing; k += 32) corr[k] = g.corr[k];
-    if (lane < 8) ang[lane] = g.ang[lane];
-    double my_osum = lane < kSpb ? g.osum[lane] : -2.0;
+__device__ __forceinline__ size_t pitch_y(int p_max) { return (size_t)kHistY + p_max; }
+__device__ __forceinline__ size_t pitch_c(int p_max) { return (size_t)kHistC + p_max; }
+__device__ __forceinline__ size_t pitch_d(int p_max) { return ((size_t)kHistD + p_max + 15) & ~(size_t)15; }
 
-    // scalar state, held redundantly (and identically) by every lane
-    ChannelScalars s = g.sc;
-    __syncwarp();
-
-    Emit em;
-    em.ev = a.events + (size_t)ch * a.ev_cap; em.ev_cap = a.ev_cap; em.n = 0; em.writer = lane == 0;
-    int nbits_out = 0;
-    char* bits = a.bits ? a.bits + (size_t)ch * a.bit_cap : nullptr;
-    float* disc = a.disc ? a.disc + (size_t)ch * a.bit_cap * 4 : nullptr;
-
-    const float2* y3 = a.y3 + (size_t)ch * a.y3_pitch + a.y3_off;
-    int m9 = (int)(s.seen % kSpb);
-
-    for (int base = 0; base < a.n_new; base += 32) {
-        const int cnt = min(32, a.n_new - base);
-        const long long n = s.seen + lane;                 // absolute index of this lane's sample
-        const bool active = lane < cnt;
-        const float2 y = active ? y3[base + lane] : make_float2(0.f, 0.f);
-        const double yi = (double)y.x, yq = (double)y.y;
-
-        // ---- feed-forward, lane = sample --------------------------------------------------
-        double pi = __shfl_up_sync(kAll, yi, 1), pq = __shfl_up_sync(kAll, yq, 1);
-        if (lane == 0) { pi = s.prev_i; pq = s.prev_q; }
-        const double re = __dadd_rn(__dmul_rn(yi, pi), __dmul_rn(yq, pq));       // decoder.C:48
-        const double im = __dsub_rn(__dmul_rn(yq, pi), __dmul_rn(yi, pq));       // decoder.C:49
-        const double angle = atan2(im, re);                                       // decoder.C:52
-        ang[8 + lane] = angle;
-        __syncwarp();
-        if (active && n >= 8) {
-            // mask {0,1,1,1,0,-1,-1,-1,0} over angles n-8 .. n, oldest first (decoder.C:161-170)
-            double t = ang[lane + 1];
-            t = __dadd_rn(t, ang[lane + 2]);
-            t = __dadd_rn(t, ang[lane + 3]);
-            t = __dsub_rn(t, ang[lane + 5]);
-            t = __dsub_rn(t, ang[lane + 6]);
-            t = __dsub_rn(t, ang[lane + 7]);
-            corr[(int)((n - 8) & (kCorrRing - 1))] = fabs(t);
-        }
-        __syncwarp();
-        double osum_new = 0.0;
-        if (active && n >= kCorrLen + 7) {
-            // decoder.C:186-190: sum ring slots j, j+9, ... in ascending slot order, as the ring stood
-            // after this sample's write.  Slot i then held value number v - ((v - i) mod 567), v = n - 8.
-            const long long v = n - 8;
-            const int j = (int)((v - (kCorrLen - 1)) % kSpb);
-            int d = (int)((v - j) % kCorrLen);
-            double acc = 0.0;
-#pragma unroll 9
-            for (int k = 0; k < 63; ++k) {
-                acc = __dadd_rn(acc, corr[(int)((v - d) & (kCorrRing - 1))]);
-                d -= kSpb;
-                if (d < 0) d += kCorrLen;
-            }
-            osum_new = acc;
-        }
-        __syncwarp();
-        {   // slide the angle history and the previous-sample carry to the end of this batch
-            const double keep = lane < 8 ? ang[cnt + lane] : 0.0;
-            __syncwarp();
-            if (lane < 8) ang[lane] = keep;
-            s.prev_i = __shfl_sync(kAll, yi, cnt - 1);
-            s.prev_q = __shfl_sync(kAll, yq, cnt - 1);
-        }
-
-        // ---- feedback, 32 uniform iterations -----------------------------------------------
-        for (int k = 0; k < cnt; ++k) {
-            const long long nk = s.seen + k;
-            const double ov = __shfl_sync(kAll, osum_new, k);
-            const double sr = __shfl_sync(kAll, yi, k), si = __shfl_sync(kAll, yq, k);
-            if (nk >= kCorrLen + 7) {
-                int j = m9 - 7; if (j < 0) j += kSpb;             // (nk - 574) mod 9
-                if (lane == j) my_osum = ov;
-                if (nk >= kCorrLen + 15 && m9 == 6) {             // every 9th sample from 582 on (decoder.C:204)
-                    double bv = my_osum; int bi = lane;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        const double ovv = __shfl_xor_sync(kAll, bv, off);
-                        const int oi = __shfl_xor_sync(kAll, bi, off);
-                        if (ovv > bv || (ovv == bv && oi < bi)) { bv = ovv; bi = oi; }
-                    }
-                    int pick = bi;                                 // first maximum, strict '>' (decoder.C:207-215)
-                    if (s.last_pick != -1 && pick != s.last_pick) {
-                        bool up;
-                        if (pick > s.last_pick) up = !(pick - s.last_pick > 4);
-                        else up = (s.last_pick - pick > 4);
-                        pick = up ? (s.last_pick + 1) % kSpb : (s.last_pick - 1 + kSpb) % kSpb;
-                    }
-                    s.last_pick = pick;
-                    const int offs = (pick + 5) % kSpb;            // decoder.C:249
-                    if (s.dstate == DS_INIT) { s.dstate = DS_WAIT; s.offs = offs; }
-                    s.next_offs = offs;
-                }
-            }
-            // mark/space discriminator (decoder.C:73-137); bd_seq_nbr % 9 == (nk + 1) % 9
-            const int tick = m9 + 1 == kSpb ? 0 : m9 + 1;
-            if (s.dstate != DS_INIT) {
-                if (s.dstate == DS_WAIT && tick == s.offs) { s.dstate = DS_BIT_START; s.burned = 0; }
-                if (s.dstate == DS_BIT_START) {
-                    if (s.burned == 2) {
-                        s.dstate = DS_RECEIVING; s.used = 0;
-                        s.br = s.bi = s.yr = s.yi = 0.f;
-                    } else {
-                        s.burned++;
-                    }
-                } else if (s.dstate == DS_RECEIVING) {
-                    const float fr = c_tone_r[s.used], fi = c_tone_i[s.used];
-                    const float srf = (float)sr, nsrf = (float)(-sr);
-                    const double pr = (double)__fmul_rn(srf, fr), pim = (double)__fmul_rn(srf, fi);
-                    const double npim = (double)__fmul_rn(nsrf, fi);
-                    const double qi = __dmul_rn(si, (double)fi), qr = __dmul_rn(si, (double)fr);
-                    s.yr = (float)__dadd_rn((double)s.yr, __dsub_rn(pr, qi));
-                    s.yi = (float)__dadd_rn((double)s.yi, __dadd_rn(pim, qr));
-                    s.br = (float)__dadd_rn((double)s.br, __dadd_rn(pr, qi));
-                    s.bi = (float)__dadd_rn((double)s.bi, __dadd_rn(npim, qr));
-                    if (++s.used == 5) {
-                        const float eb = __fadd_rn(__fmul_rn(s.br, s.br), __fmul_rn(s.bi, s.bi));
-                        const float ey = __fadd_rn(__fmul_rn(s.yr, s.yr), __fmul_rn(s.yi, s.yi));
-                        const bool is_y = !(eb > ey);
-                        if (bits && lane == 0 && nbits_out < a.bit_cap) {
-                            bits[nbits_out] = is_y ? 'Y' : 'B';
-                            if (disc) {
-                                float* dd = disc + 4 * (size_t)nbits_out;
-                                dd[0] = s.br; dd[1] = s.bi; dd[2] = s.yr; dd[3] = s.yi;
-                            }
-                        }
-                        ++nbits_out;
-                        s.dstate = DS_WAIT;
-                        s.offs = s.next_offs;
-                        fsm_bit(s, em, is_y);
-                    }
-                }
-            }
-            m9 = tick;
-        }
-        s.seen += cnt;
-        __syncwarp();
-    }
-
-    // write back
-    for (int k = lane; k < kCorrRing; k += 32) g.corr[k] = corr[k];
-    if (lane < 8) g.ang[lane] = ang[lane];
-    if (lane < kSpb) g.osum[lane] = my_osum;
-    if (lane == 0) {
-        g.sc = s;
-        a.ev_count[ch] = em.n;
-        if (a.bit_count) a.bit_count[ch] = nbits_out;
-    }
+// decoder.C:48-52
+__device__ __forceinline__ double angle_of(float2 cur, float2 prev) {
+    const double yi = cur.x, yq = cur.y, pi = prev.x, pq = prev.y;
+    const double re = __dadd_rn(__dmul_rn(yi, pi), __dmul_rn(yq, pq));
+    const double im = __dsub_rn(__dmul_rn(yq, pi), __dmul_rn(yi, pq));
+    return atan2(im, re);
 }
 
-__global__ void demod_init_kernel(ChannelState* st, int channels) {
+// grid (tiles, channels), block kTile: |mask correlation| for samples [tile0, tile0 + kTile)
+__global__ void __launch_bounds__(kTile) angle_corr_kernel(const DemodArgs a) {
+    __shared__ double s_ang[kTile + 8];
+    const int ch = blockIdx.y, tile0 = blockIdx.x * kTile, t = threadIdx.x;
+    const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY;     // y[m], m >= -kHistY
+    const int m = tile0 + t;
+    if (m < a.n_new) s_ang[8 + t] = angle_of(y[m], y[m - 1]);
+    if (t < 8) s_ang[t] = angle_of(y[tile0 - 8 + t], y[tile0 - 9 + t]);
+    __syncthreads();
+    if (m >= a.n_new) return;
+    // mask {0,1,1,1,0,-1,-1,-1,0} over angles n-8 .. n, oldest first (decoder.C:161-170); s_ang[8 + t - k] = angle[m - k]
+    double c = s_ang[t + 1];
+    c = __dadd_rn(c, s_ang[t + 2]);
+    c = __dadd_rn(c, s_ang[t + 3]);
+    c = __dsub_rn(c, s_ang[t + 5]);
+    c = __dsub_rn(c, s_ang[t + 6]);
+    c = __dsub_rn(c, s_ang[t + 7]);
+    a.b.corr[(size_t)ch * pitch_c(a.b.p_max) + kHistC + m] = fabs(c);
+}
+
+// mark/space decision of the window y[0..4] (decoder.C:109-133).  Returns true for 'Y'.
+__device__ __forceinline__ bool window_is_y(const float2* __restrict__ y, float* sums) {
+    float br = 0.f, bi = 0.f, yr = 0.f, yi = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double sr = y[k].x, si = y[k].y;
+        const float fr = c_tone_r[k], fi = c_tone_i[k];
+        const float srf = (float)sr, nsrf = (float)(-sr);
+        const double pr = (double)__fmul_rn(srf, fr), pim = (double)__fmul_rn(srf, fi);
+        const double npim = (double)__fmul_rn(nsrf, fi);
+        const double qi = __dmul_rn(si, (double)fi), qr = __dmul_rn(si, (double)fr);
+        yr = (float)__dadd_rn((double)yr, __dsub_rn(pr, qi));
+        yi = (float)__dadd_rn((double)yi, __dadd_rn(pim, qr));
+        br = (float)__dadd_rn((double)br, __dadd_rn(pr, qi));
+        bi = (float)__dadd_rn((double)bi, __dadd_rn(npim, qr));
+    }
+    if (sums) { sums[0] = br; sums[1] = bi; sums[2] = yr; sums[3] = yi; }
+    const float eb = __fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi));
+    const float ey = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+    return !(eb > ey);
+}
+
+// grid (tiles, channels), block kTile: one decision byte for samples w in [tile0 - 4, tile0 + kTile - 4)
+__global__ void __launch_bounds__(kTile) sum_decide_kernel(const DemodArgs a) {
+    constexpr int kBack = kCorrLen - 1 + 12;                 // corr history one tile needs before tile0
+    __shared__ double s_corr[kBack + kTile];
+    __shared__ double s_osum[kTile + 8];
+    const int ch = blockIdx.y, tile0 = blockIdx.x * kTile, t = threadIdx.x;
+    const double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC;      // corr[m], m >= -kHistC
+    for (int k = t; k < kBack + kTile; k += kTile) {
+        const int m = tile0 - kBack + k;
+        s_corr[k] = (m >= -kHistC && m < a.n_new) ? corr[m] : 0.0;
+    }
+    __syncthreads();
+    // per-offset sums for samples [tile0 - 12, tile0 + kTile - 4): thread t -> tile0 - 12 + t (and 8 more by t < 8)
+    auto offset_sum = [&](int m) -> double {
+        const long long n = a.seen + m;                      // absolute sample index
+        if (n < kCorrLen + 7 || m >= a.n_new) return 0.0;
+        // decoder.C:186-190: slots j, j+9, ... in ascending slot order, ring as it stood after this sample's write.
+        // Slot i then held the value written at sample n - ((n - 8 - i) mod 567).
+        const long long v = n - 8;
+        const int j = (int)((v - (kCorrLen - 1)) % kSpb);
+        int d = (int)((v - j) % kCorrLen);
+        const double* base = s_corr + (m - tile0 + kBack);   // -> corr[m]
+        double acc = 0.0;
+#pragma unroll 9
+        for (int k = 0; k < 63; ++k) {
+            acc = __dadd_rn(acc, base[-d]);
+            d -= kSpb;
+            if (d < 0) d += kCorrLen;
+        }
+        return acc;
+    };
+    s_osum[t] = offset_sum(tile0 - 12 + t);
+    if (t < 8) s_osum[kTile + t] = offset_sum(tile0 - 12 + kTile + t);
+    __syncthreads();
+    const int w = tile0 - 4 + t;
+    if (w >= a.n_new) return;
+    unsigned out = 0;
+    const long long n = a.seen + w;
+    if (w >= 0 && n >= kCorrLen + 15 && n % kSpb == 6) {
+        // first maximum of the nine sums, oldest first = offset index ascending (decoder.C:207-215); s_osum[t + 8 - k] = osum(w - k)
+        double best = -1.0;
+        int pick = 0;
+#pragma unroll
+        for (int i = 0; i < kSpb; ++i) {
+            const double v = s_osum[t + i];
+            if (v > best) { best = v; pick = i; }
+        }
+        out = (unsigned)pick;
+    }
+    if (w + 4 < a.n_new) {
+        const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY + w;
+        if (window_is_y(y, nullptr)) out |= 0x80u;
+    }
+    a.b.dec[(size_t)ch * pitch_d(a.b.p_max) + kHistD + w] = (uint8_t)out;
+}
+
+// lane = channel, warp = 32 channels.  The decision bytes are staged through shared memory in chunks
+// (coalesced), then every lane runs its own symbol clock over the chunk, one iteration per BIT:
+//   trigger t0 = first sample >= cur whose (n + 1) mod 9 equals the bit-sync offset (decoder.C:83-90);
+//   the samples t0, t0+1, t0+2 are burnt, t0+3 .. t0+7 integrated, the bit is decided at t0+7
+//   (decoder.C:91-135) = the precomputed decision of the window starting at t0+3;
+//   every evaluation sample <= t0+7 has by then updated next_offs (bs_ runs before bd_, decoder.C:57-58).
+constexpr int kChunk = 1152;                      // samples per staged chunk (multiple of 9 and 16)
+constexpr int kChunkBack = 16;                    // bytes kept before the chunk (open windows, late evaluations)
+constexpr int kRowPitch32 = (kChunk + kChunkBack) / 4 + 1;   // odd word pitch: conflict-free column reads
+
+__global__ void __launch_bounds__(32) symbol_clock_kernel(const DemodArgs a) {
+    __shared__ uint32_t s_dec[32 * kRowPitch32];
+    const int lane = threadIdx.x;
+    const int ch0 = blockIdx.x * 32, ch = ch0 + lane;
+    const bool live = ch < a.channels;
+    ChannelState s = {};
+    if (live) s = a.b.state[ch];
+    const float2* y = a.b.y3 + (size_t)(live ? ch : 0) * pitch_y(a.b.p_max) + kHistY;
+    Emit em;
+    em.ev = a.events + (size_t)(live ? ch : 0) * a.ev_cap; em.ev_cap = a.ev_cap; em.n = 0; em.writer = live;
+    int nbits_out = 0;
+    char* bits = a.bits && live ? a.bits + (size_t)ch * a.bit_cap : nullptr;
+    float* disc = a.disc && live ? a.disc + (size_t)ch * a.bit_cap * 4 : nullptr;
+    const uint8_t* my_row = reinterpret_cast<const uint8_t*>(s_dec + lane * kRowPitch32);
+
+    // first evaluation sample of this block: absolute index >= 582 and == 6 (mod 9)  (decoder.C:204)
+    int next_eval;
+    {
+        long long e = kCorrLen + 15 - a.seen;
+        if (e < 0) e = 0;
+        const int r = (int)((a.seen + e) % kSpb);
+        e += (6 - r + kSpb) % kSpb;
+        next_eval = e > a.n_new ? a.n_new : (int)e;
+    }
+    const int seen9 = (int)(a.seen % kSpb);
+
+    for (int c0 = 0; c0 < a.n_new; c0 += kChunk) {
+        const int lim = min(a.n_new, c0 + kChunk);
+        // stage rows [c0 - 16, c0 + kChunk) of 32 channels
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            if (ch0 + r >= a.channels) break;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.b.dec + (size_t)(ch0 + r) * pitch_d(a.b.p_max) + kHistD + c0 - kChunkBack);
+            const int words = (lim - c0 + kChunkBack + 3) / 4;
+            for (int k = lane; k < words; k += 32) s_dec[r * kRowPitch32 + k] = src[k];
+        }
+        __syncwarp();
+        auto byte_at = [&](int idx) -> unsigned { return my_row[idx - c0 + kChunkBack]; };
+        auto do_eval = [&](int e) {
+            int pick = (int)(byte_at(e) & 15u);
+            if (s.last_pick != -1 && pick != s.last_pick) {        // slew one step the short way round (decoder.C:217-246)
+                bool up;
+                if (pick > s.last_pick) up = !(pick - s.last_pick > 4);
+                else up = (s.last_pick - pick > 4);
+                pick = up ? (s.last_pick + 1) % kSpb : (s.last_pick - 1 + kSpb) % kSpb;
+            }
+            s.last_pick = pick;
+            const int offs = (pick + 5) % kSpb;                    // decoder.C:249
+            if (s.dstate == DS_INIT) { s.dstate = DS_WAIT; s.offs = offs; s.cur = e; }   // decoder.C:62-70
+            s.next_offs = offs;
+        };
+        while (live) {
+            if (s.dstate == DS_INIT) {
+                if (next_eval >= lim) break;
+                do_eval(next_eval);
+                next_eval += kSpb;
+                if (s.dstate == DS_INIT) continue;
+            }
+            if (s.dstate == DS_WAIT) {
+                const int tick = (seen9 + s.cur + 1) % kSpb;
+                const int t0 = s.cur + (s.offs - tick + kSpb) % kSpb;
+                if (t0 >= a.n_new) break;
+                s.dstate = DS_PENDING;
+                s.pend = t0;
+            }
+            const int td = s.pend + 7;
+            if (td >= lim) break;
+            while (next_eval <= td) { do_eval(next_eval); next_eval += kSpb; }
+            const bool is_y = (byte_at(s.pend + 3) & 0x80u) != 0;
+            if (bits && nbits_out < a.bit_cap) {
+                bits[nbits_out] = is_y ? 'Y' : 'B';
+                if (disc) window_is_y(y + s.pend + 3, disc + 4 * (size_t)nbits_out);
+            }
+            ++nbits_out;
+            s.offs = s.next_offs;
+            s.dstate = DS_WAIT;
+            s.cur = td + 1;
+            fsm_bit(s, em, is_y);
+        }
+        if (lim == a.n_new && live)
+            while (next_eval < a.n_new) { do_eval(next_eval); next_eval += kSpb; }
+    }
+    if (!live) return;
+    if (s.dstate == DS_PENDING) s.pend -= a.n_new;
+    s.cur = s.cur > a.n_new ? s.cur - a.n_new : 0;
+    s.seen = a.seen + a.n_new;
+    a.b.state[ch] = s;
+    a.ev_count[ch] = em.n;
+    if (a.bit_count) a.bit_count[ch] = nbits_out;
+}
+
+// slide every history: the last H entries of [hist | new] become the next block's hist.  One CTA per channel.
+__global__ void __launch_bounds__(256) carry_kernel(const DemodArgs a) {
+    __shared__ double s_c[kHistC];
+    __shared__ float2 s_y[kHistY];
+    const int ch = blockIdx.x, t = threadIdx.x;
+    double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max);
+    float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max);
+    for (int k = t; k < kHistC; k += blockDim.x) s_c[k] = corr[k + a.n_new];
+    if (t < kHistY) s_y[t] = y[t + a.n_new];
+    __syncthreads();
+    for (int k = t; k < kHistC; k += blockDim.x) corr[k] = s_c[k];
+    if (t < kHistY) y[t] = s_y[t];
+}
+
+__global__ void init_state_kernel(ChannelState* st, int channels) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= channels) return;
-    ChannelScalars& s = st[ch].sc;
-    // decoder::decoder (decoder.C:6-39) and byte_state_machine::init (nav_b_sm.C:16-42); rings are zero
+    ChannelState s = {};
+    // decoder::decoder (decoder.C:6-39) and byte_state_machine::init (nav_b_sm.C:16-42)
     s.last_pick = -1;
     s.dstate = DS_INIT;
     s.byte_state = BY_WAIT;
+    st[ch] = s;
 }
 
 }  // namespace
 
-cudaError_t demod_init_state(ChannelState* state, int channels, cudaStream_t stream) {
+int demod_launches_per_block() { return 4; }
+size_t demod_pitch_d(int p_max) { return ((size_t)kHistD + p_max + 15) & ~(size_t)15; }
+
+cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t stream) {
     static bool tables_done = false;
     if (!tables_done) {
         // CCIR 476 tables as (code, letters, figures); see nav_b_sm.h:60-83 -- every other code is invalid '_'.
@@ -341,15 +411,22 @@ cudaError_t demod_init_state(ChannelState* state, int channels, cudaStream_t str
         if ((e = cudaMemcpyToSymbol(c_tone_i, ti, sizeof ti)) != cudaSuccess) return e;
         tables_done = true;
     }
-    cudaError_t e = cudaMemsetAsync(state, 0, sizeof(ChannelState) * (size_t)channels, stream);
-    if (e != cudaSuccess) return e;
-    demod_init_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(state, channels);
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(b.y3, 0, sizeof(float2) * (size_t)channels * (kHistY + b.p_max), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(b.corr, 0, sizeof(double) * (size_t)channels * (kHistC + b.p_max), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(b.dec, 0, (size_t)channels * demod_pitch_d(b.p_max), stream)) != cudaSuccess) return e;
+    init_state_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(b.state, channels);
     return cudaGetLastError();
 }
 
 cudaError_t demod_launch(const DemodArgs& a, cudaStream_t stream) {
     if (a.n_new <= 0 || a.channels <= 0) return cudaSuccess;
-    demod_kernel<<<(a.channels + kWarps - 1) / kWarps, kWarps * 32, 0, stream>>>(a);
+    const dim3 g1((a.n_new + kTile - 1) / kTile, a.channels);
+    angle_corr_kernel<<<g1, kTile, 0, stream>>>(a);
+    const dim3 g2((a.n_new + 4 + kTile - 1) / kTile, a.channels);
+    sum_decide_kernel<<<g2, kTile, 0, stream>>>(a);
+    symbol_clock_kernel<<<(a.channels + 31) / 32, 32, 0, stream>>>(a);
+    carry_kernel<<<a.channels, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

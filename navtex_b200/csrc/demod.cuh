@@ -1,5 +1,5 @@
-// demod.cuh -- per-channel persistent state of the FSK demodulator / bit synchroniser / SITOR-B
-// state machine, and the launch arguments of demod_kernel (demod.cu).
+// demod.cuh -- buffers, per-channel persistent state and launch arguments of the demodulator /
+// bit synchroniser / SITOR-B state machine kernels (demod.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -8,18 +8,23 @@ namespace nvx {
 
 constexpr int kSpb = 9;                 // samples per bit at 900 Hz (decoder.h:21)
 constexpr int kCorrLen = 63 * kSpb;     // 567 (decoder.h:23-24)
-constexpr int kCorrRing = 1024;         // power-of-two time-indexed history >= kCorrLen + 32
 constexpr int kEvAbort = 0x18;          // event byte: message_abort() (nav_b_sm.C:44-52)
 
-// Everything decoder.{h,C} and nav_b_sm.{h,C} keep per channel between samples, re-expressed so
-// that ring positions are functions of the absolute 900 Hz sample count `seen`.
-struct ChannelScalars {
-    double prev_i, prev_q;    // decoder.C:54-55
+// Every per-sample array keeps a short history of the previous block in front of the new samples,
+// so the feed-forward kernels are stateless: element for block-relative sample m lives at [hist + m].
+constexpr int kHistY = 16;              // 900 Hz samples (angle needs 1, mask correlation 8 more, decisions look back 4)
+constexpr int kHistC = 576;             // |mask correlation| values (per-offset sums reach back 566)
+constexpr int kHistO = 16;              // per-offset sums (argmax looks back 8)
+constexpr int kHistD = 16;              // decision bytes (windows that started up to 4 samples before the block)
+
+// What decoder.{h,C} and nav_b_sm.{h,C} keep per channel and that is genuinely sequential.
+struct ChannelState {
     long long seen;           // 900 Hz samples consumed so far
     int last_pick;            // prev_offset (decoder.C:247), -1 = none
-    // mark/space discriminator (decoder.C:73-137)
-    int dstate, offs, next_offs, burned, used;
-    float br, bi, yr, yi;
+    // symbol clock of the mark/space discriminator (decoder.C:73-137), event form:
+    // dstate INIT / WAIT (searching the sample whose tick equals offs, from `cur` on) / PENDING (bit triggered
+    // at sample `pend`, decided 7 samples later); indices are relative to the start of the next block
+    int dstate, offs, next_offs, cur, pend;
     // SITOR-B state machine (nav_b_sm.h:92-116), arrays packed into words
     int match;                // phasing pattern bits matched (status)
     int byte_state, figures, nbits, shift;
@@ -28,34 +33,36 @@ struct ChannelScalars {
     unsigned err_mask;        // bit k set = error_buffer[k] holds an invalid code
     int err_at, err_full, err_count;
     int eoe_count, prev_dx_alpha, holdoff, enabled;
-    int pad_;
 };
 
-struct ChannelState {
-    double corr[kCorrRing];   // |mask correlation| history, value number v at [v & 1023] (decoder.C:170)
-    double ang[8];            // last 8 discriminator angles, oldest first (decoder.C:147)
-    double osum[kSpb];        // per-offset correlation sums (decoder.C:186-190)
-    ChannelScalars sc;
+struct DemodBuffers {
+    float2* y3;               // [channels][kHistY + p_max]   (the cascade kernel writes at +kHistY)
+    double* corr;             // [channels][kHistC + p_max]   |mask correlation| per sample
+    double* osum;             // [channels][kHistO + p_max]   per-offset sum computed at each sample
+    uint8_t* dec;             // [channels][kHistD + p_max]   bit 7: 'Y' decision of the 5-sample window starting here;
+                              //                              low nibble: arg max offset when this is an evaluation sample
+    ChannelState* state;      // [channels]
+    int p_max;
 };
 
 struct DemodArgs {
-    const float2* y3;         // [channels][y3_pitch]
-    long long y3_pitch;
-    long long y3_off;         // first new sample of every channel row
-    int n_new;                // new 900 Hz samples per channel
+    DemodBuffers b;
+    int n_new;                // new 900 Hz samples per channel in this block
     int channels;             // streams * 2
-    ChannelState* state;      // [channels]
+    long long seen;           // 900 Hz samples consumed before this block (same for every channel)
     // per-launch outputs
     uint8_t* events;          // [channels][ev_cap]: appended characters, '\n' = line complete, 0x18 = abort
     int* ev_count;            // [channels]
     int ev_cap;
-    char* bits;               // optional [channels][bit_cap] 'B'/'Y' decisions (debug / parity taps), may be null
+    char* bits;               // optional [channels][bit_cap] 'B'/'Y' decisions (parity taps), may be null
     float* disc;              // optional [channels][bit_cap][4] BR BI YR YI at each decision, may be null
     int* bit_count;           // [channels] (required if bits != null)
     int bit_cap;
 };
 
+size_t demod_pitch_d(int p_max);     // row pitch of DemodBuffers::dec in bytes (16-byte multiple)
 cudaError_t demod_launch(const DemodArgs& a, cudaStream_t stream);
-cudaError_t demod_init_state(ChannelState* state, int channels, cudaStream_t stream);
+cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t stream);
+int demod_launches_per_block();
 
 }  // namespace nvx

@@ -110,8 +110,7 @@ struct nvx_engine {
     float2* tail[2] = {nullptr, nullptr};
     CUtensorMap map_tail[2];
     int tail_cur = 0;
-    float2* y3 = nullptr;
-    nvx::ChannelState* chstate = nullptr;
+    nvx::DemodBuffers db = {};
     uint8_t* d_events = nullptr; int* d_ev_count = nullptr; int ev_cap = 0;
     char* d_bits = nullptr; float* d_disc = nullptr; int* d_bit_count = nullptr; int bit_cap = 0;
     uint8_t* h_events = nullptr; int* h_ev_count = nullptr;
@@ -141,7 +140,7 @@ int free_engine(nvx_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
-    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->y3); cudaFree(e->chstate);
+    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->db.y3); cudaFree(e->db.corr); cudaFree(e->db.dec); cudaFree(e->db.state);
     cudaFree(e->d_events); cudaFree(e->d_ev_count); cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
     cudaFree(e->stage_f32); cudaFree(e->stage_s16);
     cudaFreeHost(e->h_events); cudaFreeHost(e->h_ev_count);
@@ -153,7 +152,7 @@ int free_engine(nvx_engine* e) {
 int reset_state(nvx_engine* e) {
     CU_TRY(cudaMemsetAsync(e->tail[0], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
     CU_TRY(cudaMemsetAsync(e->tail[1], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
-    CU_TRY(nvx::demod_init_state(e->chstate, e->channels, e->stream));
+    CU_TRY(nvx::demod_init_state(e->db, e->channels, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     e->tail_cur = 0;
     e->sb_abs = 0;
@@ -231,15 +230,15 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     if (segs < 1) segs = 1;
     const int seg_super = (n_super + segs - 1) / segs;
     segs = (n_super + seg_super - 1) / seg_super;
-    ca.y3 = e->y3;
+    ca.y3 = e->db.y3;
     ca.n = n;
     ca.streams = e->S;
     ca.segs = segs;
     ca.seg_super = seg_super;
     ca.n_super = n_super;
     ca.sb_phase = (int)(e->sb_abs % kNcoPeriod);
-    ca.y3_pitch = e->P_max;
-    ca.y3_off = 0;
+    ca.y3_pitch = nvx::kHistY + e->P_max;
+    ca.y3_off = nvx::kHistY;
 
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
     if (e->timing) {
@@ -261,8 +260,8 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     e->tail_cur = nxt;
 
     DemodArgs da;
-    da.y3 = e->y3; da.y3_pitch = e->P_max; da.y3_off = 0;
-    da.n_new = n_super; da.channels = e->channels; da.state = e->chstate;
+    da.b = e->db;
+    da.n_new = n_super; da.channels = e->channels; da.seen = e->sb_abs;
     da.events = e->d_events; da.ev_count = e->d_ev_count; da.ev_cap = e->ev_cap;
     da.bits = e->d_bits; da.disc = e->d_disc; da.bit_count = e->d_bit_count; da.bit_cap = e->bit_cap;
     if (e->timing) CU_TRY(cudaEventRecord(t2, e->stream));
@@ -275,7 +274,7 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     e->sb_abs += n_super;
     e->last_P = n_super;
     e->stats.cascade_launches++;
-    e->stats.demod_launches++;
+    e->stats.demod_launches += nvx::demod_launches_per_block();
     e->stats.aux_launches++;
     e->stats.samples += n * e->S;
     return 0;
@@ -353,8 +352,11 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     const size_t tail_bytes = (size_t)e->S * nvx::kHalo * sizeof(float2);
     CREATE_TRY(cudaMalloc(&e->tail[0], tail_bytes));
     CREATE_TRY(cudaMalloc(&e->tail[1], tail_bytes));
-    CREATE_TRY(cudaMalloc(&e->y3, (size_t)e->channels * e->P_max * sizeof(float2)));
-    CREATE_TRY(cudaMalloc(&e->chstate, (size_t)e->channels * sizeof(nvx::ChannelState)));
+    e->db.p_max = e->P_max;
+    CREATE_TRY(cudaMalloc(&e->db.y3, (size_t)e->channels * (nvx::kHistY + e->P_max) * sizeof(float2)));
+    CREATE_TRY(cudaMalloc(&e->db.corr, (size_t)e->channels * (nvx::kHistC + e->P_max) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&e->db.dec, (size_t)e->channels * nvx::demod_pitch_d(e->P_max)));
+    CREATE_TRY(cudaMalloc(&e->db.state, (size_t)e->channels * sizeof(nvx::ChannelState)));
     CREATE_TRY(cudaMalloc(&e->d_events, (size_t)e->channels * e->ev_cap));
     CREATE_TRY(cudaMalloc(&e->d_ev_count, sizeof(int) * e->channels));
     CREATE_TRY(cudaMemset(e->d_ev_count, 0, sizeof(int) * e->channels));
@@ -456,8 +458,8 @@ int nvx_engine_read_y3(nvx_engine* e, float* out, size_t cap_floats, size_t* n_p
     *n_per_channel = P;
     if (cap_floats < (size_t)e->channels * P * 2) return fail(NVX_ERR_ARG, "y3 buffer too small");
     if (P)
-        CU_TRY(cudaMemcpy2D(out, P * sizeof(float2), e->y3, (size_t)e->P_max * sizeof(float2), P * sizeof(float2), (size_t)e->channels,
-                            cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy2D(out, P * sizeof(float2), e->db.y3 + nvx::kHistY, (size_t)(nvx::kHistY + e->P_max) * sizeof(float2),
+                            P * sizeof(float2), (size_t)e->channels, cudaMemcpyDeviceToHost));
     return rc;
 }
 
