@@ -27,6 +27,7 @@
 #include "demod.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace nvx {
 
@@ -357,12 +358,13 @@ __global__ void __launch_bounds__(256) carry_kernel(const DemodArgs a) {
     __shared__ float2 s_y[kHistY];
     const int ch = blockIdx.x, t = threadIdx.x;
     double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max);
-    float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max);
+    const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max);
+    float2* yn = a.y3_next + (size_t)ch * pitch_y(a.b.p_max);
     for (int k = t; k < kHistC; k += blockDim.x) s_c[k] = corr[k + a.n_new];
     if (t < kHistY) s_y[t] = y[t + a.n_new];
     __syncthreads();
     for (int k = t; k < kHistC; k += blockDim.x) corr[k] = s_c[k];
-    if (t < kHistY) y[t] = s_y[t];
+    if (t < kHistY) yn[t] = s_y[t];
 }
 
 __global__ void init_state_kernel(ChannelState* st, int channels) {
@@ -421,10 +423,18 @@ cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t s
 
 cudaError_t demod_launch(const DemodArgs& a, cudaStream_t stream) {
     if (a.n_new <= 0 || a.channels <= 0) return cudaSuccess;
+    // These kernels run beside the NEXT block's cascade kernel.  NVX_DEMOD_THROTTLE=<bytes> asks for that much unused
+    // dynamic shared memory, capping their occupancy in the ~48 KB the cascade leaves free (tuning knob; measured on
+    // B200: throttling speeds the cascade up 10 % but stretches the demod past it, so the default is off).
+    static int throttle = -1;
+    if (throttle < 0) {
+        const char* env = getenv("NVX_DEMOD_THROTTLE");
+        throttle = env ? atoi(env) : 0;
+    }
     const dim3 g1((a.n_new + kTile - 1) / kTile, a.channels);
-    angle_corr_kernel<<<g1, kTile, 0, stream>>>(a);
+    angle_corr_kernel<<<g1, kTile, throttle, stream>>>(a);
     const dim3 g2((a.n_new + 4 + kTile - 1) / kTile, a.channels);
-    sum_decide_kernel<<<g2, kTile, 0, stream>>>(a);
+    sum_decide_kernel<<<g2, kTile, throttle, stream>>>(a);
     symbol_clock_kernel<<<(a.channels + 31) / 32, 32, 0, stream>>>(a);
     carry_kernel<<<a.channels, 256, 0, stream>>>(a);
     return cudaGetLastError();

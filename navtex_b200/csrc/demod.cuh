@@ -46,7 +46,8 @@ struct DemodBuffers {
 };
 
 struct DemodArgs {
-    DemodBuffers b;
+    DemodBuffers b;           // b.y3 = the buffer the cascade kernel filled for this block
+    float2* y3_next;          // buffer of the NEXT block: receives the kHistY-sample history (may equal b.y3)
     int n_new;                // new 900 Hz samples per channel in this block
     int channels;             // streams * 2
     long long seen;           // 900 Hz samples consumed before this block (same for every channel)

@@ -11,7 +11,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/navtex_b200.h"
@@ -59,12 +62,12 @@ int load_encode() {
     return 0;
 }
 
-// float32 view [rows][2 * cols] of a stream-major float2 array; box = one step (56 floats) x 32 rows
+// float32 view [rows][2 * cols] of a stream-major float2 array; box = one stage (kBoxFloats) x 32 rows
 int encode_rows(CUtensorMap* map, const void* base, long long cols, long long rows) {
     if (int rc = load_encode()) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)(2 * cols), (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)(cols * 8)};
-    cuuint32_t box[2] = {(cuuint32_t)(2 * nvx::kStepIn), 32};
+    cuuint32_t box[2] = {(cuuint32_t)nvx::kBoxFloats, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -103,27 +106,41 @@ __global__ void s16_to_f32_kernel(const short2* __restrict__ in, float2* __restr
 
 }  // namespace
 
+constexpr int kBuf = 3;   // blocks in flight: cascade of block i+1/i+2 overlaps demod + event download of block i
+
 struct nvx_engine {
     nvx_config cfg;
     int S = 0, P_max = 0, channels = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // cascade, tail carry, ingest copies / conversion
+    cudaStream_t stream_demod = nullptr;  // demod kernels + event download, one block behind
+    float2* y3buf[kBuf] = {};
+    cudaEvent_t casc_done[kBuf] = {}, demod_done[kBuf] = {};
+    long long blocks = 0;
+    int last_buf = 0;
     float2* tail[2] = {nullptr, nullptr};
     CUtensorMap map_tail[2];
     int tail_cur = 0;
     nvx::DemodBuffers db = {};
-    uint8_t* d_events = nullptr; int* d_ev_count = nullptr; int ev_cap = 0;
+    uint8_t* d_events[kBuf] = {}; int* d_ev_count[kBuf] = {}; int ev_cap = 0;
     char* d_bits = nullptr; float* d_disc = nullptr; int* d_bit_count = nullptr; int bit_cap = 0;
-    uint8_t* h_events = nullptr; int* h_ev_count = nullptr;
+    uint8_t* h_events[kBuf] = {}; int* h_ev_count[kBuf] = {};
     float2* stage_f32 = nullptr; size_t stage_f32_samples = 0;
     short2* stage_s16 = nullptr; size_t stage_s16_samples = 0;
     long long sb_abs = 0;
     int last_P = 0;
-    bool events_pending = false, custom_taps = false;
+    bool custom_taps = false;
     int target_warps = 1184;
     nvx::MessageAssembler assembler;
     std::vector<nvx::AssembledMessage> ready, handed;
     std::vector<nvx_message> view;
     nvx_message_cb cb = nullptr; void* cb_user = nullptr;
+    // host-side message assembly runs on a worker thread, one block after the other, off the push path
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    long long queued = 0, drained = 0;      // blocks handed to / finished by the worker
+    bool stop = false;
+    int worker_rc = 0;
     // timing
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -139,12 +156,27 @@ int free_engine(nvx_engine* e) {
     if (!e) return 0;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->stream_demod) cudaStreamSynchronize(e->stream_demod);
+    if (e->worker.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            e->stop = true;
+        }
+        e->cv.notify_all();
+        e->worker.join();
+    }
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
-    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->db.y3); cudaFree(e->db.corr); cudaFree(e->db.dec); cudaFree(e->db.state);
-    cudaFree(e->d_events); cudaFree(e->d_ev_count); cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
+    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->db.corr); cudaFree(e->db.dec); cudaFree(e->db.state);
+    cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
     cudaFree(e->stage_f32); cudaFree(e->stage_s16);
-    cudaFreeHost(e->h_events); cudaFreeHost(e->h_ev_count);
+    for (int k = 0; k < kBuf; ++k) {
+        cudaFree(e->y3buf[k]); cudaFree(e->d_events[k]); cudaFree(e->d_ev_count[k]);
+        cudaFreeHost(e->h_events[k]); cudaFreeHost(e->h_ev_count[k]);
+        if (e->casc_done[k]) cudaEventDestroy(e->casc_done[k]);
+        if (e->demod_done[k]) cudaEventDestroy(e->demod_done[k]);
+    }
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream_demod) cudaStreamDestroy(e->stream_demod);
     delete e;
     return 0;
 }
@@ -152,12 +184,21 @@ int free_engine(nvx_engine* e) {
 int reset_state(nvx_engine* e) {
     CU_TRY(cudaMemsetAsync(e->tail[0], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
     CU_TRY(cudaMemsetAsync(e->tail[1], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
-    CU_TRY(nvx::demod_init_state(e->db, e->channels, e->stream));
+    for (int k = 0; k < kBuf; ++k) {
+        e->db.y3 = e->y3buf[k];
+        CU_TRY(nvx::demod_init_state(e->db, e->channels, e->stream));
+    }
     CU_TRY(cudaStreamSynchronize(e->stream));
     e->tail_cur = 0;
     e->sb_abs = 0;
     e->last_P = 0;
-    e->events_pending = false;
+    e->blocks = 0;
+    e->last_buf = 0;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->queued = e->drained = 0;
+        e->worker_rc = 0;
+    }
     e->assembler.reset();
     e->ready.clear();
     return 0;
@@ -172,41 +213,93 @@ cudaEvent_t next_event(nvx_engine* e) {
     return e->ev_pool[e->ev_used++];
 }
 
-// host half: run after the stream is idle
-int drain_events(nvx_engine* e) {
-    if (e->timing && !e->spans.empty()) {
-        for (const auto& sp : e->spans) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, e->ev_pool[sp.a], e->ev_pool[sp.b]);
-            if (sp.kind == 0) e->stats.cascade_ms += ms; else e->stats.demod_ms += ms;
-        }
-        e->spans.clear();
-        e->ev_used = 0;
+void collect_spans(nvx_engine* e) {
+    if (!e->timing || e->spans.empty()) return;
+    for (const auto& sp : e->spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->ev_pool[sp.a], e->ev_pool[sp.b]);
+        if (sp.kind == 0) e->stats.cascade_ms += ms; else e->stats.demod_ms += ms;
     }
-    if (!e->events_pending) return 0;
-    e->events_pending = false;
+    e->spans.clear();
+    e->ev_used = 0;
+}
+
+// host half of one block (worker thread): wait for its demod_done event, then assemble messages
+int drain_events(nvx_engine* e, int b) {
     int rc = 0;
+    std::vector<nvx::AssembledMessage> out;
     for (int ch = 0; ch < e->channels; ++ch) {
-        int n = e->h_ev_count[ch];
-        if (n > e->ev_cap) { n = e->ev_cap; rc = fail(NVX_ERR_OVERFLOW, "event buffer overflow on channel %d", ch); }
+        int n = e->h_ev_count[b][ch];
+        if (n > e->ev_cap) { n = e->ev_cap; rc = NVX_ERR_OVERFLOW; }
         if (n > 0)
-            e->assembler.feed(ch, e->cfg.first_stream_id + ch / 2, e->cfg.freq_tag[ch & 1], e->h_events + (size_t)ch * e->ev_cap,
-                              (size_t)n, &e->ready);
+            e->assembler.feed(ch, e->cfg.first_stream_id + ch / 2, e->cfg.freq_tag[ch & 1], e->h_events[b] + (size_t)ch * e->ev_cap,
+                              (size_t)n, &out);
     }
-    if (e->cb) {
-        for (auto& m : e->ready) {
-            std::string b = m.bbbb, t = m.text;
-            e->cb(e->cb_user, m.stream, &b[0], &t[0], m.freq);
-        }
-        e->ready.clear();
+    if (!out.empty()) {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (auto& m : out) e->ready.push_back(std::move(m));
     }
     return rc;
+}
+
+void worker_main(nvx_engine* e) {
+    cudaSetDevice(e->cfg.device);
+    for (;;) {
+        long long blk;
+        {
+            std::unique_lock<std::mutex> lk(e->mu);
+            e->cv.wait(lk, [&] { return e->stop || e->drained < e->queued; });
+            if (e->drained >= e->queued) return;      // stop requested and nothing left
+            blk = e->drained;
+        }
+        const int b = (int)(blk % kBuf);
+        int rc = 0;
+        if (cudaEventSynchronize(e->demod_done[b]) != cudaSuccess) rc = NVX_ERR_CUDA;
+        else rc = drain_events(e, b);
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            if (rc && !e->worker_rc) e->worker_rc = rc;
+            e->drained = blk + 1;
+        }
+        e->cv.notify_all();
+    }
+}
+
+// wait until the worker has drained every block up to (not including) `upto`
+void wait_drained(nvx_engine* e, long long upto) {
+    std::unique_lock<std::mutex> lk(e->mu);
+    e->cv.wait(lk, [&] { return e->drained >= upto; });
+}
+
+void deliver_callbacks(nvx_engine* e) {
+    if (!e->cb) return;
+    std::vector<nvx::AssembledMessage> take;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        take.swap(e->ready);
+    }
+    for (auto& m : take) {
+        std::string bb = m.bbbb, t = m.text;
+        e->cb(e->cb_user, m.stream, &bb[0], &t[0], m.freq);
+    }
 }
 
 int sync_engine(nvx_engine* e) {
     CU_TRY(cudaSetDevice(e->cfg.device));
     CU_TRY(cudaStreamSynchronize(e->stream));
-    return drain_events(e);
+    CU_TRY(cudaStreamSynchronize(e->stream_demod));
+    collect_spans(e);
+    wait_drained(e, e->blocks);
+    deliver_callbacks(e);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        rc = e->worker_rc;
+        e->worker_rc = 0;
+    }
+    if (rc == NVX_ERR_OVERFLOW) return fail(rc, "an event buffer overflowed");
+    if (rc) return fail(rc, "event download failed");
+    return 0;
 }
 
 int process_block(nvx_engine* e, const float2* d_x, long long n) {
@@ -214,9 +307,12 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     if (n <= 0 || n % kSuper != 0) return fail(NVX_ERR_ARG, "block length %lld is not a positive multiple of %d", n, kSuper);
     if (n > e->cfg.max_block) return fail(NVX_ERR_ARG, "block length %lld exceeds max_block %lld", n, e->cfg.max_block);
     if (((uintptr_t)d_x & 15) != 0) return fail(NVX_ERR_ARG, "device block is not 16-byte aligned");
-    if (e->events_pending) {
-        int rc = sync_engine(e);
-        if (rc && rc != NVX_ERR_OVERFLOW) return rc;
+    const int b = (int)(e->blocks % kBuf);
+    wait_drained(e, e->blocks - kBuf + 1);          // block (blocks - kBuf) used these buffers: long finished, normally
+    if (e->timing && e->ev_used > 4000) {            // bound the event pool in long timed runs
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream_demod));
+        collect_spans(e);
     }
     CascadeArgs ca;
     if (int rc = encode_rows(&ca.map_x, d_x, n, e->S)) return rc;
@@ -224,13 +320,13 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     const int n_super = (int)(n / kSuper);
     const int groups = (e->S + 31) / 32;
     // time segments: enough warps to fill the machine once, but keep the 7-superblock warm-up small
-    int segs = (e->target_warps + groups / 2) / groups;
+    int segs = e->target_warps / groups;            // never more warps than are resident at once (no second wave)
     const int min_seg = 63;
     if (segs > n_super / min_seg) segs = n_super / min_seg;
     if (segs < 1) segs = 1;
     const int seg_super = (n_super + segs - 1) / segs;
     segs = (n_super + seg_super - 1) / seg_super;
-    ca.y3 = e->db.y3;
+    ca.y3 = e->y3buf[b];
     ca.n = n;
     ca.streams = e->S;
     ca.segs = segs;
@@ -259,18 +355,33 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     }
     e->tail_cur = nxt;
 
+    CU_TRY(cudaEventRecord(e->casc_done[b], e->stream));
+
+    // demod of this block runs on its own stream, overlapping the next block's cascade
     DemodArgs da;
     da.b = e->db;
+    da.b.y3 = e->y3buf[b];
+    da.y3_next = e->y3buf[(b + 1) % kBuf];
     da.n_new = n_super; da.channels = e->channels; da.seen = e->sb_abs;
-    da.events = e->d_events; da.ev_count = e->d_ev_count; da.ev_cap = e->ev_cap;
+    da.events = e->d_events[b]; da.ev_count = e->d_ev_count[b]; da.ev_cap = e->ev_cap;
     da.bits = e->d_bits; da.disc = e->d_disc; da.bit_count = e->d_bit_count; da.bit_cap = e->bit_cap;
-    if (e->timing) CU_TRY(cudaEventRecord(t2, e->stream));
-    CU_TRY(demod_launch(da, e->stream));
-    if (e->timing) CU_TRY(cudaEventRecord(t3, e->stream));
-
-    CU_TRY(cudaMemcpyAsync(e->h_ev_count, e->d_ev_count, sizeof(int) * e->channels, cudaMemcpyDeviceToHost, e->stream));
-    CU_TRY(cudaMemcpyAsync(e->h_events, e->d_events, (size_t)e->channels * e->ev_cap, cudaMemcpyDeviceToHost, e->stream));
-    e->events_pending = true;
+    CU_TRY(cudaStreamWaitEvent(e->stream_demod, e->casc_done[b], 0));
+    if (e->timing) CU_TRY(cudaEventRecord(t2, e->stream_demod));
+    CU_TRY(demod_launch(da, e->stream_demod));
+    if (e->timing) CU_TRY(cudaEventRecord(t3, e->stream_demod));
+    CU_TRY(cudaMemcpyAsync(e->h_ev_count[b], e->d_ev_count[b], sizeof(int) * e->channels, cudaMemcpyDeviceToHost, e->stream_demod));
+    CU_TRY(cudaMemcpyAsync(e->h_events[b], e->d_events[b], (size_t)e->channels * e->ev_cap, cudaMemcpyDeviceToHost, e->stream_demod));
+    CU_TRY(cudaEventRecord(e->demod_done[b], e->stream_demod));
+    // the next block's cascade may overwrite neither this block's input staging nor (two blocks on) its y3
+    // buffer before the demod has consumed them: the staging buffers are only touched on e->stream (ordered),
+    // the y3 buffer is protected by the demod_done wait above
+    e->last_buf = b;
+    e->blocks++;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->queued = e->blocks;
+    }
+    e->cv.notify_all();
     e->sb_abs += n_super;
     e->last_P = n_super;
     e->stats.cascade_launches++;
@@ -348,26 +459,38 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
             return e__ == cudaErrorMemoryAllocation ? NVX_ERR_NOMEM : NVX_ERR_CUDA;                           \
         }                                                                                                     \
     } while (0)
-    CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    {   // the short demod kernels of block i get the leftover SM resources first while block i+1's cascade runs
+        int lo = 0, hi = 0;
+        CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CREATE_TRY(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, lo));
+        CREATE_TRY(cudaStreamCreateWithPriority(&e->stream_demod, cudaStreamNonBlocking, hi));
+    }
+    for (int k = 0; k < kBuf; ++k) {
+        CREATE_TRY(cudaEventCreateWithFlags(&e->casc_done[k], cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&e->demod_done[k], cudaEventDisableTiming));
+    }
     const size_t tail_bytes = (size_t)e->S * nvx::kHalo * sizeof(float2);
     CREATE_TRY(cudaMalloc(&e->tail[0], tail_bytes));
     CREATE_TRY(cudaMalloc(&e->tail[1], tail_bytes));
     e->db.p_max = e->P_max;
-    CREATE_TRY(cudaMalloc(&e->db.y3, (size_t)e->channels * (nvx::kHistY + e->P_max) * sizeof(float2)));
+    for (int k = 0; k < kBuf; ++k) CREATE_TRY(cudaMalloc(&e->y3buf[k], (size_t)e->channels * (nvx::kHistY + e->P_max) * sizeof(float2)));
     CREATE_TRY(cudaMalloc(&e->db.corr, (size_t)e->channels * (nvx::kHistC + e->P_max) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&e->db.dec, (size_t)e->channels * nvx::demod_pitch_d(e->P_max)));
     CREATE_TRY(cudaMalloc(&e->db.state, (size_t)e->channels * sizeof(nvx::ChannelState)));
-    CREATE_TRY(cudaMalloc(&e->d_events, (size_t)e->channels * e->ev_cap));
-    CREATE_TRY(cudaMalloc(&e->d_ev_count, sizeof(int) * e->channels));
-    CREATE_TRY(cudaMemset(e->d_ev_count, 0, sizeof(int) * e->channels));
+    for (int k = 0; k < kBuf; ++k) {
+        CREATE_TRY(cudaMalloc(&e->d_events[k], (size_t)e->channels * e->ev_cap));
+        CREATE_TRY(cudaMalloc(&e->d_ev_count[k], sizeof(int) * e->channels));
+        CREATE_TRY(cudaMemset(e->d_ev_count[k], 0, sizeof(int) * e->channels));
+        CREATE_TRY(cudaMallocHost(&e->h_events[k], (size_t)e->channels * e->ev_cap));
+        CREATE_TRY(cudaMallocHost(&e->h_ev_count[k], sizeof(int) * e->channels));
+        memset(e->h_ev_count[k], 0, sizeof(int) * e->channels);
+    }
     if (cfg->keep_bits) {
         CREATE_TRY(cudaMalloc(&e->d_bits, (size_t)e->channels * e->bit_cap));
         CREATE_TRY(cudaMalloc(&e->d_disc, (size_t)e->channels * e->bit_cap * 4 * sizeof(float)));
         CREATE_TRY(cudaMalloc(&e->d_bit_count, sizeof(int) * e->channels));
         CREATE_TRY(cudaMemset(e->d_bit_count, 0, sizeof(int) * e->channels));
     }
-    CREATE_TRY(cudaMallocHost(&e->h_events, (size_t)e->channels * e->ev_cap));
-    CREATE_TRY(cudaMallocHost(&e->h_ev_count, sizeof(int) * e->channels));
     CREATE_TRY(nvx::cascade_upload_constants(cfg->h1, cfg->h2, cfg->h3, e->stream));
 #undef CREATE_TRY
     for (int k = 0; k < 2; ++k)
@@ -375,6 +498,7 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     e->target_warps = nvx::cascade_target_warps(cfg->device);
     e->assembler.resize(e->channels);
     if (int rc = reset_state(e)) { free_engine(e); return rc; }
+    e->worker = std::thread(worker_main, e);
     *out = e;
     return 0;
 }
@@ -384,7 +508,11 @@ void nvx_engine_destroy(nvx_engine* e) { free_engine(e); }
 int nvx_engine_reset(nvx_engine* e) {
     if (!e) return fail(NVX_ERR_ARG, "null engine");
     CU_TRY(cudaSetDevice(e->cfg.device));
-    CU_TRY(cudaStreamSynchronize(e->stream));
+    sync_engine(e);
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->ready.clear();
+    }
     return reset_state(e);
 }
 
@@ -429,8 +557,11 @@ int nvx_engine_sync(nvx_engine* e) {
 int nvx_engine_poll_messages(nvx_engine* e, const nvx_message** msgs, size_t* count) {
     if (!e || !msgs || !count) return fail(NVX_ERR_ARG, "null argument");
     int rc = sync_engine(e);
-    e->handed.swap(e->ready);
-    e->ready.clear();
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->handed.swap(e->ready);
+        e->ready.clear();
+    }
     e->view.clear();
     for (const auto& m : e->handed) {
         nvx_message v;
@@ -458,7 +589,7 @@ int nvx_engine_read_y3(nvx_engine* e, float* out, size_t cap_floats, size_t* n_p
     *n_per_channel = P;
     if (cap_floats < (size_t)e->channels * P * 2) return fail(NVX_ERR_ARG, "y3 buffer too small");
     if (P)
-        CU_TRY(cudaMemcpy2D(out, P * sizeof(float2), e->db.y3 + nvx::kHistY, (size_t)(nvx::kHistY + e->P_max) * sizeof(float2),
+        CU_TRY(cudaMemcpy2D(out, P * sizeof(float2), e->y3buf[e->last_buf] + nvx::kHistY, (size_t)(nvx::kHistY + e->P_max) * sizeof(float2),
                             P * sizeof(float2), (size_t)e->channels, cudaMemcpyDeviceToHost));
     return rc;
 }
@@ -484,10 +615,10 @@ int nvx_engine_read_events(nvx_engine* e, int stream, int ch, char* ev, size_t c
     if (!e || !ev || !count || stream < 0 || stream >= e->S || ch < 0 || ch > 1) return fail(NVX_ERR_ARG, "bad argument");
     int rc = sync_engine(e);
     const int c = stream * 2 + ch;
-    int n = e->h_ev_count[c];
+    int n = e->h_ev_count[e->last_buf][c];
     if (n > e->ev_cap) n = e->ev_cap;
     if ((size_t)n > cap) return fail(NVX_ERR_ARG, "event buffer too small (%d needed)", n);
-    memcpy(ev, e->h_events + (size_t)c * e->ev_cap, (size_t)n);
+    memcpy(ev, e->h_events[e->last_buf] + (size_t)c * e->ev_cap, (size_t)n);
     *count = (size_t)n;
     return rc;
 }

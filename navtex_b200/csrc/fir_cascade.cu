@@ -7,11 +7,8 @@
 
 namespace nvx {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kStages = 3;
-
 template <bool kImm>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* const wbase = smem + (size_t)warp * (kStages * kStageBytes);
@@ -37,14 +34,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) fir_cascade_kernel(const
     my_super = my_super > a.seg_super ? a.seg_super : my_super;
     if (strm >= a.streams) my_super = 0;          // padding lanes compute on TMA zero fill, store nothing
 
-    const int warp_steps = (kWarmSuper + a.seg_super) * kStepsPerSuper;
+    const int warp_stages = (kWarmSuper + a.seg_super) * (kStepsPerSuper / kStepsPerStage);
     // first input sample of this segment's warm-up, relative to the chunk start (negative = carried tail)
     const long long pos0 = ((long long)first_sb - kWarmSuper) * kSuper;
 
     auto issue = [&](int t, int stage) {
         if (lane == 0) {
             const uint32_t bar = bar0 + 8 * stage;
-            const long long p = pos0 + (long long)t * kStepIn;
+            const long long p = pos0 + (long long)t * kStageIn;
             mbar_arrive_expect_tx(bar, kStageBytes);
             if (p < 0) tma_load_2d(wbase_s + stage * kStageBytes, &a.map_tail, (int)(2 * (p + kHalo)), strm0, bar);
             else       tma_load_2d(wbase_s + stage * kStageBytes, &a.map_x, (int)(2 * p), strm0, bar);
@@ -53,7 +50,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) fir_cascade_kernel(const
 
 #pragma unroll
     for (int s = 0; s < kStages; ++s)
-        if (s < warp_steps) issue(s, s);
+        if (s < warp_stages) issue(s, s);
 
     CascadeState st;
 #pragma unroll
@@ -75,16 +72,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) fir_cascade_kernel(const
 
     float2 y3[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     int r10 = 0, out = -kWarmSuper;
-    for (int t = 0; t < warp_steps; ++t) {
+    for (int t = 0; t < warp_stages; ++t) {
         mbar_wait(bar0 + 8 * stage, parity);
-        const float4* rowp = reinterpret_cast<const float4*>(wbase + stage * kStageBytes + lane * kRowBytes);
-        cascade_step<kImm>(st, rowp, phase, r10, y3);
+        const uint8_t* rowb = wbase + stage * kStageBytes + lane * kRowBytes;
+#pragma unroll
+        for (int u = 0; u < kStepsPerStage; ++u) {
+            cascade_step<kImm>(st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3);
+            phase += 7;
+            if (phase >= kNcoPeriod) phase -= kNcoPeriod;
+        }
         __syncwarp();
-        if (t + kStages < warp_steps) issue(t + kStages, stage);
+        if (t + kStages < warp_stages) issue(t + kStages, stage);
         if (++stage == kStages) { stage = 0; parity ^= 1; }
-        phase += 7;
-        if (phase >= kNcoPeriod) phase -= kNcoPeriod;
-        if (++r10 == kStepsPerSuper) {
+        r10 += kStepsPerStage;
+        if (r10 == kStepsPerSuper) {
             r10 = 0;
             if (out >= 0 && out < my_super) {
                 y3row[out] = y3[0];
@@ -132,12 +133,12 @@ cudaError_t cascade_upload_constants(const double* h1, const double* h2, const d
 
 // warps that are resident at once across the device: the host sizes the grid to one full wave
 int cascade_target_warps(int device) {
-    int sms = 148, per_sm = 2;
+    int sms = 148, per_sm = kCtasPerSm;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaFuncSetAttribute(fir_cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cascade_smem_bytes());
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_cascade_kernel<true>, kWarpsPerCta * 32,
                                                       cascade_smem_bytes()) != cudaSuccess || per_sm < 1)
-        per_sm = 2;
+        per_sm = kCtasPerSm;
     return sms * per_sm * kWarpsPerCta;
 }
 

@@ -40,8 +40,39 @@ constexpr int kStepsPerSuper = NVX_D3;             // 10
 constexpr int kWarmSuper = 7;                      // ceil(1901 / 280)
 constexpr int kHalo = kWarmSuper * kSuper;         // 1960 carried input samples per stream
 constexpr int kNcoPeriod = 9;                      // fir2cpp.C:12-14
-constexpr int kRowBytes = kStepIn * 8;             // 224 (the TMA box is dense: row pitch = row bytes)
-constexpr int kStageBytes = 32 * kRowBytes;        // 7168 per warp per stage
+// Tunables (see DESIGN.md "input staging"): how many 28-sample steps one TMA box carries per stream row, how many
+// extra floats pad each row in shared memory (bank-conflict control), ring depth and CTA shape.  Measured on B200
+// (profiles/r1_staging_sweep.md): HBM efficiency of the [32 streams x B bytes] access pattern rises with B
+// (224 B: 6.2 TB/s, 448 B: 6.9 TB/s with no compute at all), the FMA pipe wants the same number of warps on each of
+// the four SM sub-partitions (4 or 8 warps per SM), and the third ring stage matters more than a second warp per
+// sub-partition.  Default: 448-byte rows (+16 B pad), 3 stages, 4 warps, 1 CTA per SM = 178 KB of shared memory,
+// which leaves room for the small demod kernels of the previous block to run alongside.
+#ifndef NVX_STEPS_PER_STAGE
+#define NVX_STEPS_PER_STAGE 2
+#endif
+#ifndef NVX_ROW_PAD_FLOATS
+#define NVX_ROW_PAD_FLOATS 4
+#endif
+#ifndef NVX_STAGES
+#define NVX_STAGES 3
+#endif
+#ifndef NVX_WARPS_PER_CTA
+#define NVX_WARPS_PER_CTA 4
+#endif
+#ifndef NVX_CTAS_PER_SM
+#define NVX_CTAS_PER_SM 1
+#endif
+constexpr int kStepsPerStage = NVX_STEPS_PER_STAGE;
+constexpr int kStageIn = kStepIn * kStepsPerStage;             // input samples per stream per stage
+constexpr int kStepBytes = kStepIn * 8;                        // 224
+constexpr int kBoxFloats = 2 * kStageIn + NVX_ROW_PAD_FLOATS;  // TMA box width (floats); the pad is over-fetched
+constexpr int kRowBytes = kBoxFloats * 4;                      // row pitch in shared memory
+constexpr int kStageBytes = 32 * kRowBytes;                    // per warp per stage
+constexpr int kStages = NVX_STAGES;
+constexpr int kWarpsPerCta = NVX_WARPS_PER_CTA;
+constexpr int kCtasPerSm = NVX_CTAS_PER_SM;
+static_assert(kStepsPerSuper % kStepsPerStage == 0, "a stage must not straddle superblocks");
+static_assert(kRowBytes % 16 == 0 && kStageBytes % 128 == 0, "TMA box alignment");
 constexpr int kLive1 = 9, kLive2 = 6, kLive3 = 8;  // partial sums carried between steps
 
 __device__ constexpr double kH1[NVX_T1] = {NVX_H1_VALUES};

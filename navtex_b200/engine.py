@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnavtex_b200.so")
+LIB_PATH = os.environ.get("NVX_LIB") or os.path.join(_HERE, "libnavtex_b200.so")   # NVX_LIB: tuning variants only
 BLOCK_ALIGN = 280
 FS = 252_000
 
