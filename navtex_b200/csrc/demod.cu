@@ -42,10 +42,13 @@ __constant__ unsigned char c_ltrs[128];
 __constant__ unsigned char c_figs[128];
 __constant__ float c_tone_r[5];
 __constant__ float c_tone_i[5];
+__constant__ double c_tone_rd[5];   // the same tones widened to double
+__constant__ double c_tone_id[5];
 
 struct Emit {
     uint8_t* ev; int* ev_n; int ev_cap; int n;
     bool writer;
+    const unsigned char *ltrs, *figs;      // code tables in shared memory (per-lane indices would serialise the constant cache)
     __device__ __forceinline__ void put(int c) {
         if (writer && n < ev_cap) ev[n] = (uint8_t)c;
         ++n;
@@ -64,12 +67,12 @@ __device__ __forceinline__ void fsm_reset(ChannelState& s) {
 // message_byte_out, nav_b_sm.C:100-145; code 0 = "no valid copy" -> '*'
 __device__ __forceinline__ void fsm_char(ChannelState& s, Emit& e, int code) {
     if (code == 0) { e.put('*'); return; }
-    const int l = c_ltrs[code];
+    const int l = e.ltrs[code];
     if (l == 'l') { s.figures = 0; return; }
     if (l == 'f') { s.figures = 1; return; }
     if (l == 'n') { e.put('\n'); return; }
     if (l == 'r' || l == 'p' || l == 'q') return;
-    e.put(s.figures ? c_figs[code] : l);
+    e.put(s.figures ? e.figs[code] : l);
 }
 
 // message_abort, nav_b_sm.C:44-52: the host decides whether a message was in progress
@@ -97,8 +100,8 @@ __device__ __forceinline__ void fsm_byte(ChannelState& s, Emit& e, int b) {
     } else {                                           // BY_GOT_DX: byte in the RX slot
         if (s.dx_full) {
             const int dx = (s.dx_ring >> (8 * s.dx_at)) & 0x7f;
-            if (c_ltrs[b] != '_') fsm_char(s, e, b);
-            else if (c_ltrs[dx] != '_') fsm_char(s, e, dx);
+            if (e.ltrs[b] != '_') fsm_char(s, e, b);
+            else if (e.ltrs[dx] != '_') fsm_char(s, e, dx);
             else fsm_char(s, e, 0);
         }
         s.byte_state = BY_GOT_RX;
@@ -106,7 +109,7 @@ __device__ __forceinline__ void fsm_byte(ChannelState& s, Emit& e, int b) {
     // 20-byte sliding window of invalid codes (nav_b_sm.C:235-261)
     const unsigned bit = 1u << s.err_at;
     if (s.err_full && (s.err_mask & bit)) s.err_count--;
-    const bool bad = c_ltrs[b] == '_';
+    const bool bad = e.ltrs[b] == '_';
     s.err_mask = bad ? (s.err_mask | bit) : (s.err_mask & ~bit);
     if (bad) s.err_count++;
     if (++s.err_at == 20) { s.err_at = 0; s.err_full = 1; }
@@ -174,24 +177,27 @@ __global__ void __launch_bounds__(kTile) angle_corr_kernel(const DemodArgs a) {
 }
 
 // mark/space decision of the window y[0..4] (decoder.C:109-133).  Returns true for 'Y'.
+// Reference arithmetic per sample: acc = (float)((double)acc + ((double)((float)sR * f_a) +- sI * (double)f_b)).
+// (float)sR is the stored float itself, (float)(-sR) * f = -((float)sR * f) exactly, and the float accumulators are
+// carried as doubles holding float-representable values, so only the four roundings to float cost conversions.
 __device__ __forceinline__ bool window_is_y(const float2* __restrict__ y, float* sums) {
-    float br = 0.f, bi = 0.f, yr = 0.f, yi = 0.f;
+    double br = 0.0, bi = 0.0, yr = 0.0, yi = 0.0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        const double sr = y[k].x, si = y[k].y;
+        const float srf = y[k].x;
+        const double si = (double)y[k].y;
         const float fr = c_tone_r[k], fi = c_tone_i[k];
-        const float srf = (float)sr, nsrf = (float)(-sr);
         const double pr = (double)__fmul_rn(srf, fr), pim = (double)__fmul_rn(srf, fi);
-        const double npim = (double)__fmul_rn(nsrf, fi);
-        const double qi = __dmul_rn(si, (double)fi), qr = __dmul_rn(si, (double)fr);
-        yr = (float)__dadd_rn((double)yr, __dsub_rn(pr, qi));
-        yi = (float)__dadd_rn((double)yi, __dadd_rn(pim, qr));
-        br = (float)__dadd_rn((double)br, __dadd_rn(pr, qi));
-        bi = (float)__dadd_rn((double)bi, __dadd_rn(npim, qr));
+        const double qi = __dmul_rn(si, c_tone_id[k]), qr = __dmul_rn(si, c_tone_rd[k]);
+        yr = (double)(float)__dadd_rn(yr, __dsub_rn(pr, qi));
+        yi = (double)(float)__dadd_rn(yi, __dadd_rn(pim, qr));
+        br = (double)(float)__dadd_rn(br, __dadd_rn(pr, qi));
+        bi = (double)(float)__dadd_rn(bi, __dsub_rn(qr, pim));      // (-pim) + qr
     }
-    if (sums) { sums[0] = br; sums[1] = bi; sums[2] = yr; sums[3] = yi; }
-    const float eb = __fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi));
-    const float ey = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+    const float brf = (float)br, bif = (float)bi, yrf = (float)yr, yif = (float)yi;
+    if (sums) { sums[0] = brf; sums[1] = bif; sums[2] = yrf; sums[3] = yif; }
+    const float eb = __fadd_rn(__fmul_rn(brf, brf), __fmul_rn(bif, bif));
+    const float ey = __fadd_rn(__fmul_rn(yrf, yrf), __fmul_rn(yif, yif));
     return !(eb > ey);
 }
 
@@ -208,22 +214,24 @@ __global__ void __launch_bounds__(kTile) sum_decide_kernel(const DemodArgs a) {
     }
     __syncthreads();
     // per-offset sums for samples [tile0 - 12, tile0 + kTile - 4): thread t -> tile0 - 12 + t (and 8 more by t < 8)
+    const int seen9 = (int)(a.seen % kSpb), seen567 = (int)(a.seen % kCorrLen);
     auto offset_sum = [&](int m) -> double {
-        const long long n = a.seen + m;                      // absolute sample index
-        if (n < kCorrLen + 7 || m >= a.n_new) return 0.0;
+        if (a.seen + m < kCorrLen + 7 || m >= a.n_new) return 0.0;
         // decoder.C:186-190: slots j, j+9, ... in ascending slot order, ring as it stood after this sample's write.
-        // Slot i then held the value written at sample n - ((n - 8 - i) mod 567).
-        const long long v = n - 8;
-        const int j = (int)((v - (kCorrLen - 1)) % kSpb);
-        int d = (int)((v - j) % kCorrLen);
-        const double* base = s_corr + (m - tile0 + kBack);   // -> corr[m]
+        // Slot i then held the value written at sample n - ((n - 8 - i) mod 567), n = seen + m.  In time order that
+        // is: from the slot-j value forward to the newest one (q terms), then from the oldest one forward.
+        // (n - 574) mod 9 and (n - 8 - j) mod 567 in 32-bit arithmetic; m >= -12.
+        const int j = (seen9 + m + 27 - 7) % kSpb;                       // 574 = 63 * 9 + 7; m >= -12
+        const int d0 = (seen567 + m + 2 * kCorrLen - 8 - j) % kCorrLen;   // multiple of 9 away from the newest slot
+        const int q = d0 / kSpb + 1;
+        const double* p = s_corr + (m - tile0 + kBack) - d0;             // slot-j value
         double acc = 0.0;
-#pragma unroll 9
-        for (int k = 0; k < 63; ++k) {
-            acc = __dadd_rn(acc, base[-d]);
-            d -= kSpb;
-            if (d < 0) d += kCorrLen;
-        }
+        int k = 0;
+#pragma unroll 4
+        for (; k < q; ++k) acc = __dadd_rn(acc, p[kSpb * k]);
+        p -= kCorrLen;
+#pragma unroll 4
+        for (; k < 63; ++k) acc = __dadd_rn(acc, p[kSpb * k]);
         return acc;
     };
     s_osum[t] = offset_sum(tile0 - 12 + t);
@@ -232,8 +240,7 @@ __global__ void __launch_bounds__(kTile) sum_decide_kernel(const DemodArgs a) {
     const int w = tile0 - 4 + t;
     if (w >= a.n_new) return;
     unsigned out = 0;
-    const long long n = a.seen + w;
-    if (w >= 0 && n >= kCorrLen + 15 && n % kSpb == 6) {
+    if (w >= 0 && a.seen + w >= kCorrLen + 15 && (seen9 + w) % kSpb == 6) {
         // first maximum of the nine sums, oldest first = offset index ascending (decoder.C:207-215); s_osum[t + 8 - k] = osum(w - k)
         double best = -1.0;
         int pick = 0;
@@ -263,7 +270,9 @@ constexpr int kRowPitch32 = (kChunk + kChunkBack) / 4 + 1;   // odd word pitch: 
 
 __global__ void __launch_bounds__(32) symbol_clock_kernel(const DemodArgs a) {
     __shared__ uint32_t s_dec[32 * kRowPitch32];
+    __shared__ unsigned char s_ltrs[128], s_figs[128];
     const int lane = threadIdx.x;
+    for (int k = lane; k < 128; k += 32) { s_ltrs[k] = c_ltrs[k]; s_figs[k] = c_figs[k]; }
     const int ch0 = blockIdx.x * 32, ch = ch0 + lane;
     const bool live = ch < a.channels;
     ChannelState s = {};
@@ -271,6 +280,7 @@ __global__ void __launch_bounds__(32) symbol_clock_kernel(const DemodArgs a) {
     const float2* y = a.b.y3 + (size_t)(live ? ch : 0) * pitch_y(a.b.p_max) + kHistY;
     Emit em;
     em.ev = a.events + (size_t)(live ? ch : 0) * a.ev_cap; em.ev_cap = a.ev_cap; em.n = 0; em.writer = live;
+    em.ltrs = s_ltrs; em.figs = s_figs;
     int nbits_out = 0;
     char* bits = a.bits && live ? a.bits + (size_t)ch * a.bit_cap : nullptr;
     float* disc = a.disc && live ? a.disc + (size_t)ch * a.bit_cap * 4 : nullptr;
@@ -411,6 +421,10 @@ cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t s
         if ((e = cudaMemcpyToSymbol(c_figs, figs, sizeof figs)) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbol(c_tone_r, tr, sizeof tr)) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbol(c_tone_i, ti, sizeof ti)) != cudaSuccess) return e;
+        double trd[5], tid[5];
+        for (int i = 0; i < 5; ++i) { trd[i] = tr[i]; tid[i] = ti[i]; }
+        if ((e = cudaMemcpyToSymbol(c_tone_rd, trd, sizeof trd)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_tone_id, tid, sizeof tid)) != cudaSuccess) return e;
         tables_done = true;
     }
     cudaError_t e;

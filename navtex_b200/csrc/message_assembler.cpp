@@ -25,6 +25,22 @@ MessageAssembler::~MessageAssembler() {
 void MessageAssembler::resize(int channels) { ch_.assign((size_t)channels, Channel()); }
 void MessageAssembler::reset() { ch_.assign(ch_.size(), Channel()); }
 
+namespace {
+// Necessary conditions of the two patterns, checked before paying for regexec (most lines are plain text):
+// every start-of-message alternative contains three of {Z, C} and is followed by a blank and two digits;
+// every end-of-message alternative contains three N.
+void line_census(const std::string& line, int* zc, int* n, bool* blank, bool* digit) {
+    *zc = *n = 0;
+    *blank = *digit = false;
+    for (char ch : line) {
+        if (ch == 'Z' || ch == 'C') ++*zc;
+        else if (ch == 'N') ++*n;
+        else if (ch == ' ') *blank = true;
+        else if (ch >= '0' && ch <= '9') *digit = true;
+    }
+}
+}  // namespace
+
 // message_line_out, nav_b_sm.C:56-97
 void MessageAssembler::line_done(Channel& c, int stream, int freq, std::vector<AssembledMessage>* out) {
     regmatch_t m[4];
@@ -32,7 +48,10 @@ void MessageAssembler::line_done(Channel& c, int stream, int freq, std::vector<A
         bounded_append(c.text, c.line);
         bounded_append(c.text, "\n");
     }
-    if (regexec(&som_, c.line.c_str(), 4, m, 0) == 0) {
+    int zc, nn;
+    bool blank, digit;
+    line_census(c.line, &zc, &nn, &blank, &digit);
+    if (zc >= 3 && blank && digit && regexec(&som_, c.line.c_str(), 4, m, 0) == 0) {
         c.text.clear();
         bounded_append(c.text, c.line);
         bounded_append(c.text, "\n");
@@ -42,7 +61,7 @@ void MessageAssembler::line_done(Channel& c, int stream, int freq, std::vector<A
         c.bbbb.append(c.line, (size_t)m[3].rm_so, (size_t)(m[3].rm_eo - m[3].rm_so));
         if (c.bbbb.size() > 4) c.bbbb.resize(4);
         c.in_message = true;
-    } else if (regexec(&eom_, c.line.c_str(), 1, m, 0) == 0) {
+    } else if (nn >= 3 && regexec(&eom_, c.line.c_str(), 1, m, 0) == 0) {
         if (c.in_message) out->push_back(AssembledMessage{stream, freq, c.bbbb, c.text});
         c.text.clear();
         c.bbbb.clear();
