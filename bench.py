@@ -14,8 +14,9 @@ steps).  Streams are independent: N GPUs = N x 1024 streams, no collective on th
 
 value  = samples processed by all ranks / max-over-ranks device time (CUDA events on the engine stream).
 e2e    = same metric through nvx_engine_push_host_s16 (the reference's own int16 sample format) with
-         pinned HOST buffers: H2D copy, int16->float conversion, both kernels, event download and
-         host message assembly all inside the timed region.
+         pinned HOST buffers: the same captures pushed as consecutive 1.03 s blocks; H2D copy, int16->float
+         conversion, all kernels, event download and host message assembly inside the timed region, and the
+         decoded bulletins checked against what was transmitted.
 --impl reference times the reference's own CPU chain (oracle/_ref/ref_chain, built unmodified from
 the reference sources) on all host cores on a bounded sample of the same workload.
 """
@@ -37,7 +38,8 @@ sys.path.insert(0, ROOT)
 STREAMS_PER_GPU = 1024
 SUPER_PER_BLOCK = 9250              # 900 Hz outputs per stream per step -> n = 2,590,000 samples (10.28 s)
 BLOCK = SUPER_PER_BLOCK * 280
-E2E_BLOCK = 900 * 280               # 1.0 s per stream per host push (1.03 GB of int16 per step)
+E2E_CHUNKS = 10                     # the e2e arm pushes the same captures as 10 consecutive host blocks ...
+E2E_BLOCK = BLOCK // E2E_CHUNKS     # ... of 259,000 samples (1.03 s) per stream: 1.06 GB of int16 per step
 BYTES_PER_SAMPLE = 8.0 + 16.0 / 280 # algorithmic HBM bytes per input IQ sample: float2 in, 2 x float2 per 280 out
 REF_CHAIN = os.path.join(ROOT, "oracle", "_ref", "ref_chain")
 
@@ -272,23 +274,35 @@ def main():
     total_samples = world * S * BLOCK * args.steps
     value = total_samples / (max_ms * 1e-3) / 1e6                     # Msamples/s
 
+    cpu_sample = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = 4 * 252000
+        cpu_sample = [x[k, :n_cpu].round().to(torch.int16).cpu().numpy().reshape(-1) for k in range(min(os.cpu_count() or 1, 16))]
+
     # ---- end to end through the host-buffer C ABI --------------------------------------------------
+    # The same 1024 captures, as the reference's int16 samples in pinned host memory, pushed as consecutive 1.03 s
+    # blocks (step k pushes chunk k mod 10; after the tenth the captures start over, like a new emission).
     ne = E2E_BLOCK
-    host = torch.empty((S, ne, 2), dtype=torch.int16).pin_memory()
-    host.copy_(x[:, :ne].round().to(torch.int16).cpu())
+    assert ne % 280 == 0 and ne * E2E_CHUNKS == BLOCK
+    host = torch.empty((E2E_CHUNKS, S, ne, 2), dtype=torch.int16).pin_memory()
+    for k in range(E2E_CHUNKS):
+        host[k].copy_(x[:, k * ne:(k + 1) * ne].round().to(torch.int16))
+    del x
+    torch.cuda.empty_cache()
     e2e_eng = engine.Engine(S, ne, device=local, first_stream_id=rank * S)
     e2s = torch.cuda.ExternalStream(e2e_eng.stream, device=device)
-    for _ in range(max(3, args.warmup)):
-        e2e_eng.push_host_ptr(host.data_ptr(), ne, s16=True)
+    warm = E2E_CHUNKS * max(1, (max(3, args.warmup) + E2E_CHUNKS - 1) // E2E_CHUNKS)     # whole captures, so step 0 starts one
+    for k in range(warm):
+        e2e_eng.push_host_ptr(host[k % E2E_CHUNKS].data_ptr(), ne, s16=True)
         e2e_eng.poll_messages()
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     a0.record(e2s)
-    n_e2e_msgs = 0
-    for _ in range(args.steps):
-        e2e_eng.push_host_ptr(host.data_ptr(), ne, s16=True)
-        n_e2e_msgs += len(e2e_eng.poll_messages())                    # D2H of the events + host assembly: the step's result
+    e2e_msgs = []
+    for k in range(args.steps):
+        e2e_eng.push_host_ptr(host[k % E2E_CHUNKS].data_ptr(), ne, s16=True)
+        e2e_msgs += e2e_eng.poll_messages()                           # D2H of the events + host assembly: the step's result
     a1.record(e2s)
     barrier()
     e2e_wall = time.time() - tw0
@@ -297,8 +311,12 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * S * ne * args.steps / float(te.item()) / 1e6
     ev_cap = 2 * (ne // 280 // 63 + 2) + 8
+    e2e_expected = len(expect) * (args.steps // E2E_CHUNKS)
+    expect_set = set(expect)
+    e2e_exact = sum(1 for m in e2e_msgs if (m[0], m[1], m[2], m[3]) in expect_set)
     e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * ne * 4, "d2h_bytes_per_step": 2 * S * (ev_cap + 4),
-           "input": "int16 IQ in pinned host memory, [1024 streams][252000 samples] per step", "ms_per_step": float(te.item()) * 1e3 / args.steps}
+           "input": f"int16 IQ in pinned host memory, [{S} streams][{ne} samples] per step, consecutive blocks of the same captures",
+           "ms_per_step": float(te.item()) * 1e3 / args.steps}
     e2e_eng.close()
 
     if rank != 0:
@@ -313,7 +331,10 @@ def main():
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
-                "kernel": "nvx::fir_cascade_kernel<true>", "kernel_ms": casc_ms, "demod_kernel_ms": st.demod_ms / max(1, st.demod_launches),
+                "kernel": "nvx::fir_cascade_kernel<true>", "kernel_ms": casc_ms,
+                "demod_chain_ms": st.demod_ms / max(1, st.cascade_launches),
+                "demod_stage_ms": dict(zip(("angle_corr", "offset_sum", "carry", "symbol_clock", "bit_decide", "fsm"),
+                                           (v / max(1, st.cascade_launches) for v in st.demod_stage_ms))),
                 "algorithmic_bytes_per_launch": S * BLOCK * BYTES_PER_SAMPLE,
                 "kernel_gsamples_per_s": S * BLOCK / (casc_ms * 1e-3) / 1e9}
 
@@ -322,7 +343,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu = 4 * 252000
-        sample = [x[k, :n_cpu].round().to(torch.int16).cpu().numpy().reshape(-1) for k in range(min(cores, 16))]
+        sample = cpu_sample
         if os.path.exists(REF_CHAIN):
             sps, step_s, n = run_reference_cpu(sample, 2, 10, cores)
             kind = "reference"
@@ -349,7 +370,7 @@ def main():
         "gpu_launches": int(st.cascade_launches + st.demod_launches + st.aux_launches),
         "clocks": clocks,
         "check": {"bulletins_expected_per_step": len(expect), "decoded_exact": decoded_ok, "messages_total": len(msgs), "messages_gathered_all_ranks": gathered,
-                  "e2e_messages": n_e2e_msgs},
+                  "e2e_messages": len(e2e_msgs), "e2e_messages_exact": e2e_exact, "e2e_bulletins_completed_in_timed_steps": e2e_expected},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -107,6 +107,7 @@ typedef struct {
     long long demod_launches;
     long long aux_launches;     /* tail carry, s16 -> f32 conversion */
     long long samples;          /* IQ samples (all streams) pushed */
+    double demod_stage_ms[6];   /* split of demod_ms: angle/correlation, per-offset sums + arg max, history carry | symbol clock, bit decisions, SITOR-B state machine */
 } nvx_stats;
 int nvx_engine_enable_timing(nvx_engine *e, int on);
 int nvx_engine_get_stats(nvx_engine *e, nvx_stats *out, int reset);

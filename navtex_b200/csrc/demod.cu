@@ -11,19 +11,20 @@
 // host (message_assembler.cpp); the last kernel emits the character/line/abort event stream they
 // consume.
 //
-// The reference interleaves everything per sample, but almost all of it is feed-forward in time.
-// Three kernels per block:
-//   angle_corr_kernel   thread = sample: FP64 angle of y[n] conj(y[n-1]) and the 9-tap transition
-//                       mask correlation, in the reference's operation order;
-//   sum_decide_kernel   thread = sample: the 63-term per-offset sum "as the 567-ring stood at that
-//                       sample" (same ascending-slot summation order), the first-maximum arg max over
-//                       the nine sums at evaluation samples, and -- for EVERY possible bit start --
-//                       the mark/space decision of the 5-sample window starting there, with the
-//                       reference's mixed float/double accumulator arithmetic (_rn intrinsics, no
-//                       FMA contraction).  One byte per sample comes out;
-//   symbol_clock_kernel thread = channel: the only truly sequential part -- slew-limited offset
-//                       tracking, the WAIT/BIT_START/RECEIVING symbol clock (which merely selects
-//                       which precomputed decision is a bit), and the byte state machine.
+// The reference interleaves everything per sample, but almost all of it is feed-forward in time.  Per block:
+//   angle_corr_kernel   thread = sample: FP64 angle of y[n] conj(y[n-1]) and the 9-tap transition mask
+//                       correlation, in the reference's operation order;
+//   offset_sum_kernel   thread = (channel, ring revolution, offset class): the 63-term per-offset sums "as the
+//                       567-ring stood at that sample" in the reference's summation order, and the first-maximum
+//                       arg max over the nine sums at every evaluation sample (nine neighbouring lanes);
+//   symbol_clock_kernel lane = channel: the slew-limited offset tracking and the WAIT / BIT_START / RECEIVING
+//                       symbol clock in event form -- it only decides WHICH five samples make up each bit;
+//   bit_decide_kernel   thread = bit: the mark/space decision of that window with the reference's mixed
+//                       float/double accumulator arithmetic (_rn intrinsics, no FMA contraction);
+//   fsm_kernel          lane = channel: the SITOR-B byte state machine over the block's bits.
+// The two lane-per-channel kernels are latency-bound and tiny (64 warps for 2048 channels); they are shaped as
+// 16-warp CTAs with a shared-memory footprint that cannot share an SM with the cascade kernel, so that they run on
+// the few SMs the cascade grid leaves free instead of fighting its single warp per SM sub-partition.
 #include "demod.cuh"
 
 #include <math.h>
@@ -33,7 +34,9 @@ namespace nvx {
 
 namespace {
 
-constexpr int kTile = 256;
+constexpr int kThreads = 128;           // feed-forward kernels: one warp per SM sub-partition
+constexpr int kPer = 3;                 // samples per thread (independent dependency chains)
+constexpr int kTile = kThreads * kPer;  // samples per CTA
 
 enum { DS_INIT = 0, DS_WAIT = 1, DS_PENDING = 2 };   // decoder.h:16-19 (BIT_START / RECEIVING folded into PENDING)
 enum { BY_WAIT = 1, BY_GOT_DX = 2, BY_GOT_RX = 3 };                       // nav_b_sm.h:41-43
@@ -56,7 +59,7 @@ struct Emit {
 };
 
 // byte_state_machine::init, nav_b_sm.C:16-42 (the error ring contents survive, only its counters reset)
-__device__ __forceinline__ void fsm_reset(ChannelState& s) {
+__device__ __forceinline__ void fsm_reset(FsmState& s) {
     s.match = 0; s.byte_state = BY_WAIT; s.figures = 0; s.nbits = 0;
     s.dx_at = 0; s.dx_full = 0;
     s.err_count = 0; s.err_at = 0; s.err_full = 0;
@@ -65,7 +68,7 @@ __device__ __forceinline__ void fsm_reset(ChannelState& s) {
 }
 
 // message_byte_out, nav_b_sm.C:100-145; code 0 = "no valid copy" -> '*'
-__device__ __forceinline__ void fsm_char(ChannelState& s, Emit& e, int code) {
+__device__ __forceinline__ void fsm_char(FsmState& s, Emit& e, int code) {
     if (code == 0) { e.put('*'); return; }
     const int l = e.ltrs[code];
     if (l == 'l') { s.figures = 0; return; }
@@ -76,13 +79,13 @@ __device__ __forceinline__ void fsm_char(ChannelState& s, Emit& e, int code) {
 }
 
 // message_abort, nav_b_sm.C:44-52: the host decides whether a message was in progress
-__device__ __forceinline__ void fsm_abort(ChannelState& s, Emit& e) {
+__device__ __forceinline__ void fsm_abort(FsmState& s, Emit& e) {
     e.put(kEvAbort);
     fsm_reset(s);
 }
 
 // receive_rxdx_byte, nav_b_sm.C:150-262
-__device__ __forceinline__ void fsm_byte(ChannelState& s, Emit& e, int b) {
+__device__ __forceinline__ void fsm_byte(FsmState& s, Emit& e, int b) {
     if (s.byte_state == BY_WAIT) {
         if (b == 0x07) s.byte_state = BY_GOT_RX;
         if (b == 0x4c) s.byte_state = BY_GOT_DX;
@@ -120,7 +123,7 @@ __device__ __forceinline__ void fsm_byte(ChannelState& s, Emit& e, int b) {
 }
 
 // receive_bit, nav_b_sm.C:266-634.  is_y: 'Y' (=1) else 'B'.
-__device__ __forceinline__ void fsm_bit(ChannelState& s, Emit& e, bool is_y) {
+__device__ __forceinline__ void fsm_bit(FsmState& s, Emit& e, bool is_y) {
     if (s.enabled) {
         s.shift = ((s.shift << 1) | (is_y ? 1 : 0)) & 0x7f;
         if (++s.nbits == 7) {
@@ -145,8 +148,9 @@ __device__ __forceinline__ void fsm_bit(ChannelState& s, Emit& e, bool is_y) {
 
 
 __device__ __forceinline__ size_t pitch_y(int p_max) { return (size_t)kHistY + p_max; }
-__device__ __forceinline__ size_t pitch_c(int p_max) { return (size_t)kHistC + p_max; }
-__device__ __forceinline__ size_t pitch_d(int p_max) { return ((size_t)kHistD + p_max + 15) & ~(size_t)15; }
+__device__ __forceinline__ size_t pitch_c(int p_max) { return (size_t)kHistC + p_max + kPadC; }
+__host__ __device__ __forceinline__ size_t pitch_p(int p_max) { return ((size_t)p_max / kSpb + 2 + 15) & ~(size_t)15; }   // picks (bytes)
+__host__ __device__ __forceinline__ size_t pitch_b(int p_max) { return ((size_t)p_max / kSpb + 8 + 15) & ~(size_t)15; }   // bits (elements)
 
 // decoder.C:48-52
 __device__ __forceinline__ double angle_of(float2 cur, float2 prev) {
@@ -156,24 +160,33 @@ __device__ __forceinline__ double angle_of(float2 cur, float2 prev) {
     return atan2(im, re);
 }
 
-// grid (tiles, channels), block kTile: |mask correlation| for samples [tile0, tile0 + kTile)
-__global__ void __launch_bounds__(kTile) angle_corr_kernel(const DemodArgs a) {
+// grid (tiles, channels), block kThreads: |mask correlation| for samples [tile0, tile0 + kTile); every thread owns three
+// samples (strided by kThreads) so that one resident warp per SM sub-partition still has independent work in flight
+__global__ void __launch_bounds__(kThreads) angle_corr_kernel(const DemodArgs a) {
     __shared__ double s_ang[kTile + 8];
     const int ch = blockIdx.y, tile0 = blockIdx.x * kTile, t = threadIdx.x;
     const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY;     // y[m], m >= -kHistY
-    const int m = tile0 + t;
-    if (m < a.n_new) s_ang[8 + t] = angle_of(y[m], y[m - 1]);
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        const int m = tile0 + t + u * kThreads;
+        if (m < a.n_new) s_ang[8 + t + u * kThreads] = angle_of(y[m], y[m - 1]);
+    }
     if (t < 8) s_ang[t] = angle_of(y[tile0 - 8 + t], y[tile0 - 9 + t]);
     __syncthreads();
-    if (m >= a.n_new) return;
-    // mask {0,1,1,1,0,-1,-1,-1,0} over angles n-8 .. n, oldest first (decoder.C:161-170); s_ang[8 + t - k] = angle[m - k]
-    double c = s_ang[t + 1];
-    c = __dadd_rn(c, s_ang[t + 2]);
-    c = __dadd_rn(c, s_ang[t + 3]);
-    c = __dsub_rn(c, s_ang[t + 5]);
-    c = __dsub_rn(c, s_ang[t + 6]);
-    c = __dsub_rn(c, s_ang[t + 7]);
-    a.b.corr[(size_t)ch * pitch_c(a.b.p_max) + kHistC + m] = fabs(c);
+    double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        const int i = t + u * kThreads, m = tile0 + i;
+        if (m >= a.n_new) break;
+        // mask {0,1,1,1,0,-1,-1,-1,0} over angles n-8 .. n, oldest first (decoder.C:161-170); s_ang[8 + i - k] = angle[m - k]
+        double c = s_ang[i + 1];
+        c = __dadd_rn(c, s_ang[i + 2]);
+        c = __dadd_rn(c, s_ang[i + 3]);
+        c = __dsub_rn(c, s_ang[i + 5]);
+        c = __dsub_rn(c, s_ang[i + 6]);
+        c = __dsub_rn(c, s_ang[i + 7]);
+        corr[m] = fabs(c);
+    }
 }
 
 // mark/space decision of the window y[0..4] (decoder.C:109-133).  Returns true for 'Y'.
@@ -201,116 +214,167 @@ __device__ __forceinline__ bool window_is_y(const float2* __restrict__ y, float*
     return !(eb > ey);
 }
 
-// grid (tiles, channels), block kTile: one decision byte for samples w in [tile0 - 4, tile0 + kTile - 4)
-__global__ void __launch_bounds__(kTile) sum_decide_kernel(const DemodArgs a) {
-    constexpr int kBack = kCorrLen - 1 + 12;                 // corr history one tile needs before tile0
-    __shared__ double s_corr[kBack + kTile];
-    __shared__ double s_osum[kTile + 8];
-    const int ch = blockIdx.y, tile0 = blockIdx.x * kTile, t = threadIdx.x;
-    const double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC;      // corr[m], m >= -kHistC
-    for (int k = t; k < kBack + kTile; k += kTile) {
-        const int m = tile0 - kBack + k;
-        s_corr[k] = (m >= -kHistC && m < a.n_new) ? corr[m] : 0.0;
-    }
-    __syncthreads();
-    // per-offset sums for samples [tile0 - 12, tile0 + kTile - 4): thread t -> tile0 - 12 + t (and 8 more by t < 8)
-    const int seen9 = (int)(a.seen % kSpb), seen567 = (int)(a.seen % kCorrLen);
-    auto offset_sum = [&](int m) -> double {
-        if (a.seen + m < kCorrLen + 7 || m >= a.n_new) return 0.0;
-        // decoder.C:186-190: slots j, j+9, ... in ascending slot order, ring as it stood after this sample's write.
-        // Slot i then held the value written at sample n - ((n - 8 - i) mod 567), n = seen + m.  In time order that
-        // is: from the slot-j value forward to the newest one (q terms), then from the oldest one forward.
-        // (n - 574) mod 9 and (n - 8 - j) mod 567 in 32-bit arithmetic; m >= -12.
-        const int j = (seen9 + m + 27 - 7) % kSpb;                       // 574 = 63 * 9 + 7; m >= -12
-        const int d0 = (seen567 + m + 2 * kCorrLen - 8 - j) % kCorrLen;   // multiple of 9 away from the newest slot
-        const int q = d0 / kSpb + 1;
-        const double* p = s_corr + (m - tile0 + kBack) - d0;             // slot-j value
-        double acc = 0.0;
-        int k = 0;
-#pragma unroll 4
-        for (; k < q; ++k) acc = __dadd_rn(acc, p[kSpb * k]);
-        p -= kCorrLen;
-#pragma unroll 4
-        for (; k < 63; ++k) acc = __dadd_rn(acc, p[kSpb * k]);
-        return acc;
-    };
-    s_osum[t] = offset_sum(tile0 - 12 + t);
-    if (t < 8) s_osum[kTile + t] = offset_sum(tile0 - 12 + kTile + t);
-    __syncthreads();
-    const int w = tile0 - 4 + t;
-    if (w >= a.n_new) return;
-    unsigned out = 0;
-    if (w >= 0 && a.seen + w >= kCorrLen + 15 && (seen9 + w) % kSpb == 6) {
-        // first maximum of the nine sums, oldest first = offset index ascending (decoder.C:207-215); s_osum[t + 8 - k] = osum(w - k)
-        double best = -1.0;
-        int pick = 0;
+// Per-offset sums + arg max (decoder.C:181-215).  At sample n the reference adds up the 63 ring slots j, j + 9, ...
+// (j = (n - 7) mod 9) in ascending slot order, the ring standing as it did after sample n's own write.  Those slots
+// hold one residue class of samples -- the newest written at n - 8 -- and slot order is "from the value in slot j
+// forward in time to the newest, then from the oldest forward".  With K = the 567-sample ring revolution and
+// r = 0..62 the position of the newest class member inside it (n = 16 + 567 K + j + 9 r):
+//     sum(n) = ((cur[0] + ... + cur[r]) + prev[r + 1]) + ... + prev[62],
+// cur[i] = corr[n - 8 - 9 (r - i)] (this revolution), prev[i] = cur[i] one revolution earlier.  The prefix over cur is a
+// running sum along r, so ONE THREAD owns (channel, revolution K, class j), walks r = 0..62 and spends 1 + (62 - r)
+// FP64 adds per sample instead of 63 -- every add in the reference's order, so the sums are bit-identical to a
+// literal transcription.  Seven consecutive r are in flight at once (seven independent DADD chains, each prev[] value
+// loaded once per seven).
+// The arg max taken at evaluation sample n = 24 + 567 K + 9 r compares the sums made at samples n - 8 .. n, which are
+// exactly the nine classes j = 0..8 at the same (K, r): nine neighbouring lanes.  They exchange through a per-warp
+// shared-memory patch; lanes 0..20 then each resolve one (revolution, r) arg max (first maximum wins, j ascending,
+// seed -1.0 as decoder.C:207-215) and store the pick of that evaluation sample.
+// Warp = 3 revolutions x 9 classes (27 lanes); (channel, revolution) pairs are flattened over warps.
+constexpr int kSumWarps = 4;
+constexpr int kGroup = 7;                                  // r values in flight per thread
+__global__ void __launch_bounds__(kSumWarps * 32) offset_sum_kernel(const DemodArgs a, int k_lo, int n_rev) {
+    __shared__ double s_os[kSumWarps][3][kGroup][kSpb];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk = lane / kSpb, j = lane - kk * kSpb;       // lanes 27..31: kk == 3, idle
+    const long long unit = ((long long)blockIdx.x * kSumWarps + warp) * 3 + kk;     // (channel, revolution) pair
+    const bool mine = kk < 3 && unit < (long long)a.channels * n_rev;
+    const int ch = mine ? (int)(unit / n_rev) : 0;
+    const int K = k_lo + (mine ? (int)(unit % n_rev) : 0);
+    // block-relative sample of the evaluation r = 0 of this thread; its class members sit 8 samples earlier
+    const int m_first = (int)(16 + (long long)kCorrLen * K + j - a.seen);
+    const double* cur = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC + (m_first - 8);
+    const double* prev = cur - kCorrLen;
+    // the lane that resolves arg maxima: (revolution kk2, r offset u2) of this warp
+    const int kk2 = lane / kGroup, u2 = lane - kk2 * kGroup;
+    const long long unit2 = ((long long)blockIdx.x * kSumWarps + warp) * 3 + kk2;
+    const bool judge = kk2 < 3 && unit2 < (long long)a.channels * n_rev;
+    const int ch2 = judge ? (int)(unit2 / n_rev) : 0;
+    const int w_first = (int)(24 + (long long)kCorrLen * (k_lo + (judge ? (int)(unit2 % n_rev) : 0)) - a.seen);
+    uint8_t* picks2 = a.b.picks + (size_t)ch2 * pitch_p(a.b.p_max);     // evaluation samples of a block: e0 + 9 q
+
+    double run = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < kCorrLen / kSpb / kGroup; ++g) {
+        const int r0 = g * kGroup;
+        const int m0 = m_first + kSpb * r0;                 // sample of evaluation r0
+        double acc[kGroup];
+        if (mine && m0 < a.n_new) {
 #pragma unroll
-        for (int i = 0; i < kSpb; ++i) {
-            const double v = s_osum[t + i];
-            if (v > best) { best = v; pick = i; }
+            for (int u = 0; u < kGroup; ++u) {
+                run = __dadd_rn(run, __ldg(cur + kSpb * (r0 + u)));
+                acc[u] = run;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kGroup; ++u) acc[u] = 0.0;
         }
-        out = (unsigned)pick;
+        // only groups with a sample inside [-8, n_new) matter (arg max windows reach 8 samples back)
+        if (mine && m0 < a.n_new && m0 + kSpb * (kGroup - 1) >= -8) {
+            const double* p = prev + kSpb * (r0 + 1);
+            double v[kGroup - 1];
+#pragma unroll
+            for (int t = 0; t < kGroup - 1; ++t) v[t] = __ldg(p + kSpb * t);
+#pragma unroll
+            for (int u = 0; u < kGroup - 1; ++u) {
+#pragma unroll
+                for (int t = u; t < kGroup - 1; ++t) acc[u] = __dadd_rn(acc[u], v[t]);
+            }
+            p += kSpb * (kGroup - 1);
+            const int rest = kCorrLen / kSpb - kGroup - r0;   // 56, 49, ..., 0: prev[r0 + 7 .. 62] go to all seven
+#pragma unroll 1
+            for (int i = 0; i < rest; i += kGroup, p += kSpb * kGroup) {
+                double x[kGroup];
+#pragma unroll
+                for (int t = 0; t < kGroup; ++t) x[t] = __ldg(p + kSpb * t);
+#pragma unroll
+                for (int t = 0; t < kGroup; ++t) {
+#pragma unroll
+                    for (int u = 0; u < kGroup; ++u) acc[u] = __dadd_rn(acc[u], x[t]);
+                }
+            }
+        }
+        if (kk < 3) {
+#pragma unroll
+            for (int u = 0; u < kGroup; ++u) {
+                const int m = m0 + kSpb * u;
+                const bool ok = mine && m < a.n_new && a.seen + m >= kCorrLen + 7;     // ring full (decoder.C:181)
+                s_os[warp][kk][u][j] = ok ? acc[u] : 0.0;
+            }
+        }
+        __syncwarp();
+        if (judge) {
+            const int w = w_first + kSpb * (r0 + u2);
+            if (w >= 0 && w < a.n_new && a.seen + w >= kCorrLen + 15) {
+                double best = -1.0;
+                int pick = 0;
+#pragma unroll
+                for (int i = 0; i < kSpb; ++i) {
+                    const double x = s_os[warp][kk2][u2][i];
+                    if (x > best) { best = x; pick = i; }
+                }
+                picks2[w / kSpb] = (uint8_t)pick;
+            }
+        }
+        __syncwarp();
     }
-    if (w + 4 < a.n_new) {
-        const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY + w;
-        if (window_is_y(y, nullptr)) out |= 0x80u;
-    }
-    a.b.dec[(size_t)ch * pitch_d(a.b.p_max) + kHistD + w] = (uint8_t)out;
 }
 
-// lane = channel, warp = 32 channels.  The decision bytes are staged through shared memory in chunks
-// (coalesced), then every lane runs its own symbol clock over the chunk, one iteration per BIT:
-//   trigger t0 = first sample >= cur whose (n + 1) mod 9 equals the bit-sync offset (decoder.C:83-90);
-//   the samples t0, t0+1, t0+2 are burnt, t0+3 .. t0+7 integrated, the bit is decided at t0+7
-//   (decoder.C:91-135) = the precomputed decision of the window starting at t0+3;
-//   every evaluation sample <= t0+7 has by then updated next_offs (bs_ runs before bd_, decoder.C:57-58).
-constexpr int kChunk = 1152;                      // samples per staged chunk (multiple of 9 and 16)
-constexpr int kChunkBack = 16;                    // bytes kept before the chunk (open windows, late evaluations)
-constexpr int kRowPitch32 = (kChunk + kChunkBack) / 4 + 1;   // odd word pitch: conflict-free column reads
+// ---- sequential part --------------------------------------------------------------------------------------------
+// lane = channel, warp = 32 channels, CTA = kSeqWarps warps.  Per-channel byte rows (picks, bit values) are staged
+// through shared memory in chunks, coalesced, with an odd word pitch so that the per-lane reads are conflict free.
+constexpr int kSeqWarps = 16;
+constexpr int kSeqChunk = 256;                                // bytes of every channel's row staged at a time
+constexpr int kSeqPitch = kSeqChunk + 4;                      // 65 words
+constexpr int kSeqSmem = kSeqWarps * 32 * kSeqPitch;          // 133 KB: no room left for a cascade CTA on the same SM
 
-__global__ void __launch_bounds__(32) symbol_clock_kernel(const DemodArgs a) {
-    __shared__ uint32_t s_dec[32 * kRowPitch32];
-    __shared__ unsigned char s_ltrs[128], s_figs[128];
-    const int lane = threadIdx.x;
-    for (int k = lane; k < 128; k += 32) { s_ltrs[k] = c_ltrs[k]; s_figs[k] = c_figs[k]; }
-    const int ch0 = blockIdx.x * 32, ch = ch0 + lane;
-    const bool live = ch < a.channels;
-    ChannelState s = {};
-    if (live) s = a.b.state[ch];
-    const float2* y = a.b.y3 + (size_t)(live ? ch : 0) * pitch_y(a.b.p_max) + kHistY;
-    Emit em;
-    em.ev = a.events + (size_t)(live ? ch : 0) * a.ev_cap; em.ev_cap = a.ev_cap; em.n = 0; em.writer = live;
-    em.ltrs = s_ltrs; em.figs = s_figs;
-    int nbits_out = 0;
-    char* bits = a.bits && live ? a.bits + (size_t)ch * a.bit_cap : nullptr;
-    float* disc = a.disc && live ? a.disc + (size_t)ch * a.bit_cap * 4 : nullptr;
-    const uint8_t* my_row = reinterpret_cast<const uint8_t*>(s_dec + lane * kRowPitch32);
-
-    // first evaluation sample of this block: absolute index >= 582 and == 6 (mod 9)  (decoder.C:204)
-    int next_eval;
-    {
-        long long e = kCorrLen + 15 - a.seen;
-        if (e < 0) e = 0;
-        const int r = (int)((a.seen + e) % kSpb);
-        e += (6 - r + kSpb) % kSpb;
-        next_eval = e > a.n_new ? a.n_new : (int)e;
+__device__ __forceinline__ void stage_rows(uint8_t* s_rows, const uint8_t* src, size_t pitch, int ch0, int channels,
+                                           int c0, int count, int lane) {
+    // rows [ch0, ch0 + 32), bytes [c0, c0 + count) (c0 and the pitch are multiples of 4)
+    __syncwarp();
+    const int words = (count + 3) >> 2;
+    for (int r = 0; r < 32 && ch0 + r < channels; ++r) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(src + (size_t)(ch0 + r) * pitch + c0);
+        uint32_t* d = reinterpret_cast<uint32_t*>(s_rows + r * kSeqPitch);
+        for (int k = lane; k < words; k += 32) d[k] = g[k];
     }
-    const int seen9 = (int)(a.seen % kSpb);
+    __syncwarp();
+}
 
-    for (int c0 = 0; c0 < a.n_new; c0 += kChunk) {
-        const int lim = min(a.n_new, c0 + kChunk);
-        // stage rows [c0 - 16, c0 + kChunk) of 32 channels
-        __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-            if (ch0 + r >= a.channels) break;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.b.dec + (size_t)(ch0 + r) * pitch_d(a.b.p_max) + kHistD + c0 - kChunkBack);
-            const int words = (lim - c0 + kChunkBack + 3) / 4;
-            for (int k = lane; k < words; k += 32) s_dec[r * kRowPitch32 + k] = src[k];
-        }
-        __syncwarp();
-        auto byte_at = [&](int idx) -> unsigned { return my_row[idx - c0 + kChunkBack]; };
-        auto do_eval = [&](int e) {
-            int pick = (int)(byte_at(e) & 15u);
+// Symbol clock, one iteration per BIT:
+//   trigger t0 = first sample >= cur whose (n + 1) mod 9 equals the bit-sync offset (decoder.C:83-90);
+//   the samples t0, t0+1, t0+2 are burnt, t0+3 .. t0+7 integrated, the bit is decided at t0+7 (decoder.C:91-135);
+//   every evaluation sample <= t0+7 has by then updated next_offs (bs_ runs before bd_, decoder.C:57-58).
+// Output: the window start t0+3 of every bit decided in this block.
+__global__ void __launch_bounds__(kSeqWarps * 32) symbol_clock_kernel(const DemodArgs a) {
+    extern __shared__ __align__(16) uint8_t s_seq[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ch0 = (blockIdx.x * kSeqWarps + warp) * 32, ch = ch0 + lane;
+    if (ch0 >= a.channels) return;
+    const bool live = ch < a.channels;
+    uint8_t* rows = s_seq + (size_t)warp * 32 * kSeqPitch;
+    const uint8_t* my_row = rows + lane * kSeqPitch;
+    ClockState s = {};
+    if (live) s = a.b.clock[ch];
+    int* bitpos = a.b.bitpos + (size_t)(live ? ch : 0) * pitch_b(a.b.p_max);
+    const int cap = (int)pitch_b(a.b.p_max);
+    int nb = 0;
+
+    // evaluation samples of this block (decoder.C:204): w = e0 + 9 q with absolute index == 6 (mod 9), from 582 on
+    const int seen9 = (int)(a.seen % kSpb);
+    const int e0 = (6 - seen9 + kSpb) % kSpb;
+    const int n_eval = e0 < a.n_new ? (a.n_new - 1 - e0) / kSpb + 1 : 0;
+    int q = 0;
+    {
+        const long long need = kCorrLen + 15 - a.seen - e0;
+        if (need > 0) q = (int)((need + kSpb - 1) / kSpb);
+        if (q > n_eval) q = n_eval;
+    }
+    for (int c0 = (q / kSeqChunk) * kSeqChunk; c0 < n_eval || c0 == 0; c0 += kSeqChunk) {
+        const int c1 = min(n_eval, c0 + kSeqChunk);
+        if (c1 > c0) stage_rows(rows, a.b.picks, pitch_p(a.b.p_max), ch0, a.channels, c0, c1 - c0, lane);
+        const int lim = c1 == n_eval ? a.n_new : e0 + kSpb * c1;          // samples whose evaluations are staged
+        auto do_eval = [&](int qq) {
+            int pick = my_row[qq - c0];
             if (s.last_pick != -1 && pick != s.last_pick) {        // slew one step the short way round (decoder.C:217-246)
                 bool up;
                 if (pick > s.last_pick) up = !(pick - s.last_pick > 4);
@@ -319,14 +383,14 @@ __global__ void __launch_bounds__(32) symbol_clock_kernel(const DemodArgs a) {
             }
             s.last_pick = pick;
             const int offs = (pick + 5) % kSpb;                    // decoder.C:249
-            if (s.dstate == DS_INIT) { s.dstate = DS_WAIT; s.offs = offs; s.cur = e; }   // decoder.C:62-70
+            if (s.dstate == DS_INIT) { s.dstate = DS_WAIT; s.offs = offs; s.cur = e0 + kSpb * qq; }   // decoder.C:62-70
             s.next_offs = offs;
         };
         while (live) {
             if (s.dstate == DS_INIT) {
-                if (next_eval >= lim) break;
-                do_eval(next_eval);
-                next_eval += kSpb;
+                if (q >= c1) break;
+                do_eval(q);
+                ++q;
                 if (s.dstate == DS_INIT) continue;
             }
             if (s.dstate == DS_WAIT) {
@@ -338,28 +402,66 @@ __global__ void __launch_bounds__(32) symbol_clock_kernel(const DemodArgs a) {
             }
             const int td = s.pend + 7;
             if (td >= lim) break;
-            while (next_eval <= td) { do_eval(next_eval); next_eval += kSpb; }
-            const bool is_y = (byte_at(s.pend + 3) & 0x80u) != 0;
-            if (bits && nbits_out < a.bit_cap) {
-                bits[nbits_out] = is_y ? 'Y' : 'B';
-                if (disc) window_is_y(y + s.pend + 3, disc + 4 * (size_t)nbits_out);
-            }
-            ++nbits_out;
+            while (q < c1 && e0 + kSpb * q <= td) { do_eval(q); ++q; }
+            if (nb < cap) bitpos[nb] = s.pend + 3;
+            ++nb;
             s.offs = s.next_offs;
             s.dstate = DS_WAIT;
             s.cur = td + 1;
-            fsm_bit(s, em, is_y);
         }
-        if (lim == a.n_new && live)
-            while (next_eval < a.n_new) { do_eval(next_eval); next_eval += kSpb; }
+        // what is left of the chunk precedes the next bit decision (or no further bit ends in this block)
+        if (live) while (q < c1) { do_eval(q); ++q; }
+        if (c1 == n_eval) break;
     }
     if (!live) return;
     if (s.dstate == DS_PENDING) s.pend -= a.n_new;
     s.cur = s.cur > a.n_new ? s.cur - a.n_new : 0;
-    s.seen = a.seen + a.n_new;
-    a.b.state[ch] = s;
+    a.b.clock[ch] = s;
+    a.b.nbits[ch] = nb;
+    if (a.bit_count) a.bit_count[ch] = nb;
+}
+
+// grid (tiles, channels), block 128: thread = one bit of the block -> its mark/space decision
+__global__ void __launch_bounds__(128) bit_decide_kernel(const DemodArgs a) {
+    const int ch = blockIdx.y, k = blockIdx.x * 128 + threadIdx.x;
+    const int nb = min(a.b.nbits[ch], (int)pitch_b(a.b.p_max));
+    if (k >= nb) return;
+    const int w = a.b.bitpos[(size_t)ch * pitch_b(a.b.p_max) + k];
+    const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY + w;
+    const bool tap = a.bits && k < a.bit_cap;
+    const bool is_y = window_is_y(y, tap && a.disc ? a.disc + ((size_t)ch * a.bit_cap + k) * 4 : nullptr);
+    a.b.bitval[(size_t)ch * pitch_b(a.b.p_max) + k] = is_y ? 1 : 0;
+    if (tap) a.bits[(size_t)ch * a.bit_cap + k] = is_y ? 'Y' : 'B';
+}
+
+// lane = channel: receive_bit (nav_b_sm.C:266-634) over the bits of the block
+__global__ void __launch_bounds__(kSeqWarps * 32) fsm_kernel(const DemodArgs a) {
+    extern __shared__ __align__(16) uint8_t s_seq[];
+    __shared__ unsigned char s_ltrs[128], s_figs[128];      // per-lane indices would serialise the constant cache
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) { s_ltrs[k] = c_ltrs[k]; s_figs[k] = c_figs[k]; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ch0 = (blockIdx.x * kSeqWarps + warp) * 32, ch = ch0 + lane;
+    if (ch0 >= a.channels) return;
+    const bool live = ch < a.channels;
+    uint8_t* rows = s_seq + (size_t)warp * 32 * kSeqPitch;
+    const uint8_t* my_row = rows + lane * kSeqPitch;
+    FsmState s = {};
+    if (live) s = a.b.fsm[ch];
+    Emit em;
+    em.ev = a.events + (size_t)(live ? ch : 0) * a.ev_cap; em.ev_cap = a.ev_cap; em.n = 0; em.writer = live;
+    em.ltrs = s_ltrs; em.figs = s_figs;
+    const int nb = live ? min(a.b.nbits[ch], (int)pitch_b(a.b.p_max)) : 0;
+    const int nb_max = __reduce_max_sync(0xffffffffu, nb);
+    for (int c0 = 0; c0 < nb_max; c0 += kSeqChunk) {
+        const int c1 = min(nb_max, c0 + kSeqChunk);
+        stage_rows(rows, a.b.bitval, pitch_b(a.b.p_max), ch0, a.channels, c0, c1 - c0, lane);
+        const int mine = min(nb, c1);
+        for (int k = c0; k < mine; ++k) fsm_bit(s, em, my_row[k - c0] != 0);
+    }
+    if (!live) return;
+    a.b.fsm[ch] = s;
     a.ev_count[ch] = em.n;
-    if (a.bit_count) a.bit_count[ch] = nbits_out;
 }
 
 // slide every history: the last H entries of [hist | new] become the next block's hist.  One CTA per channel.
@@ -377,21 +479,28 @@ __global__ void __launch_bounds__(256) carry_kernel(const DemodArgs a) {
     if (t < kHistY) yn[t] = s_y[t];
 }
 
-__global__ void init_state_kernel(ChannelState* st, int channels) {
+__global__ void init_state_kernel(ClockState* clock, FsmState* fsm, int channels) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= channels) return;
-    ChannelState s = {};
     // decoder::decoder (decoder.C:6-39) and byte_state_machine::init (nav_b_sm.C:16-42)
-    s.last_pick = -1;
-    s.dstate = DS_INIT;
+    ClockState c = {};
+    c.last_pick = -1;
+    c.dstate = DS_INIT;
+    clock[ch] = c;
+    FsmState s = {};
     s.byte_state = BY_WAIT;
-    st[ch] = s;
+    fsm[ch] = s;
 }
 
 }  // namespace
 
-int demod_launches_per_block() { return 4; }
-size_t demod_pitch_d(int p_max) { return ((size_t)kHistD + p_max + 15) & ~(size_t)15; }
+int demod_launches_per_block() { return 6; }
+size_t demod_pick_pitch(int p_max) { return pitch_p(p_max); }
+size_t demod_bit_pitch(int p_max) { return pitch_b(p_max); }
+int demod_reserved_sms(int channels) {
+    const int ctas = (channels + kSeqWarps * 32 - 1) / (kSeqWarps * 32);
+    return ctas < 4 ? ctas : 4;
+}
 
 cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t stream) {
     static bool tables_done = false;
@@ -429,28 +538,52 @@ cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t s
     }
     cudaError_t e;
     if ((e = cudaMemsetAsync(b.y3, 0, sizeof(float2) * (size_t)channels * (kHistY + b.p_max), stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(b.corr, 0, sizeof(double) * (size_t)channels * (kHistC + b.p_max), stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(b.dec, 0, (size_t)channels * demod_pitch_d(b.p_max), stream)) != cudaSuccess) return e;
-    init_state_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(b.state, channels);
+    if ((e = cudaMemsetAsync(b.corr, 0, sizeof(double) * (size_t)channels * (kHistC + b.p_max + kPadC), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(b.picks, 0, (size_t)channels * pitch_p(b.p_max), stream)) != cudaSuccess) return e;
+    init_state_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(b.clock, b.fsm, channels);
     return cudaGetLastError();
 }
 
-cudaError_t demod_launch(const DemodArgs& a, cudaStream_t stream) {
+cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_seq, cudaEvent_t ff_done, cudaEvent_t* marks) {
     if (a.n_new <= 0 || a.channels <= 0) return cudaSuccess;
-    // These kernels run beside the NEXT block's cascade kernel.  NVX_DEMOD_THROTTLE=<bytes> asks for that much unused
-    // dynamic shared memory, capping their occupancy in the ~48 KB the cascade leaves free (tuning knob; measured on
-    // B200: throttling speeds the cascade up 10 % but stretches the demod past it, so the default is off).
-    static int throttle = -1;
-    if (throttle < 0) {
-        const char* env = getenv("NVX_DEMOD_THROTTLE");
-        throttle = env ? atoi(env) : 0;
+    auto mark = [&](int k, cudaStream_t st) { if (marks) cudaEventRecord(marks[k], st); };
+    // feed-forward part (thread = sample / ring revolution): whole-GPU kernels, ~0.3 ms per 10 s block of 2048 channels
+    mark(0, s_ff);
+    angle_corr_kernel<<<dim3((a.n_new + kTile - 1) / kTile, a.channels), kThreads, 0, s_ff>>>(a);
+    mark(1, s_ff);
+    {   // ring revolutions with an evaluation sample in [-8, n_new): samples 16 + 567 K .. 582 + 567 K
+        const long long lo = a.seen - 8 - (kCorrLen + 15), hi = a.seen + a.n_new - 17;
+        const int k_lo = lo <= 0 ? 0 : (int)((lo + kCorrLen - 1) / kCorrLen);
+        if (hi >= 0 && (int)(hi / kCorrLen) >= k_lo) {
+            const int n_rev = (int)(hi / kCorrLen) - k_lo + 1;
+            const long long units = (long long)a.channels * n_rev;
+            offset_sum_kernel<<<(unsigned)((units + 3 * kSumWarps - 1) / (3 * kSumWarps)), kSumWarps * 32, 0, s_ff>>>(a, k_lo, n_rev);
+        }
     }
-    const dim3 g1((a.n_new + kTile - 1) / kTile, a.channels);
-    angle_corr_kernel<<<g1, kTile, throttle, stream>>>(a);
-    const dim3 g2((a.n_new + 4 + kTile - 1) / kTile, a.channels);
-    sum_decide_kernel<<<g2, kTile, throttle, stream>>>(a);
-    symbol_clock_kernel<<<(a.channels + 31) / 32, 32, 0, stream>>>(a);
-    carry_kernel<<<a.channels, 256, 0, stream>>>(a);
+    mark(2, s_ff);
+    carry_kernel<<<a.channels, 256, 0, s_ff>>>(a);
+    mark(3, s_ff);
+    // sequential part: few warps, latency-bound, runs beside the next block's cascade on the SMs it leaves free
+    if (s_seq != s_ff) {
+        cudaError_t e = cudaEventRecord(ff_done, s_ff);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(s_seq, ff_done, 0)) != cudaSuccess) return e;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(symbol_clock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const unsigned seq_ctas = (a.channels + kSeqWarps * 32 - 1) / (kSeqWarps * 32);
+    mark(4, s_seq);
+    symbol_clock_kernel<<<seq_ctas, kSeqWarps * 32, kSeqSmem, s_seq>>>(a);
+    mark(5, s_seq);
+    bit_decide_kernel<<<dim3((unsigned)((a.n_new / kSpb + 2 + 127) / 128), a.channels), 128, 0, s_seq>>>(a);
+    mark(6, s_seq);
+    fsm_kernel<<<seq_ctas, kSeqWarps * 32, kSeqSmem, s_seq>>>(a);
+    mark(7, s_seq);
     return cudaGetLastError();
 }
 

@@ -13,19 +13,20 @@ constexpr int kEvAbort = 0x18;          // event byte: message_abort() (nav_b_sm
 // Every per-sample array keeps a short history of the previous block in front of the new samples,
 // so the feed-forward kernels are stateless: element for block-relative sample m lives at [hist + m].
 constexpr int kHistY = 16;              // 900 Hz samples (angle needs 1, mask correlation 8 more, decisions look back 4)
-constexpr int kHistC = 576;             // |mask correlation| values (per-offset sums reach back 566)
-constexpr int kHistO = 16;              // per-offset sums (argmax looks back 8)
-constexpr int kHistD = 16;              // decision bytes (windows that started up to 4 samples before the block)
+constexpr int kHistC = 640;             // |mask correlation| values (the per-offset sum threads reach back up to 628)
+constexpr int kPadC = 64;               // readable slack behind the new samples (a thread's running prefix may run 46 past the block)
 
-// What decoder.{h,C} and nav_b_sm.{h,C} keep per channel and that is genuinely sequential.
-struct ChannelState {
-    long long seen;           // 900 Hz samples consumed so far
+// What decoder.{h,C} keeps per channel and that is genuinely sequential: the slew-limited offset tracker and the
+// symbol clock of the mark/space discriminator (decoder.C:73-137, :217-249), in event form.
+struct ClockState {
     int last_pick;            // prev_offset (decoder.C:247), -1 = none
-    // symbol clock of the mark/space discriminator (decoder.C:73-137), event form:
     // dstate INIT / WAIT (searching the sample whose tick equals offs, from `cur` on) / PENDING (bit triggered
     // at sample `pend`, decided 7 samples later); indices are relative to the start of the next block
     int dstate, offs, next_offs, cur, pend;
-    // SITOR-B state machine (nav_b_sm.h:92-116), arrays packed into words
+};
+
+// SITOR-B state machine (nav_b_sm.h:92-116), arrays packed into words
+struct FsmState {
     int match;                // phasing pattern bits matched (status)
     int byte_state, figures, nbits, shift;
     unsigned dx_ring;         // 3 bytes, slot k at bits [8k, 8k+8)
@@ -36,17 +37,19 @@ struct ChannelState {
 };
 
 struct DemodBuffers {
-    float2* y3;               // [channels][kHistY + p_max]   (the cascade kernel writes at +kHistY)
-    double* corr;             // [channels][kHistC + p_max]   |mask correlation| per sample
-    double* osum;             // [channels][kHistO + p_max]   per-offset sum computed at each sample
-    uint8_t* dec;             // [channels][kHistD + p_max]   bit 7: 'Y' decision of the 5-sample window starting here;
-                              //                              low nibble: arg max offset when this is an evaluation sample
-    ChannelState* state;      // [channels]
+    float2* y3;               // [channels][kHistY + p_max]   (the cascade kernel writes at +kHistY); one per block in flight
+    double* corr;             // [channels][kHistC + p_max + kPadC]   |mask correlation| per sample
+    uint8_t* picks;           // [channels][pick pitch]  arg max offset of every evaluation sample of the block; one per block in flight
+    int* bitpos;              // [channels][bit pitch]   first sample of the 5-sample window of every bit of the block
+    uint8_t* bitval;          // [channels][bit pitch]   1 = 'Y', 0 = 'B'
+    int* nbits;               // [channels]              bits decided in the block
+    ClockState* clock;        // [channels]
+    FsmState* fsm;            // [channels]
     int p_max;
 };
 
 struct DemodArgs {
-    DemodBuffers b;           // b.y3 = the buffer the cascade kernel filled for this block
+    DemodBuffers b;           // b.y3 / b.picks = the buffers of this block
     float2* y3_next;          // buffer of the NEXT block: receives the kHistY-sample history (may equal b.y3)
     int n_new;                // new 900 Hz samples per channel in this block
     int channels;             // streams * 2
@@ -61,8 +64,14 @@ struct DemodArgs {
     int bit_cap;
 };
 
-size_t demod_pitch_d(int p_max);     // row pitch of DemodBuffers::dec in bytes (16-byte multiple)
-cudaError_t demod_launch(const DemodArgs& a, cudaStream_t stream);
+size_t demod_pick_pitch(int p_max);  // row pitch of DemodBuffers::picks in bytes
+size_t demod_bit_pitch(int p_max);   // row pitch of DemodBuffers::bitpos / bitval in elements
+// SMs the sequential kernels want for themselves (the cascade grid is sized to leave them free)
+int demod_reserved_sms(int channels);
+// Queues the feed-forward kernels (angle/correlation, per-offset sums + arg max, history carry) on s_ff and the
+// sequential symbol clock, the per-bit window decisions and the SITOR-B state machine on s_seq (ordered after them
+// through ff_done when the two streams differ).  marks: optional 8 events recorded around the kernels (timing mode).
+cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_seq, cudaEvent_t ff_done, cudaEvent_t* marks = nullptr);
 cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t stream);
 int demod_launches_per_block();
 

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <condition_variable>
@@ -26,7 +27,7 @@ namespace nvx {
 size_t cascade_smem_bytes();
 cudaError_t cascade_upload_constants(const double* h1, const double* h2, const double* h3, cudaStream_t stream);
 cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, cudaStream_t stream);
-int cascade_target_warps(int device);
+int cascade_target_warps(int device, int reserved_sms);
 }  // namespace nvx
 
 namespace {
@@ -114,7 +115,8 @@ struct nvx_engine {
     cudaStream_t stream = nullptr;        // cascade, tail carry, ingest copies / conversion
     cudaStream_t stream_demod = nullptr;  // demod kernels + event download, one block behind
     float2* y3buf[kBuf] = {};
-    cudaEvent_t casc_done[kBuf] = {}, demod_done[kBuf] = {};
+    uint8_t* pickbuf[kBuf] = {};
+    cudaEvent_t casc_done[kBuf] = {}, demod_done[kBuf] = {}, ff_done[kBuf] = {};
     long long blocks = 0;
     int last_buf = 0;
     float2* tail[2] = {nullptr, nullptr};
@@ -129,6 +131,8 @@ struct nvx_engine {
     long long sb_abs = 0;
     int last_P = 0;
     bool custom_taps = false;
+    bool serial = false;                  // NVX_PIPELINE=serial: the next cascade waits for this block's whole demod
+    bool ff_on_main = true;               // feed-forward demod kernels follow the cascade on the main stream
     int target_warps = 1184;
     nvx::MessageAssembler assembler;
     std::vector<nvx::AssembledMessage> ready, handed;
@@ -166,7 +170,8 @@ int free_engine(nvx_engine* e) {
         e->worker.join();
     }
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
-    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->db.corr); cudaFree(e->db.dec); cudaFree(e->db.state);
+    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->db.corr); cudaFree(e->db.clock); cudaFree(e->db.fsm);
+    cudaFree(e->db.bitpos); cudaFree(e->db.bitval); cudaFree(e->db.nbits);
     cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
     cudaFree(e->stage_f32); cudaFree(e->stage_s16);
     for (int k = 0; k < kBuf; ++k) {
@@ -174,6 +179,8 @@ int free_engine(nvx_engine* e) {
         cudaFreeHost(e->h_events[k]); cudaFreeHost(e->h_ev_count[k]);
         if (e->casc_done[k]) cudaEventDestroy(e->casc_done[k]);
         if (e->demod_done[k]) cudaEventDestroy(e->demod_done[k]);
+        if (e->ff_done[k]) cudaEventDestroy(e->ff_done[k]);
+        cudaFree(e->pickbuf[k]);
     }
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream_demod) cudaStreamDestroy(e->stream_demod);
@@ -186,6 +193,7 @@ int reset_state(nvx_engine* e) {
     CU_TRY(cudaMemsetAsync(e->tail[1], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
     for (int k = 0; k < kBuf; ++k) {
         e->db.y3 = e->y3buf[k];
+        e->db.picks = e->pickbuf[k];
         CU_TRY(nvx::demod_init_state(e->db, e->channels, e->stream));
     }
     CU_TRY(cudaStreamSynchronize(e->stream));
@@ -218,7 +226,9 @@ void collect_spans(nvx_engine* e) {
     for (const auto& sp : e->spans) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e->ev_pool[sp.a], e->ev_pool[sp.b]);
-        if (sp.kind == 0) e->stats.cascade_ms += ms; else e->stats.demod_ms += ms;
+        if (sp.kind == 0) e->stats.cascade_ms += ms;
+        else if (sp.kind == 1) e->stats.demod_ms += ms;
+        else e->stats.demod_stage_ms[sp.kind - 2] += ms;
     }
     e->spans.clear();
     e->ev_used = 0;
@@ -336,12 +346,15 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     ca.y3_pitch = nvx::kHistY + e->P_max;
     ca.y3_off = nvx::kHistY;
 
-    cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, marks[8] = {};
     if (e->timing) {
         const int base = (int)e->ev_used;
-        t0 = next_event(e); t1 = next_event(e); t2 = next_event(e); t3 = next_event(e);
+        t0 = next_event(e); t1 = next_event(e);
+        for (int k = 0; k < 8; ++k) marks[k] = next_event(e);
         e->spans.push_back({base, base + 1, 0});
-        e->spans.push_back({base + 2, base + 3, 1});
+        e->spans.push_back({base + 2, base + 9, 1});                                      // whole demod chain
+        for (int k = 0; k < 3; ++k) e->spans.push_back({base + 2 + k, base + 3 + k, 2 + k});   // angle, sums, carry
+        for (int k = 0; k < 3; ++k) e->spans.push_back({base + 6 + k, base + 7 + k, 5 + k});   // clock, decide, fsm
         CU_TRY(cudaEventRecord(t0, e->stream));
     }
     CU_TRY(cascade_launch(ca, e->custom_taps, e->stream));
@@ -361,17 +374,23 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     DemodArgs da;
     da.b = e->db;
     da.b.y3 = e->y3buf[b];
+    da.b.picks = e->pickbuf[b];
     da.y3_next = e->y3buf[(b + 1) % kBuf];
     da.n_new = n_super; da.channels = e->channels; da.seen = e->sb_abs;
     da.events = e->d_events[b]; da.ev_count = e->d_ev_count[b]; da.ev_cap = e->ev_cap;
     da.bits = e->d_bits; da.disc = e->d_disc; da.bit_count = e->d_bit_count; da.bit_cap = e->bit_cap;
-    CU_TRY(cudaStreamWaitEvent(e->stream_demod, e->casc_done[b], 0));
-    if (e->timing) CU_TRY(cudaEventRecord(t2, e->stream_demod));
-    CU_TRY(demod_launch(da, e->stream_demod));
-    if (e->timing) CU_TRY(cudaEventRecord(t3, e->stream_demod));
+    // The feed-forward demod kernels are short whole-GPU kernels; beside the cascade (one warp per SM sub-partition,
+    // no latency slack) they cost it more than they take alone, so by default they follow it on the main stream and
+    // only the sequential symbol-clock / state-machine kernel (64 warps) overlaps the next block's cascade.
+    cudaStream_t s_ff = e->ff_on_main ? e->stream : e->stream_demod;
+    if (!e->ff_on_main) CU_TRY(cudaStreamWaitEvent(e->stream_demod, e->casc_done[b], 0));
+    // the history carry of this block writes into the y3 buffer block i-2 used: its symbol clock must be done (it is, normally)
+    else if (e->blocks >= kBuf - 1) CU_TRY(cudaStreamWaitEvent(e->stream, e->demod_done[(b + 1) % kBuf], 0));
+    CU_TRY(demod_launch(da, s_ff, e->stream_demod, e->ff_done[b], e->timing ? marks : nullptr));
     CU_TRY(cudaMemcpyAsync(e->h_ev_count[b], e->d_ev_count[b], sizeof(int) * e->channels, cudaMemcpyDeviceToHost, e->stream_demod));
     CU_TRY(cudaMemcpyAsync(e->h_events[b], e->d_events[b], (size_t)e->channels * e->ev_cap, cudaMemcpyDeviceToHost, e->stream_demod));
     CU_TRY(cudaEventRecord(e->demod_done[b], e->stream_demod));
+    if (e->serial) CU_TRY(cudaStreamWaitEvent(e->stream, e->demod_done[b], 0));
     // the next block's cascade may overwrite neither this block's input staging nor (two blocks on) its y3
     // buffer before the demod has consumed them: the staging buffers are only touched on e->stream (ordered),
     // the y3 buffer is protected by the demod_done wait above
@@ -464,19 +483,30 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CREATE_TRY(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, lo));
         CREATE_TRY(cudaStreamCreateWithPriority(&e->stream_demod, cudaStreamNonBlocking, hi));
+        // tuning knob NVX_PIPELINE: "overlap" = feed-forward demod kernels on the demod stream too (beside the next
+        // cascade), "serial" = the next cascade waits for the whole demod; default = see process_block
+        const char* mode = getenv("NVX_PIPELINE");
+        e->ff_on_main = !(mode && !strcmp(mode, "overlap"));
+        e->serial = mode && !strcmp(mode, "serial");
     }
     for (int k = 0; k < kBuf; ++k) {
         CREATE_TRY(cudaEventCreateWithFlags(&e->casc_done[k], cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&e->demod_done[k], cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&e->ff_done[k], cudaEventDisableTiming));
     }
     const size_t tail_bytes = (size_t)e->S * nvx::kHalo * sizeof(float2);
     CREATE_TRY(cudaMalloc(&e->tail[0], tail_bytes));
     CREATE_TRY(cudaMalloc(&e->tail[1], tail_bytes));
     e->db.p_max = e->P_max;
     for (int k = 0; k < kBuf; ++k) CREATE_TRY(cudaMalloc(&e->y3buf[k], (size_t)e->channels * (nvx::kHistY + e->P_max) * sizeof(float2)));
-    CREATE_TRY(cudaMalloc(&e->db.corr, (size_t)e->channels * (nvx::kHistC + e->P_max) * sizeof(double)));
-    CREATE_TRY(cudaMalloc(&e->db.dec, (size_t)e->channels * nvx::demod_pitch_d(e->P_max)));
-    CREATE_TRY(cudaMalloc(&e->db.state, (size_t)e->channels * sizeof(nvx::ChannelState)));
+    CREATE_TRY(cudaMalloc(&e->db.corr, (size_t)e->channels * (nvx::kHistC + e->P_max + nvx::kPadC) * sizeof(double)));
+    for (int k = 0; k < kBuf; ++k) CREATE_TRY(cudaMalloc(&e->pickbuf[k], (size_t)e->channels * nvx::demod_pick_pitch(e->P_max)));
+    CREATE_TRY(cudaMalloc(&e->db.bitpos, (size_t)e->channels * nvx::demod_bit_pitch(e->P_max) * sizeof(int)));
+    CREATE_TRY(cudaMalloc(&e->db.bitval, (size_t)e->channels * nvx::demod_bit_pitch(e->P_max)));
+    CREATE_TRY(cudaMalloc(&e->db.nbits, (size_t)e->channels * sizeof(int)));
+    CREATE_TRY(cudaMemset(e->db.nbits, 0, (size_t)e->channels * sizeof(int)));
+    CREATE_TRY(cudaMalloc(&e->db.clock, (size_t)e->channels * sizeof(nvx::ClockState)));
+    CREATE_TRY(cudaMalloc(&e->db.fsm, (size_t)e->channels * sizeof(nvx::FsmState)));
     for (int k = 0; k < kBuf; ++k) {
         CREATE_TRY(cudaMalloc(&e->d_events[k], (size_t)e->channels * e->ev_cap));
         CREATE_TRY(cudaMalloc(&e->d_ev_count[k], sizeof(int) * e->channels));
@@ -495,7 +525,7 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
 #undef CREATE_TRY
     for (int k = 0; k < 2; ++k)
         if (int rc = encode_rows(&e->map_tail[k], e->tail[k], nvx::kHalo, e->S)) { free_engine(e); return rc; }
-    e->target_warps = nvx::cascade_target_warps(cfg->device);
+    e->target_warps = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels));
     e->assembler.resize(e->channels);
     if (int rc = reset_state(e)) { free_engine(e); return rc; }
     e->worker = std::thread(worker_main, e);

@@ -131,14 +131,16 @@ cudaError_t cascade_upload_constants(const double* h1, const double* h2, const d
     return cudaStreamSynchronize(stream);
 }
 
-// warps that are resident at once across the device: the host sizes the grid to one full wave
-int cascade_target_warps(int device) {
+// warps that are resident at once across the device, leaving `reserved_sms` SMs to the sequential demod kernels:
+// the host sizes the grid to at most one full wave
+int cascade_target_warps(int device, int reserved_sms) {
     int sms = 148, per_sm = kCtasPerSm;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaFuncSetAttribute(fir_cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cascade_smem_bytes());
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_cascade_kernel<true>, kWarpsPerCta * 32,
                                                       cascade_smem_bytes()) != cudaSuccess || per_sm < 1)
         per_sm = kCtasPerSm;
+    if (sms - reserved_sms >= 8) sms -= reserved_sms;
     return sms * per_sm * kWarpsPerCta;
 }
 

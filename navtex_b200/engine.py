@@ -34,7 +34,8 @@ class Message(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("cascade_ms", C.c_double), ("demod_ms", C.c_double), ("cascade_launches", C.c_longlong),
-                ("demod_launches", C.c_longlong), ("aux_launches", C.c_longlong), ("samples", C.c_longlong)]
+                ("demod_launches", C.c_longlong), ("aux_launches", C.c_longlong), ("samples", C.c_longlong),
+                ("demod_stage_ms", C.c_double * 6)]
 
 
 class SynthDesc(C.Structure):

@@ -35,5 +35,6 @@ st = eng.stats()
 tot = a.streams * n * a.steps
 print(f"streams={a.streams} n={n} steps={a.steps} wall={wall*1e3/a.steps:.3f} ms/step "
       f"cascade={st.cascade_ms/a.steps:.3f} ms demod={st.demod_ms/a.steps:.3f} ms")
+print("demod stages (ms/step): " + " ".join(f"{nm}={st.demod_stage_ms[k]/a.steps:.3f}" for k, nm in enumerate(("angle", "sum", "carry", "clock", "decide", "fsm"))))
 print(f"cascade: {tot/st.cascade_ms/1e6:.1f} Gsamples/s = {tot*8.06/st.cascade_ms/1e6:.0f} GB/s algorithmic; "
       f"whole step (wall): {tot/wall/1e9:.1f} Gsamples/s")
