@@ -55,6 +55,12 @@ typedef struct {
     const double *h1, *h2, *h3;
     int keep_bits;              /* record 'B'/'Y' decisions and discriminator sums for nvx_engine_read_bits */
     int first_stream_id;        /* global id of stream 0 (multi-GPU sharding; only used to label messages) */
+    /* optional per-stream channel offsets [n_streams][2] in Hz (multiples of 0.5 Hz, |f| < 31500): channel c of stream
+     * s is mixed down by nco_hz[2 s + c].  NULL = the reference's +14000 / -14000 with its 9-entry table
+     * (fir2cpp.C:12-14, :104-107); a non-NULL array selects the general-NCO kernel variant for every stream */
+    const double *nco_hz;
+    /* optional per-stream tags [n_streams][2] handed to add_message instead of freq_tag (e.g. 4209 for 4209.5 kHz) */
+    const int *stream_freq_tag;
 } nvx_config;
 
 typedef struct {
@@ -109,6 +115,7 @@ typedef struct {
     long long samples;          /* IQ samples (all streams) pushed */
     double demod_stage_ms[6];   /* split of demod_ms: angle/correlation, per-offset sums + arg max, history carry | symbol clock, bit decisions, SITOR-B state machine */
 } nvx_stats;
+/* on: 0 = off, 1 = time the fused-FIR kernel only (two event records per block), 2 = also every demod stage */
 int nvx_engine_enable_timing(nvx_engine *e, int on);
 int nvx_engine_get_stats(nvx_engine *e, nvx_stats *out, int reset);
 /* the CUDA stream everything is queued on (cudaStream_t as void*), for callers that produce input on the device */

@@ -24,10 +24,10 @@
 #include "message_assembler.h"
 
 namespace nvx {
-size_t cascade_smem_bytes();
+int cascade_box_elems(bool s16);
 cudaError_t cascade_upload_constants(const double* h1, const double* h2, const double* h3, cudaStream_t stream);
-cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, cudaStream_t stream);
-int cascade_target_warps(int device, int reserved_sms);
+cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, bool s16, cudaStream_t stream);
+int cascade_target_warps(int device, int reserved_sms, bool s16);
 }  // namespace nvx
 
 namespace {
@@ -63,46 +63,36 @@ int load_encode() {
     return 0;
 }
 
-// float32 view [rows][2 * cols] of a stream-major float2 array; box = one stage (kBoxFloats) x 32 rows
-int encode_rows(CUtensorMap* map, const void* base, long long cols, long long rows) {
+// 32-bit-element view of a stream-major sample array: [rows][2 * cols] floats for float2 samples, [rows][cols] words for
+// short2 samples (one word = one I,Q pair); box = one ring stage x 32 rows
+int encode_rows(CUtensorMap* map, const void* base, long long cols, long long rows, bool s16) {
     if (int rc = load_encode()) return rc;
-    cuuint64_t dims[2] = {(cuuint64_t)(2 * cols), (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)(cols * 8)};
-    cuuint32_t box[2] = {(cuuint32_t)nvx::kBoxFloats, 32};
+    const long long el = s16 ? 1 : 2;
+    cuuint64_t dims[2] = {(cuuint64_t)(el * cols), (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(cols * el * 4)};
+    cuuint32_t box[2] = {(cuuint32_t)nvx::cascade_box_elems(s16), 32};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = g_encode(map, s16 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NVX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%lld rows=%lld", (int)r, cols, rows);
     return 0;
 }
 
-// new_tail[s] = last kHalo samples of (old_tail[s] ++ x[s][0..n))
-__global__ void tail_carry_kernel(const float2* __restrict__ old_tail, const float2* __restrict__ x, float2* __restrict__ new_tail,
+// new_tail[s] = last kHalo samples of (old_tail[s] ++ x[s][0..n)); kPer samples (16 bytes) per thread
+template <typename Sample>
+__global__ void tail_carry_kernel(const Sample* __restrict__ old_tail, const Sample* __restrict__ x, Sample* __restrict__ new_tail,
                                   int streams, long long n) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 = 2 samples
-    const long long per = nvx::kHalo / 2;
+    constexpr int kPer = 16 / (int)sizeof(Sample);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = nvx::kHalo / kPer;
     if (idx >= per * streams) return;
     const int s = (int)(idx / per);
-    const long long k = (idx % per) * 2;
-    const long long p = n - nvx::kHalo + k;                                      // n and kHalo are even
-    const float4* src = p >= 0 ? reinterpret_cast<const float4*>(x + (size_t)s * n + p)
-                               : reinterpret_cast<const float4*>(old_tail + (size_t)s * nvx::kHalo + (nvx::kHalo + p));
-    *reinterpret_cast<float4*>(new_tail + (size_t)s * nvx::kHalo + k) = *src;
-}
-
-// interleaved int16 I,Q -> float2, the (double)short of capt_sched.c:511 (exact in float)
-__global__ void s16_to_f32_kernel(const short2* __restrict__ in, float2* __restrict__ out, long long count) {
-    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (; i + 3 < count; i += stride) {
-        const int4 v = *reinterpret_cast<const int4*>(in + i);                   // 4 IQ pairs
-        const short2 a = *reinterpret_cast<const short2*>(&v.x), b = *reinterpret_cast<const short2*>(&v.y);
-        const short2 c = *reinterpret_cast<const short2*>(&v.z), d = *reinterpret_cast<const short2*>(&v.w);
-        float4* o = reinterpret_cast<float4*>(out + i);
-        o[0] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
-        o[1] = make_float4((float)c.x, (float)c.y, (float)d.x, (float)d.y);
-    }
+    const long long k = (idx % per) * kPer;
+    const long long p = n - nvx::kHalo + k;                                      // n and kHalo are multiples of 4
+    const int4* src = p >= 0 ? reinterpret_cast<const int4*>(x + (size_t)s * n + p)
+                             : reinterpret_cast<const int4*>(old_tail + (size_t)s * nvx::kHalo + (nvx::kHalo + p));
+    *reinterpret_cast<int4*>(new_tail + (size_t)s * nvx::kHalo + k) = *src;
 }
 
 }  // namespace
@@ -119,9 +109,11 @@ struct nvx_engine {
     cudaEvent_t casc_done[kBuf] = {}, demod_done[kBuf] = {}, ff_done[kBuf] = {};
     long long blocks = 0;
     int last_buf = 0;
-    float2* tail[2] = {nullptr, nullptr};
-    CUtensorMap map_tail[2];
+    // carried input tail, ping-pong, in the sample format being pushed: [S][kHalo] float2 or short2
+    void* tail[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [format][ping-pong]
+    CUtensorMap map_tail[2][2];
     int tail_cur = 0;
+    int fmt = -1;                         // -1 = nothing pushed since create/reset, 0 = float2, 1 = short2
     nvx::DemodBuffers db = {};
     uint8_t* d_events[kBuf] = {}; int* d_ev_count[kBuf] = {}; int ev_cap = 0;
     char* d_bits = nullptr; float* d_disc = nullptr; int* d_bit_count = nullptr; int bit_cap = 0;
@@ -131,9 +123,11 @@ struct nvx_engine {
     long long sb_abs = 0;
     int last_P = 0;
     bool custom_taps = false;
+    nvx::NcoParam* d_nco = nullptr;       // per-stream NCO parameters (general-NCO kernel variant), else null
+    std::vector<int> stream_tag;          // optional [S][2] message tags
     bool serial = false;                  // NVX_PIPELINE=serial: the next cascade waits for this block's whole demod
     bool ff_on_main = true;               // feed-forward demod kernels follow the cascade on the main stream
-    int target_warps = 1184;
+    int target_warps[2] = {576, 576};     // resident cascade warps per sample format
     nvx::MessageAssembler assembler;
     std::vector<nvx::AssembledMessage> ready, handed;
     std::vector<nvx_message> view;
@@ -146,7 +140,7 @@ struct nvx_engine {
     bool stop = false;
     int worker_rc = 0;
     // timing
-    bool timing = false;
+    int timing = 0;                       // 0 off, 1 = cascade span only, 2 = every demod stage too
     std::vector<cudaEvent_t> ev_pool;
     struct Span { int a, b, kind; };
     std::vector<Span> spans;
@@ -170,10 +164,11 @@ int free_engine(nvx_engine* e) {
         e->worker.join();
     }
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
-    cudaFree(e->tail[0]); cudaFree(e->tail[1]); cudaFree(e->db.corr); cudaFree(e->db.clock); cudaFree(e->db.fsm);
+    for (int f = 0; f < 2; ++f) { cudaFree(e->tail[f][0]); cudaFree(e->tail[f][1]); }
+    cudaFree(e->db.corr); cudaFree(e->db.clock); cudaFree(e->db.fsm);
     cudaFree(e->db.bitpos); cudaFree(e->db.bitval); cudaFree(e->db.nbits);
     cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
-    cudaFree(e->stage_f32); cudaFree(e->stage_s16);
+    cudaFree(e->stage_f32); cudaFree(e->stage_s16); cudaFree(e->d_nco);
     for (int k = 0; k < kBuf; ++k) {
         cudaFree(e->y3buf[k]); cudaFree(e->d_events[k]); cudaFree(e->d_ev_count[k]);
         cudaFreeHost(e->h_events[k]); cudaFreeHost(e->h_ev_count[k]);
@@ -189,8 +184,10 @@ int free_engine(nvx_engine* e) {
 }
 
 int reset_state(nvx_engine* e) {
-    CU_TRY(cudaMemsetAsync(e->tail[0], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
-    CU_TRY(cudaMemsetAsync(e->tail[1], 0, (size_t)e->S * nvx::kHalo * sizeof(float2), e->stream));
+    for (int f = 0; f < 2; ++f)
+        for (int k = 0; k < 2; ++k)
+            CU_TRY(cudaMemsetAsync(e->tail[f][k], 0, (size_t)e->S * nvx::kHalo * (f ? sizeof(short2) : sizeof(float2)), e->stream));
+    e->fmt = -1;
     for (int k = 0; k < kBuf; ++k) {
         e->db.y3 = e->y3buf[k];
         e->db.picks = e->pickbuf[k];
@@ -242,7 +239,8 @@ int drain_events(nvx_engine* e, int b) {
         int n = e->h_ev_count[b][ch];
         if (n > e->ev_cap) { n = e->ev_cap; rc = NVX_ERR_OVERFLOW; }
         if (n > 0)
-            e->assembler.feed(ch, e->cfg.first_stream_id + ch / 2, e->cfg.freq_tag[ch & 1], e->h_events[b] + (size_t)ch * e->ev_cap,
+            e->assembler.feed(ch, e->cfg.first_stream_id + ch / 2, e->stream_tag.empty() ? e->cfg.freq_tag[ch & 1] : e->stream_tag[ch],
+                              e->h_events[b] + (size_t)ch * e->ev_cap,
                               (size_t)n, &out);
     }
     if (!out.empty()) {
@@ -312,8 +310,11 @@ int sync_engine(nvx_engine* e) {
     return 0;
 }
 
-int process_block(nvx_engine* e, const float2* d_x, long long n) {
+int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     using namespace nvx;
+    if (e->fmt >= 0 && e->fmt != (int)s16)
+        return fail(NVX_ERR_ARG, "sample format changed between pushes (float and int16 blocks cannot be mixed without a reset)");
+    e->fmt = (int)s16;
     if (n <= 0 || n % kSuper != 0) return fail(NVX_ERR_ARG, "block length %lld is not a positive multiple of %d", n, kSuper);
     if (n > e->cfg.max_block) return fail(NVX_ERR_ARG, "block length %lld exceeds max_block %lld", n, e->cfg.max_block);
     if (((uintptr_t)d_x & 15) != 0) return fail(NVX_ERR_ARG, "device block is not 16-byte aligned");
@@ -325,12 +326,12 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
         collect_spans(e);
     }
     CascadeArgs ca;
-    if (int rc = encode_rows(&ca.map_x, d_x, n, e->S)) return rc;
-    ca.map_tail = e->map_tail[e->tail_cur];
+    if (int rc = encode_rows(&ca.map_x, d_x, n, e->S, s16)) return rc;
+    ca.map_tail = e->map_tail[s16][e->tail_cur];
     const int n_super = (int)(n / kSuper);
     const int groups = (e->S + 31) / 32;
     // time segments: enough warps to fill the machine once, but keep the 7-superblock warm-up small
-    int segs = e->target_warps / groups;            // never more warps than are resident at once (no second wave)
+    int segs = e->target_warps[s16] / groups;            // never more warps than are resident at once (no second wave)
     const int min_seg = 63;
     if (segs > n_super / min_seg) segs = n_super / min_seg;
     if (segs < 1) segs = 1;
@@ -343,6 +344,8 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     ca.seg_super = seg_super;
     ca.n_super = n_super;
     ca.sb_phase = (int)(e->sb_abs % kNcoPeriod);
+    ca.sb_abs = e->sb_abs;
+    ca.nco = e->d_nco;
     ca.y3_pitch = nvx::kHistY + e->P_max;
     ca.y3_off = nvx::kHistY;
 
@@ -350,20 +353,28 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     if (e->timing) {
         const int base = (int)e->ev_used;
         t0 = next_event(e); t1 = next_event(e);
-        for (int k = 0; k < 8; ++k) marks[k] = next_event(e);
         e->spans.push_back({base, base + 1, 0});
-        e->spans.push_back({base + 2, base + 9, 1});                                      // whole demod chain
-        for (int k = 0; k < 3; ++k) e->spans.push_back({base + 2 + k, base + 3 + k, 2 + k});   // angle, sums, carry
-        for (int k = 0; k < 3; ++k) e->spans.push_back({base + 6 + k, base + 7 + k, 5 + k});   // clock, decide, fsm
+        if (e->timing > 1) {
+            for (int k = 0; k < 8; ++k) marks[k] = next_event(e);
+            e->spans.push_back({base + 2, base + 9, 1});                                      // whole demod chain
+            for (int k = 0; k < 3; ++k) e->spans.push_back({base + 2 + k, base + 3 + k, 2 + k});   // angle, sums, carry
+            for (int k = 0; k < 3; ++k) e->spans.push_back({base + 6 + k, base + 7 + k, 5 + k});   // clock, decide, fsm
+        }
         CU_TRY(cudaEventRecord(t0, e->stream));
     }
-    CU_TRY(cascade_launch(ca, e->custom_taps, e->stream));
+    CU_TRY(cascade_launch(ca, e->custom_taps, s16, e->stream));
     if (e->timing) CU_TRY(cudaEventRecord(t1, e->stream));
 
     const int nxt = e->tail_cur ^ 1;
     {
-        const long long work = (long long)e->S * (kHalo / 2);
-        tail_carry_kernel<<<(unsigned)((work + 255) / 256), 256, 0, e->stream>>>(e->tail[e->tail_cur], d_x, e->tail[nxt], e->S, n);
+        const long long work = (long long)e->S * (kHalo / (s16 ? 4 : 2));
+        const unsigned grid = (unsigned)((work + 255) / 256);
+        if (s16)
+            tail_carry_kernel<short2><<<grid, 256, 0, e->stream>>>(static_cast<const short2*>(e->tail[1][e->tail_cur]), static_cast<const short2*>(d_x),
+                                                                   static_cast<short2*>(e->tail[1][nxt]), e->S, n);
+        else
+            tail_carry_kernel<float2><<<grid, 256, 0, e->stream>>>(static_cast<const float2*>(e->tail[0][e->tail_cur]), static_cast<const float2*>(d_x),
+                                                                   static_cast<float2*>(e->tail[0][nxt]), e->S, n);
         CU_TRY(cudaGetLastError());
     }
     e->tail_cur = nxt;
@@ -386,7 +397,7 @@ int process_block(nvx_engine* e, const float2* d_x, long long n) {
     if (!e->ff_on_main) CU_TRY(cudaStreamWaitEvent(e->stream_demod, e->casc_done[b], 0));
     // the history carry of this block writes into the y3 buffer block i-2 used: its symbol clock must be done (it is, normally)
     else if (e->blocks >= kBuf - 1) CU_TRY(cudaStreamWaitEvent(e->stream, e->demod_done[(b + 1) % kBuf], 0));
-    CU_TRY(demod_launch(da, s_ff, e->stream_demod, e->ff_done[b], e->timing ? marks : nullptr));
+    CU_TRY(demod_launch(da, s_ff, e->stream_demod, e->ff_done[b], e->timing > 1 ? marks : nullptr));
     CU_TRY(cudaMemcpyAsync(e->h_ev_count[b], e->d_ev_count[b], sizeof(int) * e->channels, cudaMemcpyDeviceToHost, e->stream_demod));
     CU_TRY(cudaMemcpyAsync(e->h_events[b], e->d_events[b], (size_t)e->channels * e->ev_cap, cudaMemcpyDeviceToHost, e->stream_demod));
     CU_TRY(cudaEventRecord(e->demod_done[b], e->stream_demod));
@@ -427,15 +438,6 @@ int ensure_stage_s16(nvx_engine* e, size_t samples) {
     return 0;
 }
 
-int convert_and_process(nvx_engine* e, const short2* d_in, long long n) {
-    const size_t total = (size_t)e->S * (size_t)n;
-    if (int rc = ensure_stage_f32(e, total)) return rc;
-    s16_to_f32_kernel<<<148 * 8, 256, 0, e->stream>>>(d_in, e->stage_f32, (long long)total);
-    CU_TRY(cudaGetLastError());
-    e->stats.aux_launches++;
-    return process_block(e, e->stage_f32, n);
-}
-
 }  // namespace
 
 extern "C" {
@@ -462,6 +464,25 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     e->cfg = *cfg;
     if (e->cfg.freq_tag[0] == 0 && e->cfg.freq_tag[1] == 0) { e->cfg.freq_tag[0] = 518; e->cfg.freq_tag[1] = 490; }
     e->cfg.h1 = e->cfg.h2 = e->cfg.h3 = nullptr;    // copied to the device below, not retained
+    e->cfg.nco_hz = nullptr;
+    e->cfg.stream_freq_tag = nullptr;
+    if (cfg->stream_freq_tag) e->stream_tag.assign(cfg->stream_freq_tag, cfg->stream_freq_tag + 2 * (size_t)cfg->n_streams);
+    std::vector<nvx::NcoParam> nco;
+    if (cfg->nco_hz) {
+        nco.resize((size_t)cfg->n_streams);
+        for (int k = 0; k < 2 * cfg->n_streams; ++k) {
+            const double f = cfg->nco_hz[k], twice = 2.0 * f;
+            if (!(fabs(f) < 31500.0) || twice != nearbyint(twice)) {
+                delete e;
+                return fail(NVX_ERR_ARG, "nco_hz[%d] = %g is not a multiple of 0.5 Hz inside +-31.5 kHz", k, f);
+            }
+            long long num = (long long)twice % nvx::kNcoDen;
+            if (num < 0) num += nvx::kNcoDen;
+            nco[(size_t)k / 2].num[k & 1] = (int)num;
+            // same expression as fir2cpp.C:105-106 for table entry 1, rounded once to float
+            nco[(size_t)k / 2].step[k & 1] = make_float2((float)cos((2 * M_PI * 1 * f) / 63000), (float)-sin((2 * M_PI * 1 * f) / 63000));
+        }
+    }
     e->S = cfg->n_streams;
     e->channels = 2 * e->S;
     e->P_max = (int)(cfg->max_block / nvx::kSuper);
@@ -494,9 +515,9 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         CREATE_TRY(cudaEventCreateWithFlags(&e->demod_done[k], cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&e->ff_done[k], cudaEventDisableTiming));
     }
-    const size_t tail_bytes = (size_t)e->S * nvx::kHalo * sizeof(float2);
-    CREATE_TRY(cudaMalloc(&e->tail[0], tail_bytes));
-    CREATE_TRY(cudaMalloc(&e->tail[1], tail_bytes));
+    for (int f = 0; f < 2; ++f)
+        for (int k = 0; k < 2; ++k)
+            CREATE_TRY(cudaMalloc(&e->tail[f][k], (size_t)e->S * nvx::kHalo * (f ? sizeof(short2) : sizeof(float2))));
     e->db.p_max = e->P_max;
     for (int k = 0; k < kBuf; ++k) CREATE_TRY(cudaMalloc(&e->y3buf[k], (size_t)e->channels * (nvx::kHistY + e->P_max) * sizeof(float2)));
     CREATE_TRY(cudaMalloc(&e->db.corr, (size_t)e->channels * (nvx::kHistC + e->P_max + nvx::kPadC) * sizeof(double)));
@@ -522,10 +543,15 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         CREATE_TRY(cudaMemset(e->d_bit_count, 0, sizeof(int) * e->channels));
     }
     CREATE_TRY(nvx::cascade_upload_constants(cfg->h1, cfg->h2, cfg->h3, e->stream));
+    if (!nco.empty()) {
+        CREATE_TRY(cudaMalloc(&e->d_nco, nco.size() * sizeof(nvx::NcoParam)));
+        CREATE_TRY(cudaMemcpy(e->d_nco, nco.data(), nco.size() * sizeof(nvx::NcoParam), cudaMemcpyHostToDevice));
+    }
 #undef CREATE_TRY
-    for (int k = 0; k < 2; ++k)
-        if (int rc = encode_rows(&e->map_tail[k], e->tail[k], nvx::kHalo, e->S)) { free_engine(e); return rc; }
-    e->target_warps = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels));
+    for (int f = 0; f < 2; ++f)
+        for (int k = 0; k < 2; ++k)
+            if (int rc = encode_rows(&e->map_tail[f][k], e->tail[f][k], nvx::kHalo, e->S, f != 0)) { free_engine(e); return rc; }
+    for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels), f != 0);
     e->assembler.resize(e->channels);
     if (int rc = reset_state(e)) { free_engine(e); return rc; }
     e->worker = std::thread(worker_main, e);
@@ -549,14 +575,14 @@ int nvx_engine_reset(nvx_engine* e) {
 int nvx_engine_push_device_f32(nvx_engine* e, const void* d_iq, long long n) {
     if (!e || !d_iq) return fail(NVX_ERR_ARG, "null argument");
     CU_TRY(cudaSetDevice(e->cfg.device));
-    return process_block(e, static_cast<const float2*>(d_iq), n);
+    return process_block(e, d_iq, n, false);
 }
 
 int nvx_engine_push_device_s16(nvx_engine* e, const void* d_iq, long long n) {
     if (!e || !d_iq) return fail(NVX_ERR_ARG, "null argument");
     if (((uintptr_t)d_iq & 15) != 0) return fail(NVX_ERR_ARG, "device block is not 16-byte aligned");
     CU_TRY(cudaSetDevice(e->cfg.device));
-    return convert_and_process(e, static_cast<const short2*>(d_iq), n);
+    return process_block(e, d_iq, n, true);
 }
 
 int nvx_engine_push_host_f32(nvx_engine* e, const float* iq, long long n) {
@@ -566,7 +592,7 @@ int nvx_engine_push_host_f32(nvx_engine* e, const float* iq, long long n) {
     const size_t total = (size_t)e->S * (size_t)n;
     if (int rc = ensure_stage_f32(e, total)) return rc;
     CU_TRY(cudaMemcpyAsync(e->stage_f32, iq, total * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
-    return process_block(e, e->stage_f32, n);
+    return process_block(e, e->stage_f32, n, false);
 }
 
 int nvx_engine_push_host_s16(nvx_engine* e, const int16_t* iq, long long n) {
@@ -576,7 +602,7 @@ int nvx_engine_push_host_s16(nvx_engine* e, const int16_t* iq, long long n) {
     const size_t total = (size_t)e->S * (size_t)n;
     if (int rc = ensure_stage_s16(e, total)) return rc;
     CU_TRY(cudaMemcpyAsync(e->stage_s16, iq, total * sizeof(short2), cudaMemcpyHostToDevice, e->stream));
-    return convert_and_process(e, e->stage_s16, n);
+    return process_block(e, e->stage_s16, n, true);
 }
 
 int nvx_engine_sync(nvx_engine* e) {
@@ -656,7 +682,7 @@ int nvx_engine_read_events(nvx_engine* e, int stream, int ch, char* ev, size_t c
 int nvx_engine_enable_timing(nvx_engine* e, int on) {
     if (!e) return fail(NVX_ERR_ARG, "null engine");
     int rc = sync_engine(e);
-    e->timing = on != 0;
+    e->timing = on < 0 ? 0 : on;
     return rc;
 }
 

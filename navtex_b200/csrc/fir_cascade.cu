@@ -7,8 +7,12 @@
 
 namespace nvx {
 
-template <bool kImm>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
+template <bool kImm, bool kGenNco, bool kS16>
+__global__ void __launch_bounds__(InFmt<kS16>::kWarps * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
+    using F = InFmt<kS16>;
+    constexpr int kWarpsPerCta = F::kWarps;
+    constexpr int kStages = F::kStages, kStageBytes = F::kStageBytes, kStepsPerStage = F::kSteps, kStageIn = F::kStageIn;
+    constexpr int kRowBytes = F::kRowBytes, kStepBytes = F::kStepBytes, kEl = F::kElemsPerSample;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* const wbase = smem + (size_t)warp * (kStages * kStageBytes);
@@ -43,8 +47,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) fir_cascade_ker
             const uint32_t bar = bar0 + 8 * stage;
             const long long p = pos0 + (long long)t * kStageIn;
             mbar_arrive_expect_tx(bar, kStageBytes);
-            if (p < 0) tma_load_2d(wbase_s + stage * kStageBytes, &a.map_tail, (int)(2 * (p + kHalo)), strm0, bar);
-            else       tma_load_2d(wbase_s + stage * kStageBytes, &a.map_x, (int)(2 * p), strm0, bar);
+            if (p < 0) tma_load_2d(wbase_s + stage * kStageBytes, &a.map_tail, (int)(kEl * (p + kHalo)), strm0, bar);
+            else       tma_load_2d(wbase_s + stage * kStageBytes, &a.map_x, (int)(kEl * p), strm0, bar);
         }
     };
 
@@ -66,6 +70,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) fir_cascade_ker
     // NCO phase of the first stage-1 output of a step: (70 sb_abs + 7 r10) mod 9, sb_abs = absolute
     // superblock index; identical for every lane (same time position, all streams share the chunk clock).
     int phase = (7 * ((a.sb_phase + first_sb + 9 * kWarmSuper - kWarmSuper) % kNcoPeriod)) % kNcoPeriod;
+    // general NCO: exact phase numerators of this lane's two channels at the first stage-1 output of the warm-up
+    NcoLane nl = {};
+    int nco_idx[2] = {0, 0}, nco_adv[2] = {0, 0};
+    if (kGenNco) {
+        const NcoParam np = a.nco[strm < a.streams ? strm : a.streams - 1];
+        long long k0 = ((a.sb_abs + first_sb - kWarmSuper) * (long long)(kSuper / NVX_D1)) % kNcoDen;    // 70 outputs per superblock
+        if (k0 < 0) k0 += kNcoDen;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            nco_idx[c] = (int)((k0 * np.num[c]) % kNcoDen);
+            nco_adv[c] = (int)(((long long)NVX_D2 * np.num[c]) % kNcoDen);
+            nl.step[c] = np.step[c];
+        }
+    }
     int stage = 0;
     uint32_t parity = 0;
     float2* const y3row = a.y3 + (size_t)strm * 2 * a.y3_pitch + a.y3_off + first_sb;
@@ -75,9 +93,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) fir_cascade_ker
     for (int t = 0; t < warp_stages; ++t) {
         mbar_wait(bar0 + 8 * stage, parity);
         const uint8_t* rowb = wbase + stage * kStageBytes + lane * kRowBytes;
+#ifdef NVX_ROLL_STEPS
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int u = 0; u < kStepsPerStage; ++u) {
-            cascade_step<kImm>(st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3);
+            if (kGenNco) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float t = (float)nco_idx[c] * (2.0f / kNcoDen);      // turns * 2, in [0, 2)
+                    if (t > 1.0f) t -= 2.0f;
+                    float sn, cs;
+                    sincospif(t, &sn, &cs);
+                    nl.w[c] = make_float2(cs, -sn);
+                    nco_idx[c] += nco_adv[c];
+                    if (nco_idx[c] >= kNcoDen) nco_idx[c] -= kNcoDen;
+                }
+            }
+            cascade_step<kImm, kGenNco, kS16>(st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3, nl);
             phase += 7;
             if (phase >= kNcoPeriod) phase -= kNcoPeriod;
         }
@@ -96,7 +130,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) fir_cascade_ker
     }
 }
 
-size_t cascade_smem_bytes() { return (size_t)kWarpsPerCta * kStages * kStageBytes + kWarpsPerCta * kStages * 8; }
+size_t cascade_smem_bytes(bool s16) { return s16 ? InFmt<true>::kSmemBytes : InFmt<false>::kSmemBytes; }
+int cascade_box_elems(bool s16) { return s16 ? InFmt<true>::kBoxElems : InFmt<false>::kBoxElems; }
 
 static void fill_constants(const double* h1, const double* h2, const double* h3, TapSet* t, NcoTable* n) {
     static const double d1[NVX_T1] = {NVX_H1_VALUES};
@@ -133,30 +168,44 @@ cudaError_t cascade_upload_constants(const double* h1, const double* h2, const d
 
 // warps that are resident at once across the device, leaving `reserved_sms` SMs to the sequential demod kernels:
 // the host sizes the grid to at most one full wave
-int cascade_target_warps(int device, int reserved_sms) {
+template <bool kS16>
+static int target_warps_fmt(int device, int reserved_sms) {
     int sms = 148, per_sm = kCtasPerSm;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(fir_cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cascade_smem_bytes());
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_cascade_kernel<true>, kWarpsPerCta * 32,
-                                                      cascade_smem_bytes()) != cudaSuccess || per_sm < 1)
+    auto kern = fir_cascade_kernel<true, false, kS16>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, InFmt<kS16>::kSmemBytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, InFmt<kS16>::kWarps * 32, InFmt<kS16>::kSmemBytes) != cudaSuccess ||
+        per_sm < 1)
         per_sm = kCtasPerSm;
     if (sms - reserved_sms >= 8) sms -= reserved_sms;
-    return sms * per_sm * kWarpsPerCta;
+    return sms * per_sm * InFmt<kS16>::kWarps;
+}
+int cascade_target_warps(int device, int reserved_sms, bool s16) {
+    return s16 ? target_warps_fmt<true>(device, reserved_sms) : target_warps_fmt<false>(device, reserved_sms);
 }
 
-cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, cudaStream_t stream) {
-    static bool attr_set[2] = {false, false};
-    const size_t smem = cascade_smem_bytes();
-    auto kern = custom_taps ? fir_cascade_kernel<false> : fir_cascade_kernel<true>;
-    if (!attr_set[custom_taps]) {
+template <bool kS16>
+static cudaError_t launch_fmt(const CascadeArgs& a, bool custom_taps, cudaStream_t stream) {
+    static bool attr_set[4] = {false, false, false, false};
+    const size_t smem = InFmt<kS16>::kSmemBytes;
+    const bool gen = a.nco != nullptr;
+    auto kern = gen ? (custom_taps ? fir_cascade_kernel<false, true, kS16> : fir_cascade_kernel<true, true, kS16>)
+                    : (custom_taps ? fir_cascade_kernel<false, false, kS16> : fir_cascade_kernel<true, false, kS16>);
+    const int which = (gen ? 2 : 0) + (custom_taps ? 1 : 0);
+    if (!attr_set[which]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set[custom_taps] = true;
+        attr_set[which] = true;
     }
+    constexpr int kWarpsPerCta = InFmt<kS16>::kWarps;
     const long long warps = (long long)((a.streams + 31) / 32) * a.segs;
     const unsigned grid = (unsigned)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
     kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, bool s16, cudaStream_t stream) {
+    return s16 ? launch_fmt<true>(a, custom_taps, stream) : launch_fmt<false>(a, custom_taps, stream);
 }
 
 }  // namespace nvx

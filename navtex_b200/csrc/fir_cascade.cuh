@@ -62,17 +62,43 @@ constexpr int kNcoPeriod = 9;                      // fir2cpp.C:12-14
 #ifndef NVX_CTAS_PER_SM
 #define NVX_CTAS_PER_SM 1
 #endif
-constexpr int kStepsPerStage = NVX_STEPS_PER_STAGE;
-constexpr int kStageIn = kStepIn * kStepsPerStage;             // input samples per stream per stage
-constexpr int kStepBytes = kStepIn * 8;                        // 224
-constexpr int kBoxFloats = 2 * kStageIn + NVX_ROW_PAD_FLOATS;  // TMA box width (floats); the pad is over-fetched
-constexpr int kRowBytes = kBoxFloats * 4;                      // row pitch in shared memory
-constexpr int kStageBytes = 32 * kRowBytes;                    // per warp per stage
-constexpr int kStages = NVX_STAGES;
-constexpr int kWarpsPerCta = NVX_WARPS_PER_CTA;
+#ifndef NVX_S16_STEPS_PER_STAGE
+#define NVX_S16_STEPS_PER_STAGE 2
+#endif
+#ifndef NVX_S16_ROW_PAD_BYTES
+#define NVX_S16_ROW_PAD_BYTES 16
+#endif
+#ifndef NVX_S16_STAGES
+#define NVX_S16_STAGES 3
+#endif
+#ifndef NVX_S16_WARPS_PER_CTA
+#define NVX_S16_WARPS_PER_CTA 8
+#endif
 constexpr int kCtasPerSm = NVX_CTAS_PER_SM;
-static_assert(kStepsPerSuper % kStepsPerStage == 0, "a stage must not straddle superblocks");
-static_assert(kRowBytes % 16 == 0 && kStageBytes % 128 == 0, "TMA box alignment");
+// Staging geometry per input sample format.  float2 input: 8 B / sample, 2 steps = 448 B (+16 B pad) per row.
+// short2 input (the radio's / WAV's own int16 I,Q pairs, capt_sched.c:120-128): 4 B / sample, 2 steps = 224 B (+16 B pad)
+// per row; both pads make the per-lane LDS.128 row reads bank-conflict free (row pitch = 4 or 28 words mod 32).  The
+// int16 variant is FP32-issue-bound, not HBM-bound (4.06 B / sample), so short rows cost it nothing, while a loop body
+// of more than two steps would outgrow the 32 KB L1.5 instruction cache -- with one warp per SM sub-partition an
+// instruction fetch from L2 is not hidden (measured: 5 steps per stage = 5.3 ms, 2 steps = 3.3 ms per block).  Being
+// issue-bound it also wants a second warp per sub-partition: 8 warps x 3 stages = 2.9 ms (4 warps x 6 stages: 3.27 ms).
+template <bool kS16>
+struct InFmt {
+    static constexpr int kSteps = kS16 ? NVX_S16_STEPS_PER_STAGE : NVX_STEPS_PER_STAGE;   // 28-sample steps per TMA box row
+    static constexpr int kSampleBytes = kS16 ? 4 : 8;
+    static constexpr int kStepBytes = kStepIn * kSampleBytes;
+    static constexpr int kStageIn = kSteps * kStepIn;                                     // input samples per stream per stage
+    static constexpr int kRowBytes = kSteps * kStepBytes + (kS16 ? NVX_S16_ROW_PAD_BYTES : NVX_ROW_PAD_FLOATS * 4);
+    static constexpr int kBoxElems = kRowBytes / 4;                                       // TMA box width in 32-bit elements (pad over-fetched)
+    static constexpr int kElemsPerSample = kSampleBytes / 4;
+    static constexpr int kStageBytes = 32 * kRowBytes;                                    // per warp per stage
+    static constexpr int kStages = kS16 ? NVX_S16_STAGES : NVX_STAGES;
+    static constexpr int kWarps = kS16 ? NVX_S16_WARPS_PER_CTA : NVX_WARPS_PER_CTA;      // per CTA
+    static constexpr int kSmemBytes = kWarps * kStages * kStageBytes + kWarps * kStages * 8;
+    static_assert(kStepsPerSuper % kSteps == 0, "a stage must not straddle superblocks");
+    static_assert(kRowBytes % 16 == 0 && kStageBytes % 128 == 0 && kBoxElems <= 256, "TMA box alignment");
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
+};
 constexpr int kLive1 = 9, kLive2 = 6, kLive3 = 8;  // partial sums carried between steps
 
 __device__ constexpr double kH1[NVX_T1] = {NVX_H1_VALUES};
@@ -90,9 +116,18 @@ struct TapSet {
 struct NcoTable { float2 w[kNcoPeriod + NVX_D2]; };
 
 
+// Per-stream channel offsets other than the reference's +-14 kHz (fir2cpp.C:12-14 generalised): the phase of stage-1
+// output k is k * f / 63000 turns, tracked exactly as an integer numerator over 126000 (f on a 0.5 Hz grid); every
+// 28-sample step re-seeds the phasor from that exact phase (sincospif) and advances it by six complex multiplies.
+constexpr int kNcoDen = 126000;
+struct NcoParam {
+    int num[2];        // (2 f) mod 126000, per channel
+    float2 step[2];    // (cos, -sin)(2 pi f / 63000): rotation per stage-1 output
+};
+
 struct CascadeArgs {
-    CUtensorMap map_x;    // float32 view [S][2 n] of this chunk (stream-major IQ), box 56 x 32
-    CUtensorMap map_tail; // float32 view [S][2 kHalo]: the kHalo samples that preceded the chunk (zeros at start)
+    CUtensorMap map_x;    // 32-bit view [S][2 n] (float2 input) or [S][n] (short2 input) of this chunk, box InFmt::kBoxElems x 32
+    CUtensorMap map_tail; // same view of [S][kHalo]: the kHalo samples that preceded the chunk (zeros at start)
     float2* y3;           // [S][2][y3_pitch] 900 Hz output; this chunk's samples start at y3_off
     long long n;          // samples per stream in this chunk (multiple of kSuper)
     int streams;
@@ -100,6 +135,8 @@ struct CascadeArgs {
     int seg_super;        // superblocks per segment (last one may be short)
     int n_super;          // n / kSuper
     int sb_phase;         // (absolute superblock index of chunk start) mod 9
+    long long sb_abs;     // absolute superblock index of chunk start
+    const NcoParam* nco;  // [S] per-stream NCO (kernel variants with kGenNco), else null
     long long y3_pitch;
     long long y3_off;
 };
@@ -147,9 +184,24 @@ struct CascadeState {
 // One step: 28 inputs of one row -> 7 stage-1 outputs -> mix -> one stage-2 output per channel ->
 // scattered into the stage-3 partial sums.  r10 = position of this step inside its superblock.
 // y3 is written when r10 == 9 completed a 900 Hz sample.
-template <bool kImm>
+// Per-lane phasors of the general NCO (unused by the reference-table variants)
+struct NcoLane {
+    float2 w[2];      // current (cos, -sin) per channel
+    float2 step[2];
+};
+
+// (double)short of capt_sched.c:511, exact in float, without the quarter-rate I2F unit: flip the sign bits (offset
+// binary u = v + 32768), drop each half under the exponent of 2^23 (PRMT), subtract 2^23 + 32768 with one packed add
+__device__ __forceinline__ float2 iq_of(int packed) {
+    const unsigned w = (unsigned)packed ^ 0x80008000u;
+    const float2 biased = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)),
+                                      __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)));
+    return __fadd2_rn(biased, make_float2(-8421376.0f, -8421376.0f));
+}
+
+template <bool kImm, bool kGenNco, bool kS16>
 __device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __restrict__ row, int nco_phase,
-                                             const int r10, float2 (&y3)[2]) {
+                                             const int r10, float2 (&y3)[2], NcoLane& nl) {
     float2 w[kLive1 + NVX_D2];
 #pragma unroll
     for (int j = 0; j < kLive1; ++j) w[j] = st.a1[j];
@@ -167,9 +219,15 @@ __device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __r
 #pragma unroll
     for (int q = 0; q < NVX_D2; ++q) {
         // four inputs complete stage-1 output q of this step
-        const float4 v0 = row[2 * q], v1 = row[2 * q + 1];
-        const float2 xs[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y),
-                              make_float2(v1.z, v1.w)};
+        float2 xs[4];
+        if (kS16) {
+            const int4 v = reinterpret_cast<const int4*>(row)[q];
+            xs[0] = iq_of(v.x); xs[1] = iq_of(v.y); xs[2] = iq_of(v.z); xs[3] = iq_of(v.w);
+        } else {
+            const float4 v0 = row[2 * q], v1 = row[2 * q + 1];
+            xs[0] = make_float2(v0.x, v0.y); xs[1] = make_float2(v0.z, v0.w);
+            xs[2] = make_float2(v1.x, v1.y); xs[3] = make_float2(v1.z, v1.w);
+        }
 #pragma unroll
         for (int r = 0; r < NVX_D1; ++r) {
 #pragma unroll
@@ -177,11 +235,21 @@ __device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __r
         }
         const float2 y1 = w[q];
         // NCO mix (fir2cpp.C:115-124): ch0 = y1 * (re + j im), ch1 = y1 * (re - j im), (re, im) = (cos, -sin)
-        const float2 rot = c_nco.w[nco_phase + q];
-        const float ar = y1.x * rot.x, br = y1.y * rot.x;
         float2 m[2];
-        m[0] = make_float2(fmaf(-y1.y, rot.y, ar), fmaf(y1.x, rot.y, br));
-        m[1] = make_float2(fmaf(y1.y, rot.y, ar), fmaf(-y1.x, rot.y, br));
+        if (kGenNco) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float2 rot = nl.w[c];
+                m[c] = make_float2(fmaf(-y1.y, rot.y, y1.x * rot.x), fmaf(y1.x, rot.y, y1.y * rot.x));
+                if (q + 1 < NVX_D2)     // advance the phasor: w *= step
+                    nl.w[c] = make_float2(fmaf(-rot.y, nl.step[c].y, rot.x * nl.step[c].x), fmaf(rot.x, nl.step[c].y, rot.y * nl.step[c].x));
+            }
+        } else {
+            const float2 rot = c_nco.w[nco_phase + q];
+            const float ar = y1.x * rot.x, br = y1.y * rot.x;
+            m[0] = make_float2(fmaf(-y1.y, rot.y, ar), fmaf(y1.x, rot.y, br));
+            m[1] = make_float2(fmaf(y1.y, rot.y, ar), fmaf(-y1.x, rot.y, br));
+        }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll

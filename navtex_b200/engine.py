@@ -25,6 +25,7 @@ class Config(C.Structure):
         ("device", C.c_int), ("n_streams", C.c_int), ("max_block", C.c_longlong), ("freq_tag", C.c_int * 2),
         ("h1", C.POINTER(C.c_double)), ("h2", C.POINTER(C.c_double)), ("h3", C.POINTER(C.c_double)),
         ("keep_bits", C.c_int), ("first_stream_id", C.c_int),
+        ("nco_hz", C.POINTER(C.c_double)), ("stream_freq_tag", C.POINTER(C.c_int)),
     ]
 
 
@@ -110,7 +111,7 @@ class Engine:
     """One GPU, S streams.  Mirrors the reference's init / per-sample push / add_message flow, batched."""
 
     def __init__(self, n_streams: int, max_block: int, device: int = 0, keep_bits: bool = False, taps=None,
-                 first_stream_id: int = 0):
+                 first_stream_id: int = 0, nco_hz=None, stream_freq_tag=None):
         L = load_library()
         cfg = Config()
         L.nvx_default_config(C.byref(cfg))
@@ -121,6 +122,12 @@ class Engine:
             self._taps = [np.ascontiguousarray(t, dtype=np.float64) for t in taps]
             assert [len(t) for t in self._taps] == [37, 47, 71]
             cfg.h1, cfg.h2, cfg.h3 = (t.ctypes.data_as(C.POINTER(C.c_double)) for t in self._taps)
+        if nco_hz is not None:           # [S, 2] per-stream channel offsets in Hz
+            self._nco = np.ascontiguousarray(nco_hz, dtype=np.float64).reshape(n_streams, 2)
+            cfg.nco_hz = self._nco.ctypes.data_as(C.POINTER(C.c_double))
+        if stream_freq_tag is not None:
+            self._tags = np.ascontiguousarray(stream_freq_tag, dtype=np.int32).reshape(n_streams, 2)
+            cfg.stream_freq_tag = self._tags.ctypes.data_as(C.POINTER(C.c_int))
         self._h = C.c_void_p()
         _check(L.nvx_engine_create(C.byref(cfg), C.byref(self._h)))
         self.L, self.S, self.max_block, self.device = L, n_streams, max_block, device
@@ -189,8 +196,10 @@ class Engine:
         _check(self.L.nvx_engine_read_events(self._h, stream, ch, ev.ctypes.data_as(C.c_void_p), cap, C.byref(got)))
         return ev[: got.value].tobytes()
 
-    def enable_timing(self, on: bool = True):
-        _check(self.L.nvx_engine_enable_timing(self._h, int(on)), allow_overflow=True)
+    def enable_timing(self, level=2):
+        """0/False off, 1 fused-FIR kernel only, 2/True every stage."""
+        level = 2 if level is True else int(level)
+        _check(self.L.nvx_engine_enable_timing(self._h, level), allow_overflow=True)
 
     def stats(self, reset: bool = True) -> Stats:
         st = Stats()
