@@ -199,6 +199,100 @@ def impl_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_config4(args, torch, dist, device, rank, world, local, barrier):
+    """BASELINE.json configs[3]: 8192 streams per GPU (65536 over 8 GPUs) x 60 s of traffic, too large to be resident
+    (124 GB per 8 s as float2): generated on the device block by block (counter-based generator keyed by
+    (seed, stream, absolute sample): any block of any stream is reproducible) and decoded through the carried state.
+    Generation is untimed: see the comment at the timed loop."""
+    import numpy as np
+    from navtex_b200 import engine, sharding, synth
+
+    S = 8192
+    block = 1125 * 280                               # 1.25 s per stream per block: 20.6 GB of float2 per GPU
+    n_blocks = max(1, int(round(args.seconds * 252000 / block)))
+    seconds = n_blocks * block / 252000
+    rng = np.random.default_rng(65536 + rank)
+    bits, off, start, amp, sigma, expect = [], [], [], [], [], []
+    for s in range(S):
+        text, bbbb = synth.random_message(rng, n_lines=2, words_per_line=4)
+        b = synth.message_bits(text, n_phasing=30, n_tail=6)
+        dur = len(b) / 100.0
+        bits.append(b)
+        ch = s % 2
+        off.append(14000.0 if ch == 0 else -14000.0)
+        start.append(0.3 + max(0.0, seconds - dur - 1.5) * rng.random())
+        amp.append(3000.0 + 6000.0 * rng.random())
+        sigma.append(amp[-1] * 10 ** (rng.uniform(-6.0, 14.0) / 20) / np.sqrt(2))
+        if start[-1] + dur + 0.5 < seconds:
+            expect.append((s + rank * S, 518 if ch == 0 else 490, bbbb, text))
+    bufs = [torch.empty((S, block, 2), dtype=torch.float32, device=device) for _ in range(2)]
+    eng = engine.Engine(S, block, device=local, first_stream_id=rank * S)
+    es = torch.cuda.ExternalStream(eng.stream, device=device)
+
+    def generate(k):
+        engine.synth_fill_device(local, bufs[k % 2].data_ptr(), S, k * block, block, bits, off, start, amp, sigma,
+                                 seed=65536 + rank, cuda_stream=eng.stream)
+
+    generate(0)
+    eng.push_device(bufs[0].data_ptr(), block)       # warm-up (engine reset afterwards)
+    eng.poll_messages()
+    eng.reset()
+    eng.enable_timing(1)
+    eng.stats()
+    barrier()
+    # The generator call is host-synchronous (it ends with a device-wide sync), so the engine's stream is idle when a
+    # block is pushed: events on that stream around the push bracket exactly the block's cascade, tail carry and
+    # feed-forward demod kernels; the block's sequential kernels run on the demod stream beside the next generator
+    # call (in the resident benchmark: beside the next cascade).  The last block's remainder is added at the end.
+    spans = []
+    t_wall0 = time.time()
+    for k in range(n_blocks):
+        generate(k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(es)
+        eng.push_device(bufs[k % 2].data_ptr(), block)
+        e1.record(es)
+        spans.append((e0, e1))
+    e2 = torch.cuda.Event(enable_timing=True)
+    eng.sync()
+    e2.record(es)
+    torch.cuda.synchronize()
+    t_all = (time.time() - t_wall0) * 1e3
+    dec_ms = sum(a.elapsed_time(b) for a, b in spans) + spans[-1][1].elapsed_time(e2)
+    t = torch.tensor([dec_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dec_ms = float(t.item())
+    st = eng.stats()
+    msgs = eng.poll_messages()
+    got = {(m[0], m[1], m[2], m[3]) for m in msgs}
+    ok = sum(1 for e in expect if e in got)
+    merged = sharding.gather_messages(msgs)
+    if rank != 0:
+        return
+    total = world * S * block * n_blocks
+    peak, peak_src = measured_peak()
+    casc_ms = st.cascade_ms / max(1, st.cascade_launches)
+    print(json.dumps({
+        "metric": "iq_msamples_per_s", "value": total / (dec_ms * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": world,
+        "steps": n_blocks, "warmup": 1, "ms_per_step": dec_ms / n_blocks, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[3]: 8192 streams per GPU x %.1f s of traffic, generated on the device per 1.25 s block" % seconds,
+                   "streams_per_gpu": S, "samples_per_stream_per_step": block, "blocks": n_blocks,
+                   "input": "float2 IQ, 20.6 GB per block per GPU, regenerated every block (nothing cache-warm)",
+                   "parallelism": f"stream-sharded x{world}, no collectives"},
+        "timing": {"decode_ms": dec_ms, "wall_ms_including_generation": t_all,
+                   "how": "sum over blocks of the CUDA-event span of each push on the engine stream (generator untimed) + drain of the last block"},
+        "realtime_streams": total / (dec_ms * 1e-3) / 252000,
+        "roofline": {"bound": "hbm", "achieved": S * block * BYTES_PER_SAMPLE / (casc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": S * block * BYTES_PER_SAMPLE / (casc_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "nvx::fir_cascade_kernel<true,false,false>", "kernel_ms": casc_ms},
+        "gpu_launches": int(st.cascade_launches + st.demod_launches + st.aux_launches),
+        "check": {"bulletins_complete_in_capture": len(expect), "decoded_exact": ok, "messages_total": len(msgs),
+                  "messages_gathered_all_ranks": len(merged) if merged is not None else 0},
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +300,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
+                    help="config2 (default, the metric's configuration): 1024 streams/GPU resident; config4: 8192 streams/GPU x "
+                         "--seconds of traffic generated on the device block by block (BASELINE.json configs[3])")
+    ap.add_argument("--seconds", type=float, default=60.0, help="config4: traffic per stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,6 +329,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.workload == "config4":
+        run_config4(args, torch, dist, device, rank, world, local, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     S = STREAMS_PER_GPU
     x, expect = build_workload(torch, device, rank)
@@ -280,6 +384,40 @@ def main():
     max_ms = float(t.item())
     total_samples = world * S * BLOCK * args.steps
     value = total_samples / (max_ms * 1e-3) / 1e6                     # Msamples/s
+
+    # ---- secondary: the same captures resident as int16 I,Q (the radio's own format), fused-ingest kernel variant ----
+    x16 = x.round().to(torch.int16)
+    eng16 = engine.Engine(S, BLOCK, device=local, first_stream_id=rank * S)
+    s16s = torch.cuda.ExternalStream(eng16.stream, device=device)
+    for _ in range(args.warmup):
+        eng16.push_device(x16.data_ptr(), BLOCK, s16=True)
+    eng16.poll_messages()
+    eng16.enable_timing(1)
+    eng16.stats()
+    k16 = min(args.steps, 20)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(s16s)
+    for _ in range(k16):
+        eng16.push_device(x16.data_ptr(), BLOCK, s16=True)
+    eng16.sync()
+    b1.record(s16s)
+    barrier()
+    st16 = eng16.stats()
+    got16 = {(m[0], m[1], m[2], m[3]) for m in eng16.poll_messages()}
+    t16 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+    casc16_ms = st16.cascade_ms / max(1, st16.cascade_launches)
+    int16_input = {
+        "value": world * S * BLOCK * k16 / (float(t16.item()) * 1e-3) / 1e6, "unit": "Msamples/s", "steps": k16,
+        "ms_per_step": float(t16.item()) / k16, "kernel": "nvx::fir_cascade_kernel<true,false,true> (short2 rows by TMA, PRMT/FADD2 conversion)",
+        "kernel_ms": casc16_ms, "algorithmic_bytes_per_sample": 4.0 + 16.0 / 280,
+        "achieved_gbs": S * BLOCK * (4.0 + 16.0 / 280) / (casc16_ms * 1e-3) / 1e9, "bound": "fp32 issue (not HBM)",
+        "decoded_exact": sum(1 for e in expect if e in got16),
+    }
+    eng16.close()
+    del x16, eng16
 
     cpu_sample = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -373,7 +511,7 @@ def main():
                    "input": "float2 IQ resident in HBM, 21.2 GB per GPU per step (larger than L2; no flush needed)",
                    "parallelism": f"stream-sharded x{world}, no collectives"},
         "realtime_streams": value / 0.252,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "int16_input": int16_input,
         "gpu_launches": int(st.cascade_launches + st.demod_launches + st.aux_launches),
         "clocks": clocks,
         "check": {"bulletins_expected_per_step": len(expect), "decoded_exact": decoded_ok, "messages_total": len(msgs), "messages_gathered_all_ranks": gathered,

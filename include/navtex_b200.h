@@ -51,7 +51,9 @@ typedef struct {
     int n_streams;              /* S */
     long long max_block;        /* largest n a push will carry (samples per stream) */
     int freq_tag[2];            /* tags handed to add_message for channel 0 (+14 kHz) / 1 (-14 kHz); 0,0 = 518,490 */
-    /* optional replacement tap sets of the reference lengths 37 / 47 / 71 (NULL = reference taps) */
+    /* optional replacement tap sets (NULL = reference taps).  With n1 = n2 = n3 = 0 they have the reference lengths
+     * 37 / 47 / 71 and run through the fused cascade kernel; other lengths (1 .. 1024, e.g. the 255-tap stress designs)
+     * select the long-tap path: one register-tiled FIR kernel per stage, intermediates in HBM */
     const double *h1, *h2, *h3;
     int keep_bits;              /* record 'B'/'Y' decisions and discriminator sums for nvx_engine_read_bits */
     int first_stream_id;        /* global id of stream 0 (multi-GPU sharding; only used to label messages) */
@@ -61,6 +63,7 @@ typedef struct {
     const double *nco_hz;
     /* optional per-stream tags [n_streams][2] handed to add_message instead of freq_tag (e.g. 4209 for 4209.5 kHz) */
     const int *stream_freq_tag;
+    int n1, n2, n3;             /* tap counts of h1 / h2 / h3; 0 = reference length */
 } nvx_config;
 
 typedef struct {

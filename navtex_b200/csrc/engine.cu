@@ -21,6 +21,7 @@
 #include "../../include/navtex_b200.h"
 #include "demod.cuh"
 #include "fir_cascade.cuh"
+#include "fir_long.cuh"
 #include "message_assembler.h"
 
 namespace nvx {
@@ -124,6 +125,12 @@ struct nvx_engine {
     int last_P = 0;
     bool custom_taps = false;
     nvx::NcoParam* d_nco = nullptr;       // per-stream NCO parameters (general-NCO kernel variant), else null
+    // long-tap path (tap counts other than 37 / 47 / 71): per-stage kernels, intermediates and histories in HBM
+    bool long_taps = false;
+    nvx::LongStage lst[3];
+    float2* lhist[3][2] = {};             // [stage][ping-pong]: [rows][H]
+    float2 *y1buf = nullptr, *y2buf = nullptr;
+    int lcur = 0;
     std::vector<int> stream_tag;          // optional [S][2] message tags
     bool serial = false;                  // NVX_PIPELINE=serial: the next cascade waits for this block's whole demod
     bool ff_on_main = true;               // feed-forward demod kernels follow the cascade on the main stream
@@ -169,6 +176,8 @@ int free_engine(nvx_engine* e) {
     cudaFree(e->db.bitpos); cudaFree(e->db.bitval); cudaFree(e->db.nbits);
     cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
     cudaFree(e->stage_f32); cudaFree(e->stage_s16); cudaFree(e->d_nco);
+    for (int k = 0; k < 3; ++k) { cudaFree(e->lhist[k][0]); cudaFree(e->lhist[k][1]); }
+    cudaFree(e->y1buf); cudaFree(e->y2buf);
     for (int k = 0; k < kBuf; ++k) {
         cudaFree(e->y3buf[k]); cudaFree(e->d_events[k]); cudaFree(e->d_ev_count[k]);
         cudaFreeHost(e->h_events[k]); cudaFreeHost(e->h_ev_count[k]);
@@ -188,6 +197,11 @@ int reset_state(nvx_engine* e) {
         for (int k = 0; k < 2; ++k)
             CU_TRY(cudaMemsetAsync(e->tail[f][k], 0, (size_t)e->S * nvx::kHalo * (f ? sizeof(short2) : sizeof(float2)), e->stream));
     e->fmt = -1;
+    if (e->long_taps)
+        for (int k = 0; k < 3; ++k)
+            for (int q = 0; q < 2; ++q)
+                CU_TRY(cudaMemsetAsync(e->lhist[k][q], 0, (size_t)(k == 2 ? e->channels : e->S) * e->lst[k].H * sizeof(float2), e->stream));
+    e->lcur = 0;
     for (int k = 0; k < kBuf; ++k) {
         e->db.y3 = e->y3buf[k];
         e->db.picks = e->pickbuf[k];
@@ -362,11 +376,31 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         }
         CU_TRY(cudaEventRecord(t0, e->stream));
     }
-    CU_TRY(cascade_launch(ca, e->custom_taps, s16, e->stream));
+    if (e->long_taps) {
+        const int cur = e->lcur, nx = cur ^ 1;
+        const long long p1 = e->cfg.max_block / NVX_D1, p2 = e->cfg.max_block / (NVX_D1 * NVX_D2);
+        LongArgs la = {};
+        la.in = d_x; la.hist = e->lhist[0][cur]; la.out = e->y1buf; la.n_in = n; la.out_pitch = p1; la.out_off = 0;
+        la.rows_in = e->S; la.stage = 0; la.s16 = s16;
+        CU_TRY(long_launch(la, e->lst[0], n, e->stream));
+        CU_TRY(long_carry(e->lhist[0][cur], d_x, n, e->lhist[0][nx], e->S, e->lst[0].H, n, s16, e->stream));
+        la.in = e->y1buf; la.hist = e->lhist[1][cur]; la.out = e->y2buf; la.n_in = n / NVX_D1; la.out_pitch = p2;
+        la.stage = 1; la.s16 = 0; la.k_abs = e->sb_abs * (kSuper / NVX_D1); la.nco = e->d_nco;
+        CU_TRY(long_launch(la, e->lst[1], p1, e->stream));
+        CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->S, e->lst[1].H, n / NVX_D1, 0, e->stream));
+        la.in = e->y2buf; la.hist = e->lhist[2][cur]; la.out = e->y3buf[b]; la.n_in = n / (NVX_D1 * NVX_D2);
+        la.out_pitch = ca.y3_pitch; la.out_off = ca.y3_off; la.rows_in = e->channels; la.stage = 2; la.nco = nullptr;
+        CU_TRY(long_launch(la, e->lst[2], p2, e->stream));
+        CU_TRY(long_carry(e->lhist[2][cur], e->y2buf, p2, e->lhist[2][nx], e->channels, e->lst[2].H, la.n_in, 0, e->stream));
+        e->lcur = nx;
+        e->stats.aux_launches += 5;
+    } else {
+        CU_TRY(cascade_launch(ca, e->custom_taps, s16, e->stream));
+    }
     if (e->timing) CU_TRY(cudaEventRecord(t1, e->stream));
 
     const int nxt = e->tail_cur ^ 1;
-    {
+    if (!e->long_taps) {
         const long long work = (long long)e->S * (kHalo / (s16 ? 4 : 2));
         const unsigned grid = (unsigned)((work + 255) / 256);
         if (s16)
@@ -487,6 +521,19 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     e->channels = 2 * e->S;
     e->P_max = (int)(cfg->max_block / nvx::kSuper);
     e->custom_taps = cfg->h1 || cfg->h2 || cfg->h3;
+    e->long_taps = cfg->n1 || cfg->n2 || cfg->n3;
+    if (e->long_taps) {
+        const int n[3] = {cfg->n1 ? cfg->n1 : NVX_T1, cfg->n2 ? cfg->n2 : NVX_T2, cfg->n3 ? cfg->n3 : NVX_T3};
+        const int D[3] = {NVX_D1, NVX_D2, NVX_D3};
+        if ((cfg->n1 && !cfg->h1) || (cfg->n2 && !cfg->h2) || (cfg->n3 && !cfg->h3)) {
+            delete e;
+            return fail(NVX_ERR_ARG, "a tap count was given without its tap array");
+        }
+        for (int k = 0; k < 3; ++k) {
+            if (n[k] < 1 || n[k] > nvx::kLongMaxTaps) { delete e; return fail(NVX_ERR_ARG, "tap count %d outside 1..%d", n[k], nvx::kLongMaxTaps); }
+            e->lst[k] = nvx::long_stage(D[k], n[k]);
+        }
+    }
     // per block and channel: at most one character plus one abort per 14 bits ... generous bound
     e->ev_cap = 2 * (e->P_max / 63 + 2) + 8;
     e->bit_cap = cfg->keep_bits ? e->P_max / 9 + 2 : 0;
@@ -542,7 +589,18 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         CREATE_TRY(cudaMalloc(&e->d_bit_count, sizeof(int) * e->channels));
         CREATE_TRY(cudaMemset(e->d_bit_count, 0, sizeof(int) * e->channels));
     }
-    CREATE_TRY(nvx::cascade_upload_constants(cfg->h1, cfg->h2, cfg->h3, e->stream));
+    if (e->long_taps) {
+        static const double d1[NVX_T1] = {NVX_H1_VALUES}, d2[NVX_T2] = {NVX_H2_VALUES}, d3[NVX_T3] = {NVX_H3_VALUES};
+        CREATE_TRY(nvx::long_upload_taps(cfg->h1 ? cfg->h1 : d1, e->lst[0].T, cfg->h2 ? cfg->h2 : d2, e->lst[1].T,
+                                         cfg->h3 ? cfg->h3 : d3, e->lst[2].T, e->stream));
+        for (int k = 0; k < 3; ++k)
+            for (int q = 0; q < 2; ++q)
+                CREATE_TRY(cudaMalloc(&e->lhist[k][q], (size_t)(k == 2 ? e->channels : e->S) * e->lst[k].H * sizeof(float2)));
+        CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->S * (cfg->max_block / NVX_D1) * sizeof(float2)));
+        CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));
+    } else {
+        CREATE_TRY(nvx::cascade_upload_constants(cfg->h1, cfg->h2, cfg->h3, e->stream));
+    }
     if (!nco.empty()) {
         CREATE_TRY(cudaMalloc(&e->d_nco, nco.size() * sizeof(nvx::NcoParam)));
         CREATE_TRY(cudaMemcpy(e->d_nco, nco.data(), nco.size() * sizeof(nvx::NcoParam), cudaMemcpyHostToDevice));

@@ -1,0 +1,218 @@
+// fir_long.cu -- register-tiled polyphase decimating FIR kernels for long tap sets (see fir_long.cuh).
+#include "fir_long.cuh"
+
+#include <math.h>
+
+namespace nvx {
+
+namespace {
+
+constexpr int kTapSlots = 1152;                     // per stage: D * J <= 1024 + D * kLongR
+__constant__ float c_long_taps[3][kTapSlots];       // [stage][p * J + j] = h[D j + D - 1 - p] (0 beyond T)
+__constant__ float2 c_long_nco[kNcoPeriod];         // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
+
+__device__ __forceinline__ float2 ffma2s(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+
+__device__ __forceinline__ float2 load_sample(const LongArgs& a, int row, long long in_pitch, int H, long long g) {
+    if (g < 0) return a.hist[(size_t)row * H + (H + g)];
+    if (g >= a.n_in) return make_float2(0.f, 0.f);
+    if (a.s16) {
+        const short2 v = static_cast<const short2*>(a.in)[(size_t)row * in_pitch + g];
+        return make_float2((float)v.x, (float)v.y);
+    }
+    return static_cast<const float2*>(a.in)[(size_t)row * in_pitch + g];
+}
+
+// Shared-memory layout of a tile: the inputs in their natural (interleaved) order, f = sample index relative to the
+// tile's first input, with one pad slot after every 8 D samples: slot(f) = f + f / (8 D).  A thread's outputs are 8
+// apart from its neighbour's, i.e. 8 D inputs: the pad turns that lane stride into 8 D + 1 (odd), so both the staging
+// stores (consecutive f) and the window loads (fixed phase, lane stride 8 D + 1) are bank-conflict free, and the
+// staging needs no de-interleaving arithmetic.
+template <int D>
+__device__ __forceinline__ int slot(int f) { return f + f / (kLongR * D); }
+
+// grid (tiles, output rows); STAGE 1 (the second stage) has two output rows (channels) per input row and mixes while staging
+template <int D, int STAGE>
+__global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a, const int J, const long long in_pitch) {
+    extern __shared__ __align__(16) float2 s_x[];
+    const int H = D * J;
+    const int F = D * (kLongTile + J - 1);                    // inputs staged per tile
+    const int row_out = blockIdx.y;
+    const int row_in = STAGE == 1 ? row_out >> 1 : row_out;
+    const int ch = row_out & 1;
+    const long long k0 = (long long)blockIdx.x * kLongTile;  // first output of the tile
+    const long long n_out = a.n_in / D;
+    const long long g0 = (long long)D * (k0 - J + 1);        // first input the tile needs (oldest tap of output k0)
+
+    // ---- stage the tile; stage 2 rotates by the channel's NCO on the way in ----
+    NcoParam np = {};
+    if (STAGE == 1 && a.nco) np = a.nco[row_in];
+    constexpr int kBatch = 8;                                 // loads in flight per thread (the staging is latency-bound)
+    for (int base = 0; base < F; base += kLongThreads * kBatch) {
+        float2 v[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            const int f = base + i * kLongThreads + (int)threadIdx.x;
+            v[i] = f < F ? load_sample(a, row_in, in_pitch, H, g0 + f) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            const int f = base + i * kLongThreads + (int)threadIdx.x;
+            if (f >= F) break;
+            float2 x = v[i];
+            if (STAGE == 1) {
+                const long long g = g0 + f;
+                float2 rot;
+                if (a.nco) {
+                    long long k = (a.k_abs + g) % kNcoDen;
+                    if (k < 0) k += kNcoDen;
+                    const int ph = (int)((k * np.num[ch]) % kNcoDen);
+                    float t = (float)ph * (2.0f / kNcoDen);
+                    if (t > 1.0f) t -= 2.0f;
+                    float sn, cs;
+                    sincospif(t, &sn, &cs);
+                    rot = make_float2(cs, -sn);
+                } else {
+                    long long k = (a.k_abs + g) % kNcoPeriod;
+                    if (k < 0) k += kNcoPeriod;
+                    rot = c_long_nco[k];
+                    if (ch) rot.y = -rot.y;                   // "490": conjugate rotation (fir2cpp.C:121-124)
+                }
+                x = make_float2(fmaf(-x.y, rot.y, x.x * rot.x), fmaf(x.x, rot.y, x.y * rot.x));
+            }
+            s_x[slot<D>(f)] = x;
+        }
+    }
+    __syncthreads();
+
+    // ---- R consecutive outputs per thread ----
+    // Output k0 + R t + u, tap j = jb + jj of phase p reads position R (q - 1) + (u - jj + R - 1) of that phase, q = t +
+    // (J - jb) / R, i.e. input f = D pos + p.  The window win[i] holds positions R (q - 1) + i, i < 2 R - 1; since
+    // D i + p < 8 D exactly when i < 8, its slots are (8 D + 1)(q - 1) + D i + p + (i >= 8).
+    const int t = threadIdx.x;
+    float2 acc[kLongR];
+#pragma unroll
+    for (int u = 0; u < kLongR; ++u) acc[u] = make_float2(0.f, 0.f);
+    const float* taps = c_long_taps[STAGE];
+    constexpr int kLane = kLongR * D + 1;
+#pragma unroll 1
+    for (int p = 0; p < D; ++p) {
+        const float* hp = taps + p * J;
+        const float2* sp = s_x + kLane * (t + J / kLongR - 1) + p;     // window base of tap block 0
+        float2 win[2 * kLongR - 1];
+#pragma unroll
+        for (int i = 0; i < 2 * kLongR - 1; ++i) win[i] = sp[D * i + (i >= kLongR)];
+#pragma unroll 1
+        for (int jb = 0; jb < J; jb += kLongR) {
+#pragma unroll
+            for (int jj = 0; jj < kLongR; ++jj) {
+                const float h = hp[jb + jj];
+#pragma unroll
+                for (int u = 0; u < kLongR; ++u) acc[u] = ffma2s(win[u - jj + kLongR - 1], h, acc[u]);
+            }
+            // slide one tap block towards older samples
+            sp -= kLane;
+#pragma unroll
+            for (int i = 2 * kLongR - 2; i >= kLongR; --i) win[i] = win[i - kLongR];
+            if (jb + kLongR < J) {
+#pragma unroll
+                for (int i = 0; i < kLongR; ++i) win[i] = sp[D * i];
+            }
+        }
+    }
+    float2* out = a.out + (size_t)row_out * a.out_pitch + a.out_off + k0 + (long long)kLongR * t;
+#pragma unroll
+    for (int u = 0; u < kLongR; ++u)
+        if (k0 + (long long)kLongR * t + u < n_out) out[u] = acc[u];
+}
+
+template <typename Sample>
+__global__ void long_carry_kernel(const float2* __restrict__ old_hist, const Sample* __restrict__ block, long long pitch,
+                                  float2* __restrict__ new_hist, int rows, int H, long long n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * H) return;
+    const int row = (int)(idx / H), i = (int)(idx % H);
+    const long long src = n - H + i;
+    float2 v;
+    if (src >= 0) {
+        const Sample s = block[(size_t)row * pitch + src];
+        v = make_float2((float)s.x, (float)s.y);
+    } else {
+        v = old_hist[(size_t)row * H + (H + src)];
+    }
+    new_hist[(size_t)row * H + i] = v;
+}
+
+template <int D, int STAGE>
+cudaError_t launch_one(const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream) {
+    const int F = D * (kLongTile + st.J - 1);
+    const size_t smem = (size_t)(F + F / (kLongR * D) + 2) * sizeof(float2);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(fir_long_kernel<D, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    const long long n_out = a.n_in / D;
+    const int rows_out = STAGE == 1 ? 2 * a.rows_in : a.rows_in;
+    fir_long_kernel<D, STAGE><<<dim3((unsigned)((n_out + kLongTile - 1) / kLongTile), (unsigned)rows_out), kLongThreads, smem, stream>>>(
+        a, st.J, in_pitch);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+LongStage long_stage(int D, int T) {
+    LongStage s;
+    s.D = D;
+    s.T = T;
+    const int per_phase = (T + D - 1) / D;
+    s.J = (per_phase + kLongR - 1) / kLongR * kLongR;
+    s.H = D * s.J;
+    return s;
+}
+
+cudaError_t long_upload_taps(const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, cudaStream_t stream) {
+    static float host[3][kTapSlots];
+    const double* h[3] = {h1, h2, h3};
+    const int n[3] = {n1, n2, n3}, D[3] = {NVX_D1, NVX_D2, NVX_D3};
+    for (int s = 0; s < 3; ++s) {
+        const LongStage st = long_stage(D[s], n[s]);
+        if (n[s] < 1 || n[s] > kLongMaxTaps || st.D * st.J > kTapSlots) return cudaErrorInvalidValue;
+        for (int k = 0; k < kTapSlots; ++k) host[s][k] = 0.f;
+        for (int p = 0; p < st.D; ++p)
+            for (int j = 0; j < st.J; ++j) {
+                const int i = st.D * j + st.D - 1 - p;
+                host[s][p * st.J + j] = i < n[s] ? (float)h[s][i] : 0.f;
+            }
+    }
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_long_taps, host, sizeof host, 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    float2 nco[kNcoPeriod];
+    for (int k = 0; k < kNcoPeriod; ++k)       // same expression as fir2cpp.C:105-106, rounded once to float
+        nco[k] = make_float2((float)cos((2 * M_PI * k * 14000) / 63000), (float)-sin((2 * M_PI * k * 14000) / 63000));
+    e = cudaMemcpyToSymbolAsync(c_long_nco, nco, sizeof nco, 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(stream);
+}
+
+cudaError_t long_launch(const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream) {
+    switch (a.stage) {
+        case 0: return launch_one<NVX_D1, 0>(a, st, in_pitch, stream);
+        case 1: return launch_one<NVX_D2, 1>(a, st, in_pitch, stream);
+        default: return launch_one<NVX_D3, 2>(a, st, in_pitch, stream);
+    }
+}
+
+cudaError_t long_carry(const float2* old_hist, const void* block, long long pitch, float2* new_hist, int rows, int H, long long n,
+                       int s16, cudaStream_t stream) {
+    const long long work = (long long)rows * H;
+    const unsigned grid = (unsigned)((work + 255) / 256);
+    if (s16)
+        long_carry_kernel<short2><<<grid, 256, 0, stream>>>(old_hist, static_cast<const short2*>(block), pitch, new_hist, rows, H, n);
+    else
+        long_carry_kernel<float2><<<grid, 256, 0, stream>>>(old_hist, static_cast<const float2*>(block), pitch, new_hist, rows, H, n);
+    return cudaGetLastError();
+}
+
+}  // namespace nvx

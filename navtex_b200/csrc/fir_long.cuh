@@ -1,0 +1,58 @@
+// fir_long.cuh -- the three decimating FIR stages as separate, register-tiled kernels for tap sets LONGER than the
+// reference's 37 / 47 / 71 (BASELINE.json configs[4]: "long-tap FIR stress, 255+ taps").
+//
+// Same arithmetic definition as the reference stages:
+//   y[k] = sum_{i < T} h[i] x[D (k + 1) - 1 - i]     fir1cpp.C:80-136 (D = 4), fir2cpp.C:131-215 (D = 7, after the
+//                                                     NCO mix of fir2cpp.C:112-128), fir3cpp.C:22-60 (D = 10)
+// but a different machine mapping from the fused cascade: with hundreds of taps the partial sums of the transposed
+// form no longer fit the register file and the work is FP32-bound (~330 flop per input sample at 255 taps, 42 flop/B),
+// so the intermediates may as well round-trip through HBM (+4.6 B per input sample) and every stage becomes a plain
+// polyphase, register-tiled FIR:
+//   * a CTA owns (row, tile of kLongTile consecutive outputs); the inputs that tile needs are staged in shared memory
+//     de-interleaved by decimation phase (x_p[m] = x[D m + p]) so that lanes read consecutive addresses;
+//   * a thread owns R = 8 consecutive outputs; per phase it slides an R-wide register window over x_p and applies the
+//     taps of that phase (warp-uniform constant-bank operands) as packed FFMA2 on (I, Q): R * R FFMA2 per R loads;
+//   * the stage-2 kernel applies the NCO rotation while staging (9-entry table of the reference or the exact per-stream
+//     phase of the general NCO).
+// History between blocks is carried per stage (last H inputs of each row), not recomputed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fir_cascade.cuh"
+
+namespace nvx {
+
+constexpr int kLongR = 8;                       // outputs per thread
+constexpr int kLongThreads = 128;
+constexpr int kLongTile = kLongR * kLongThreads;   // outputs per CTA
+constexpr int kLongMaxTaps = 1024;              // per stage
+
+struct LongStage {
+    int D;            // decimation
+    int T;            // taps
+    int J;            // taps per phase, padded to a multiple of kLongR: D * J >= T
+    int H;            // history samples carried per row: D * J
+};
+
+struct LongArgs {
+    const void* in;           // [rows_in][in_pitch] float2 (or short2 for stage 1 with s16 input), this block
+    const float2* hist;       // [rows_in][H] float2: the H samples that preceded the block (always float2)
+    float2* out;              // [rows_out][out_pitch], written at out_off + k
+    long long n_in;           // input samples per row in this block (multiple of D)
+    long long out_pitch, out_off;
+    int rows_in;              // streams (stage 1, 2) or channels (stage 3)
+    int stage;                // 0, 1, 2
+    int s16;                  // stage 1 only: input block is short2
+    long long k_abs;          // stage 2: absolute index of the block's first input sample (63 kHz clock), for the NCO
+    const NcoParam* nco;      // stage 2: per-stream general NCO or null (reference table)
+};
+
+LongStage long_stage(int D, int T);
+cudaError_t long_upload_taps(const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, cudaStream_t stream);
+cudaError_t long_launch(const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream);
+// new_hist = last H samples of (old_hist ++ block[.][0..n)) per row; block rows are `pitch` samples apart, short2 if s16
+cudaError_t long_carry(const float2* old_hist, const void* block, long long pitch, float2* new_hist, int rows, int H, long long n,
+                       int s16, cudaStream_t stream);
+
+}  // namespace nvx

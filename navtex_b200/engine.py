@@ -26,6 +26,7 @@ class Config(C.Structure):
         ("h1", C.POINTER(C.c_double)), ("h2", C.POINTER(C.c_double)), ("h3", C.POINTER(C.c_double)),
         ("keep_bits", C.c_int), ("first_stream_id", C.c_int),
         ("nco_hz", C.POINTER(C.c_double)), ("stream_freq_tag", C.POINTER(C.c_int)),
+        ("n1", C.c_int), ("n2", C.c_int), ("n3", C.c_int),
     ]
 
 
@@ -120,8 +121,9 @@ class Engine:
         self._taps = None
         if taps is not None:
             self._taps = [np.ascontiguousarray(t, dtype=np.float64) for t in taps]
-            assert [len(t) for t in self._taps] == [37, 47, 71]
             cfg.h1, cfg.h2, cfg.h3 = (t.ctypes.data_as(C.POINTER(C.c_double)) for t in self._taps)
+            if [len(t) for t in self._taps] != [37, 47, 71]:       # other lengths: the long-tap path
+                cfg.n1, cfg.n2, cfg.n3 = (len(t) for t in self._taps)
         if nco_hz is not None:           # [S, 2] per-stream channel offsets in Hz
             self._nco = np.ascontiguousarray(nco_hz, dtype=np.float64).reshape(n_streams, 2)
             cfg.nco_hz = self._nco.ctypes.data_as(C.POINTER(C.c_double))

@@ -1,0 +1,100 @@
+"""BASELINE.json configs[4] on the GPU: long-tap FIR stress (255-tap Kaiser designs for all three stages, steeper
+than fir1cpp.C:8 / fir2cpp.C:22 / fir3cpp.h:16) through the long-tap path (one register-tiled kernel per stage).
+
+The unmodified reference cannot run other tap sets, so parity is against the C restatement of the three stages
+(oracle/navtex_oracle.c, h1/h2/h3 parameters), which is pinned to the compiled reference at the default taps."""
+import numpy as np
+import pytest
+from scipy import signal
+
+import oracle_lib as ol
+from navtex_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+
+
+def designs(n1=255, n2=255, n3=255):
+    h1 = signal.firwin(n1, 20000, window=("kaiser", 8.0), fs=252000)
+    h2 = signal.firwin(n2, 2000, window=("kaiser", 8.0), fs=63000)
+    h3 = signal.firwin(n3, 250, window=("kaiser", 7.0), fs=9000)
+    return h1, h2, h3
+
+
+def _capture(text, offset, seconds, snr, seed):
+    em = synth.Emission(text, offset, start_s=0.3, n_phasing=18, n_tail=5)
+    return synth.quantise_s16(synth.fsk_iq([em], seconds, snr_db=snr, seed=seed))
+
+
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (101, 383, 129), (37, 47, 500)])
+def test_long_taps_against_restated_oracle(lengths):
+    taps = designs(*lengths)
+    seconds = 11.0
+    n = int(seconds * 252000)
+    rng = np.random.default_rng(21)
+    iqs, want = [], []
+    for s in range(3):
+        text, bbbb = synth.random_message(rng, n_lines=1, words_per_line=3)
+        occ = s % 2
+        iqs.append(_capture(text, 14000.0 if occ == 0 else -14000.0, seconds, snr=-6.0, seed=400 + s))
+        want.append((518 if occ == 0 else 490, bbbb, text))
+    x = np.stack([iq.reshape(-1, 2) for iq in iqs])                 # int16: the long path converts while staging
+    eng = engine.Engine(3, n, keep_bits=True, taps=taps)
+    eng.push_host(np.ascontiguousarray(x))
+    msgs = eng.poll_messages()
+    y3 = eng.read_y3()
+    for s in range(3):
+        o = ol.run_oracle(iqs[s], h1=taps[0], h2=taps[1], h3=taps[2])
+        scale = max(np.abs(o.y3["518"]).max(), np.abs(o.y3["490"]).max())
+        for c, tag in enumerate(ol.CHANNELS):
+            err = np.abs(y3[s, c].astype(np.complex128) - o.y3[tag]).max() / scale
+            assert err <= REL_TOL, (lengths, s, tag, err)
+        occ = s % 2
+        bits, _ = eng.read_bits(s, occ)
+        assert bits == o.bits[ol.CHANNELS[occ]]
+        assert eng.read_events(s, occ) == o.events[ol.CHANNELS[occ]]
+        assert o.messages == [want[s]]
+        assert [m[1:] for m in msgs if m[0] == s] == [want[s]]
+    eng.close()
+
+
+def test_long_taps_blocking_and_format_invariance():
+    """Histories are carried per stage: any blocking, float or int16 input, gives bit-identical 900 Hz samples."""
+    taps = designs(255, 255, 255)
+    n = 252000 * 2
+    rng = np.random.default_rng(23)
+    x = np.rint(rng.normal(0, 3000, size=(2, n, 2))).astype(np.int16)
+    one = engine.Engine(2, n, taps=taps)
+    one.push_host(x.astype(np.float32))
+    ref = one.read_y3()
+    one.close()
+    for blk in (280, 280 * 333, 2520 * 40):
+        m = n if blk > 280 else 280 * 300
+        eng = engine.Engine(2, blk, taps=taps)
+        ys = []
+        for a in range(0, m, blk):
+            eng.push_host(np.ascontiguousarray(x[:, a:a + blk]))
+            ys.append(eng.read_y3())
+        eng.close()
+        y = np.concatenate(ys, axis=2)
+        assert np.array_equal(y.view(np.uint64), ref[:, :, : y.shape[2]].view(np.uint64)), blk
+
+
+def test_long_taps_with_per_stream_nco():
+    taps = designs(255, 255, 255)
+    seconds = 11.0
+    n = int(seconds * 252000)
+    rng = np.random.default_rng(25)
+    text, bbbb = synth.random_message(rng, n_lines=1, words_per_line=3)
+    iq = _capture(text, 9500.0, seconds, snr=-6.0, seed=500)
+    eng = engine.Engine(1, n, taps=taps, nco_hz=[[9500.0, -4500.5]], stream_freq_tag=[[4209, 4195]])
+    eng.push_host(np.ascontiguousarray(iq.reshape(1, -1, 2)))
+    msgs = eng.poll_messages()
+    y3 = eng.read_y3()
+    o = ol.run_oracle(iq, h1=taps[0], h2=taps[1], h3=taps[2], nco_hz=(9500.0, -4500.5), freq_tag=(4209, 4195))
+    scale = max(np.abs(o.y3["518"]).max(), np.abs(o.y3["490"]).max())
+    for c, tag in enumerate(ol.CHANNELS):
+        assert np.abs(y3[0, c].astype(np.complex128) - o.y3[tag]).max() <= REL_TOL * scale
+    assert [m[1:] for m in msgs] == o.messages == [(4209, bbbb, text)]
+    eng.close()
