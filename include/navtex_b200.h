@@ -128,6 +128,37 @@ void *nvx_engine_stream(nvx_engine *e);
  * channel's event bytes; calls cb once per completed message and returns their number */
 int nvx_host_assemble(const unsigned char *events, size_t n, int stream, int freq, nvx_message_cb cb, void *user);
 
+/* ---- SDRplay-format front end (host): replaces the ring buffer + 50 ms consumer loop of capt_sched.c:105-148, :484-528 --- */
+typedef struct nvx_capture nvx_capture;
+/* one ring of ring_samples int16 I,Q pairs per stream (>= 2 max_block); max_block <= the engine's */
+int nvx_capture_create(nvx_engine *e, int n_streams, long long max_block, long long ring_samples, nvx_capture **out);
+void nvx_capture_destroy(nvx_capture *c);
+/* producer (the radio callback of stream `stream`, capt_sched.c:105: separate xi[] / xq[] arrays); one producer thread per
+ * stream.  NVX_ERR_OVERFLOW = the ring was full, the excess was dropped (and counted) instead of overwriting unread data */
+int nvx_capture_write(nvx_capture *c, int stream, const short *xi, const short *xq, unsigned num_samples);
+/* consumer: push what every stream has in common (multiple of 280, <= max_block) as one int16 block.
+ * Returns samples per stream pushed, 0 if there was less than 280, or a negative nvx_status */
+long long nvx_capture_pump(nvx_capture *c);
+/* or let a poller thread pump every poll_ms (<= 0: 50 ms, capt_sched.c:489); stop() drains what is left */
+int nvx_capture_start(nvx_capture *c, int poll_ms);
+int nvx_capture_stop(nvx_capture *c);
+long long nvx_capture_dropped(nvx_capture *c, int stream);
+
+/* ---- in-memory message store behind add_message (message_store.c:59-97): newest message per (stream, B1B2B3B4) -------- */
+typedef struct nvx_store nvx_store;
+nvx_store *nvx_store_create(void);
+void nvx_store_destroy(nvx_store *s);
+/* 0, or -1 like message_store.c:69-73 when the store is unusable; replaces an older message with the same bbbb */
+int nvx_store_add(nvx_store *s, int stream, const char *bbbb, const char *message, int freq);
+int nvx_store_add_at(nvx_store *s, int stream, const char *bbbb, const char *message, int freq, long long unix_time);
+/* nvx_message_cb-shaped: nvx_engine_set_message_callback(e, nvx_store_sink, store) */
+int nvx_store_sink(void *store, int stream, char *bbbb, char *message, int freq);
+size_t nvx_store_count(nvx_store *s);
+/* row k in insertion order; stamp = UTC "%Y-%m-%d %H:%M" (message_store.c:30); *text valid until the next add/purge */
+int nvx_store_get(nvx_store *s, size_t k, int *stream, int *freq, char bbbb[8], char stamp[20], const char **text);
+int nvx_store_purge(nvx_store *s, long long now_unix, long long max_age_s);   /* reference: 72 h, message_store.c:13 */
+int nvx_store_dump_csv(nvx_store *s, const char *path);
+
 /* ---- synthetic captures on the device (bench / tests): SITOR-B FSK + AWGN, int16-valued float2 - */
 typedef struct {
     const uint8_t *bits;        /* host: concatenated per-stream bit strings (1 = 'Y'), 100 baud */

@@ -9,8 +9,9 @@ for f in fir_cascade fir_long demod engine synth; do
   $NVCC $FLAGS -c $f.cu -o ../build/$f.o 2> ../build/$f.ptxas.log || { cat ../build/$f.ptxas.log; exit 1; }
 done
 $NVCC $FLAGS -c message_assembler.cpp -o ../build/message_assembler.o
+$NVCC $FLAGS -c capture_frontend.cpp -o ../build/capture_frontend.o
 $NVCC -shared -o ../libnavtex_b200.so ../build/fir_cascade.o ../build/fir_long.o ../build/demod.o ../build/engine.o ../build/synth.o \
-      ../build/message_assembler.o -arch=sm_100a -lcudart_static -lpthread -ldl -lrt
+      ../build/message_assembler.o ../build/capture_frontend.o -arch=sm_100a -lcudart_static -lpthread -ldl -lrt
 g++ -O2 -std=c++17 -fPIC -shared -o ../libnavtex_compat.so navtex_compat.cpp -L.. -lnavtex_b200 -Wl,-rpath,'$ORIGIN'
 grep -h "registers\|spill" ../build/*.ptxas.log | sort | uniq -c
 ls -la ../libnavtex_b200.so ../libnavtex_compat.so

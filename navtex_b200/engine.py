@@ -52,6 +52,9 @@ EXPORTS = (
     "nvx_engine_sync", "nvx_engine_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
     "nvx_engine_read_bits", "nvx_engine_read_events", "nvx_engine_enable_timing", "nvx_engine_get_stats",
     "nvx_engine_stream", "nvx_synth_fill_device", "nvx_host_assemble",
+    "nvx_capture_create", "nvx_capture_destroy", "nvx_capture_write", "nvx_capture_pump", "nvx_capture_start", "nvx_capture_stop",
+    "nvx_capture_dropped", "nvx_store_create", "nvx_store_destroy", "nvx_store_add", "nvx_store_add_at", "nvx_store_sink",
+    "nvx_store_count", "nvx_store_get", "nvx_store_purge", "nvx_store_dump_csv",
 )
 
 MESSAGE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int)
@@ -86,6 +89,27 @@ def load_library():
     L.nvx_engine_stream.restype = C.c_void_p
     L.nvx_synth_fill_device.argtypes = [C.c_int, C.POINTER(SynthDesc), C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]
     L.nvx_host_assemble.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, MESSAGE_CB, C.c_void_p]
+    L.nvx_engine_set_message_callback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nvx_capture_create.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p)]
+    L.nvx_capture_destroy.argtypes = [C.c_void_p]
+    L.nvx_capture_destroy.restype = None
+    L.nvx_capture_write.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint]
+    for name in ("nvx_capture_pump", "nvx_capture_dropped"):
+        getattr(L, name).restype = C.c_longlong
+    L.nvx_capture_pump.argtypes = [C.c_void_p]
+    L.nvx_capture_dropped.argtypes = [C.c_void_p, C.c_int]
+    L.nvx_capture_start.argtypes = [C.c_void_p, C.c_int]
+    L.nvx_capture_stop.argtypes = [C.c_void_p]
+    L.nvx_store_create.restype = C.c_void_p
+    L.nvx_store_destroy.argtypes = [C.c_void_p]
+    L.nvx_store_destroy.restype = None
+    L.nvx_store_add.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    L.nvx_store_add_at.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_longlong]
+    L.nvx_store_count.argtypes = [C.c_void_p]
+    L.nvx_store_count.restype = C.c_size_t
+    L.nvx_store_get.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p)]
+    L.nvx_store_purge.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong]
+    L.nvx_store_dump_csv.argtypes = [C.c_void_p, C.c_char_p]
     _lib = L
     return L
 
@@ -211,6 +235,83 @@ class Engine:
     @property
     def stream(self) -> int:
         return self.L.nvx_engine_stream(self._h) or 0
+
+
+class Store:
+    """In-memory message store behind add_message (message_store.c:59-97): newest message per (stream, bbbb)."""
+
+    def __init__(self):
+        self.L = load_library()
+        self._h = C.c_void_p(self.L.nvx_store_create())
+
+    def close(self):
+        if self._h and self._h.value:
+            self.L.nvx_store_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def add(self, stream, bbbb, text, freq, when=None):
+        if when is None:
+            return self.L.nvx_store_add(self._h, stream, bbbb.encode("latin-1"), text.encode("latin-1"), freq)
+        return self.L.nvx_store_add_at(self._h, stream, bbbb.encode("latin-1"), text.encode("latin-1"), freq, int(when))
+
+    def attach(self, eng: "Engine"):
+        """Route the engine's messages into this store (nvx_store_sink as the add_message-shaped callback)."""
+        fn = C.cast(self.L.nvx_store_sink, C.c_void_p)
+        _check(self.L.nvx_engine_set_message_callback(eng._h, fn, self._h))
+
+    def rows(self):
+        out = []
+        for k in range(self.L.nvx_store_count(self._h)):
+            stream, freq = C.c_int(), C.c_int()
+            bbbb, stamp = C.create_string_buffer(8), C.create_string_buffer(20)
+            text = C.c_char_p()
+            _check(self.L.nvx_store_get(self._h, k, C.byref(stream), C.byref(freq), bbbb, stamp, C.byref(text)))
+            out.append((stream.value, freq.value, bbbb.value.decode("latin-1"), stamp.value.decode(), text.value.decode("latin-1")))
+        return out
+
+    def purge(self, now, max_age_s=72 * 3600):
+        return self.L.nvx_store_purge(self._h, int(now), int(max_age_s))
+
+    def dump_csv(self, path):
+        _check(self.L.nvx_store_dump_csv(self._h, path.encode()))
+
+
+class Capture:
+    """SDRplay-format front end: per-stream int16 rings fed by radio callbacks, pumped into the engine in blocks."""
+
+    def __init__(self, eng: "Engine", max_block: int, ring_samples: int):
+        self.L, self.eng = eng.L, eng
+        self._h = C.c_void_p()
+        _check(self.L.nvx_capture_create(eng._h, eng.S, max_block, ring_samples, C.byref(self._h)))
+
+    def write(self, stream: int, xi: np.ndarray, xq: np.ndarray) -> int:
+        xi = np.ascontiguousarray(xi, dtype=np.int16)
+        xq = np.ascontiguousarray(xq, dtype=np.int16)
+        return self.L.nvx_capture_write(self._h, stream, xi.ctypes.data_as(C.c_void_p), xq.ctypes.data_as(C.c_void_p), len(xi))
+
+    def pump(self) -> int:
+        n = self.L.nvx_capture_pump(self._h)
+        if n < 0:
+            _check(int(n))
+        return int(n)
+
+    def start(self, poll_ms: int = 50):
+        _check(self.L.nvx_capture_start(self._h, poll_ms))
+
+    def stop(self):
+        _check(self.L.nvx_capture_stop(self._h), allow_overflow=True)
+
+    def dropped(self, stream: int) -> int:
+        return int(self.L.nvx_capture_dropped(self._h, stream))
+
+    def close(self):
+        if self._h and self._h.value:
+            self.L.nvx_capture_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 def synth_fill_device(device: int, d_ptr: int, n_streams: int, t0: int, n: int, bits_per_stream, offset_hz, start_s,

@@ -65,3 +65,23 @@ def test_host_assembler_quirks():
     # abort stores the partial message, and nothing when none is in progress
     assert engine.host_assemble(b"ZCZC GH78\nPART\x18") == [(0, 518, "GH78", "ZCZC GH78\n")]
     assert engine.host_assemble(b"NOISE\x18NNNN\n") == []
+
+
+def test_message_store_replaces_by_bbbb_and_purges(tmp_path):
+    """message_store.c:59-97 semantics: add = delete-by-bbbb + insert with a UTC minute stamp; purge by age."""
+    st = engine.Store()
+    t0 = 1_700_000_000
+    assert st.add(0, "PA12", "ZCZC PA12\nOLD\nNNNN\n", 518, when=t0) == 0
+    assert st.add(0, "QB07", "ZCZC QB07\nICE\nNNNN\n", 490, when=t0 + 60) == 0
+    assert st.add(0, "PA12", "ZCZC PA12\nNEW \"quoted\"\nNNNN\n", 518, when=t0 + 120) == 0      # replaces the first
+    assert st.add(1, "PA12", "ZCZC PA12\nOTHER RADIO\nNNNN\n", 518, when=t0 + 180) == 0        # another stream: kept apart
+    rows = st.rows()
+    assert [(r[0], r[2]) for r in rows] == [(0, "QB07"), (0, "PA12"), (1, "PA12")]
+    assert rows[1][4].startswith("ZCZC PA12\nNEW") and rows[1][3] == "2023-11-14 22:15"
+    path = str(tmp_path / "messages.csv")
+    st.dump_csv(path)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "id,stream,freq,bbbb,timestamp,message" and len(lines) == 4
+    assert '""quoted""' in lines[2] and "\\n" in lines[2]
+    assert st.purge(now=t0 + 100 + 72 * 3600) == 1 and len(st.rows()) == 2      # only the t0 + 60 row is older than 72 h
+    st.close()

@@ -203,3 +203,35 @@ def test_compat_shim_one_stream(batch, tmp_path):
     assert L.navtex_compat_flush() == 0
     assert got == oracle[k].messages
     L.navtex_compat_shutdown()
+
+
+def test_capture_front_end_and_message_store(batch):
+    """Radio-callback-shaped input (separate xi / xq arrays, ragged callback sizes, one ring per stream) pumped into
+    the engine in whatever multiples of 280 are available; messages land in the store exactly as the oracle's."""
+    names, x, oracle = batch
+    S, n = x.shape[0], x.shape[1]
+    eng = engine.Engine(S, 70000)
+    store = engine.Store()
+    store.attach(eng)
+    cap = engine.Capture(eng, 70000, 4 * 70000)
+    rng = np.random.default_rng(1)
+    pos = [0] * S
+    while min(pos) < n:
+        for s in range(S):
+            k = min(n - pos[s], int(rng.integers(500, 9000)))
+            if k:
+                assert cap.write(s, x[s, pos[s]:pos[s] + k, 0], x[s, pos[s]:pos[s] + k, 1]) == 0
+                pos[s] += k
+        while cap.pump() > 0:
+            pass
+    eng.sync()
+    assert all(cap.dropped(s) == 0 for s in range(S))
+    got = sorted((r[0], r[1], r[2], r[4]) for r in store.rows())
+    want = sorted((k, f, b, t) for k in range(S) for f, b, t in oracle[k].messages)
+    assert got == want
+    # ring overrun is reported, not silently overwritten
+    big = np.zeros(4 * 70000 + 10, dtype=np.int16)
+    assert cap.write(0, big, big) == -4 and cap.dropped(0) == 10
+    cap.close()
+    store.close()
+    eng.close()
