@@ -476,7 +476,7 @@ def main():
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
-                "kernel": "nvx::fir_cascade_kernel<true>", "kernel_ms": casc_ms,
+                "kernel": "nvx::fir_cascade_kernel<true,false,false>", "kernel_ms": casc_ms,
                 "demod_chain_ms": st2.demod_ms / max(1, st2.cascade_launches),
                 "demod_stage_ms": dict(zip(("angle_corr", "offset_sum", "carry", "symbol_clock", "bit_decide", "fsm"),
                                            (v / max(1, st2.cascade_launches) for v in st2.demod_stage_ms))),

@@ -46,7 +46,13 @@ __global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a
 
     // ---- stage the tile; stage 2 rotates by the channel's NCO on the way in ----
     NcoParam np = {};
-    if (STAGE == 1 && a.nco) np = a.nco[row_in];
+    int k9 = 0, kden = 0;                                     // NCO clock of the tile's first input, reduced once
+    if (STAGE == 1) {
+        if (a.nco) np = a.nco[row_in];
+        long long k = (a.k_abs + g0) % kNcoPeriod, kd = (a.k_abs + g0) % kNcoDen;
+        k9 = (int)(k < 0 ? k + kNcoPeriod : k);
+        kden = (int)(kd < 0 ? kd + kNcoDen : kd);
+    }
     constexpr int kBatch = 8;                                 // loads in flight per thread (the staging is latency-bound)
     for (int base = 0; base < F; base += kLongThreads * kBatch) {
         float2 v[kBatch];
@@ -61,11 +67,9 @@ __global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a
             if (f >= F) break;
             float2 x = v[i];
             if (STAGE == 1) {
-                const long long g = g0 + f;
                 float2 rot;
                 if (a.nco) {
-                    long long k = (a.k_abs + g) % kNcoDen;
-                    if (k < 0) k += kNcoDen;
+                    const long long k = (kden + f) % kNcoDen;
                     const int ph = (int)((k * np.num[ch]) % kNcoDen);
                     float t = (float)ph * (2.0f / kNcoDen);
                     if (t > 1.0f) t -= 2.0f;
@@ -73,9 +77,7 @@ __global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a
                     sincospif(t, &sn, &cs);
                     rot = make_float2(cs, -sn);
                 } else {
-                    long long k = (a.k_abs + g) % kNcoPeriod;
-                    if (k < 0) k += kNcoPeriod;
-                    rot = c_long_nco[k];
+                    rot = c_long_nco[(k9 + f) % kNcoPeriod];
                     if (ch) rot.y = -rot.y;                   // "490": conjugate rotation (fir2cpp.C:121-124)
                 }
                 x = make_float2(fmaf(-x.y, rot.y, x.x * rot.x), fmaf(x.x, rot.y, x.y * rot.x));
