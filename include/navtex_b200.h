@@ -85,9 +85,13 @@ void nvx_engine_destroy(nvx_engine *e);
 /* back to the state right after create (zero FIR history, decoder INIT, phasing search) */
 int nvx_engine_reset(nvx_engine *e);
 
-/* ---- ingest: n samples for every stream.  Host variants copy H2D (pinned or pageable) ----- */
+/* ---- ingest: n samples for every stream.  Host variants copy H2D on a copy stream into one of two staging slots, so
+ * the copy of block k+1 overlaps the kernels of block k.  A pageable buffer may be reused as soon as the call returns;
+ * a pinned (cudaHostAlloc / cudaHostRegister) buffer is read asynchronously and must stay unchanged until
+ * nvx_engine_wait_ingest() or nvx_engine_sync() returns.  One engine takes one sample format between resets. */
 int nvx_engine_push_host_f32(nvx_engine *e, const float *iq, long long n);
 int nvx_engine_push_host_s16(nvx_engine *e, const int16_t *iq, long long n);   /* SDRplay / WAV sample format */
+int nvx_engine_wait_ingest(nvx_engine *e);                                      /* every host buffer pushed so far has been read */
 /* device-resident float2 block [S][n], 16-byte aligned; processed in place, asynchronously on the
  * engine's stream (ordered after everything previously queued on it) */
 int nvx_engine_push_device_f32(nvx_engine *e, const void *d_iq, long long n);
@@ -98,6 +102,8 @@ int nvx_engine_sync(nvx_engine *e);
 /* ---- results -------------------------------------------------------------------------------- */
 /* messages completed since the previous poll (implies sync); pointers valid until the next poll */
 int nvx_engine_poll_messages(nvx_engine *e, const nvx_message **msgs, size_t *count);
+/* same without waiting: whatever the blocks already finished have completed (the pipeline keeps running) */
+int nvx_engine_try_poll_messages(nvx_engine *e, const nvx_message **msgs, size_t *count);
 /* alternatively deliver them through an add_message-shaped callback during sync/poll */
 int nvx_engine_set_message_callback(nvx_engine *e, nvx_message_cb cb, void *user);
 

@@ -119,8 +119,13 @@ struct nvx_engine {
     uint8_t* d_events[kBuf] = {}; int* d_ev_count[kBuf] = {}; int ev_cap = 0;
     char* d_bits = nullptr; float* d_disc = nullptr; int* d_bit_count = nullptr; int bit_cap = 0;
     uint8_t* h_events[kBuf] = {}; int* h_ev_count[kBuf] = {};
-    float2* stage_f32 = nullptr; size_t stage_f32_samples = 0;
-    short2* stage_s16 = nullptr; size_t stage_s16_samples = 0;
+    // host ingest: two device staging slots filled by a copy stream, so the H2D copy of block k+1 runs beside the
+    // kernels of block k
+    cudaStream_t stream_copy = nullptr;
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_bytes[2] = {0, 0};
+    cudaEvent_t copy_done[2] = {}, stage_free[2] = {};
+    long long host_pushes = 0;
     long long sb_abs = 0;
     int last_P = 0;
     bool custom_taps = false;
@@ -175,7 +180,14 @@ int free_engine(nvx_engine* e) {
     cudaFree(e->db.corr); cudaFree(e->db.clock); cudaFree(e->db.fsm);
     cudaFree(e->db.bitpos); cudaFree(e->db.bitval); cudaFree(e->db.nbits);
     cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
-    cudaFree(e->stage_f32); cudaFree(e->stage_s16); cudaFree(e->d_nco);
+    if (e->stream_copy) cudaStreamSynchronize(e->stream_copy);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(e->stage[k]);
+        if (e->copy_done[k]) cudaEventDestroy(e->copy_done[k]);
+        if (e->stage_free[k]) cudaEventDestroy(e->stage_free[k]);
+    }
+    if (e->stream_copy) cudaStreamDestroy(e->stream_copy);
+    cudaFree(e->d_nco);
     for (int k = 0; k < 3; ++k) { cudaFree(e->lhist[k][0]); cudaFree(e->lhist[k][1]); }
     cudaFree(e->y1buf); cudaFree(e->y2buf);
     for (int k = 0; k < kBuf; ++k) {
@@ -308,6 +320,7 @@ void deliver_callbacks(nvx_engine* e) {
 
 int sync_engine(nvx_engine* e) {
     CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->stream_copy));
     CU_TRY(cudaStreamSynchronize(e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream_demod));
     collect_spans(e);
@@ -455,20 +468,27 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     return 0;
 }
 
-int ensure_stage_f32(nvx_engine* e, size_t samples) {
-    if (e->stage_f32_samples >= samples) return 0;
-    cudaFree(e->stage_f32);
-    e->stage_f32 = nullptr; e->stage_f32_samples = 0;
-    CU_TRY(cudaMalloc(&e->stage_f32, samples * sizeof(float2)));
-    e->stage_f32_samples = samples;
-    return 0;
-}
-int ensure_stage_s16(nvx_engine* e, size_t samples) {
-    if (e->stage_s16_samples >= samples) return 0;
-    cudaFree(e->stage_s16);
-    e->stage_s16 = nullptr; e->stage_s16_samples = 0;
-    CU_TRY(cudaMalloc(&e->stage_s16, samples * sizeof(short2)));
-    e->stage_s16_samples = samples;
+// H2D on the copy stream into staging slot k % 2, then the block's kernels on the main stream
+int push_host(nvx_engine* e, const void* iq, long long n, bool s16) {
+    if (n <= 0 || n % nvx::kSuper != 0 || n > e->cfg.max_block) return fail(NVX_ERR_ARG, "bad block length %lld", n);
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const size_t bytes = (size_t)e->S * (size_t)n * (s16 ? sizeof(short2) : sizeof(float2));
+    const int slot = (int)(e->host_pushes % 2);
+    if (e->stage_bytes[slot] < bytes) {
+        CU_TRY(cudaStreamSynchronize(e->stream_copy));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        cudaFree(e->stage[slot]);
+        e->stage[slot] = nullptr; e->stage_bytes[slot] = 0;
+        CU_TRY(cudaMalloc(&e->stage[slot], bytes));
+        e->stage_bytes[slot] = bytes;
+    }
+    CU_TRY(cudaStreamWaitEvent(e->stream_copy, e->stage_free[slot], 0));     // the block that used this slot two pushes ago
+    CU_TRY(cudaMemcpyAsync(e->stage[slot], iq, bytes, cudaMemcpyHostToDevice, e->stream_copy));
+    CU_TRY(cudaEventRecord(e->copy_done[slot], e->stream_copy));
+    CU_TRY(cudaStreamWaitEvent(e->stream, e->copy_done[slot], 0));
+    if (int rc = process_block(e, e->stage[slot], n, s16)) return rc;
+    CU_TRY(cudaEventRecord(e->stage_free[slot], e->stream));
+    e->host_pushes++;
     return 0;
 }
 
@@ -550,6 +570,11 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         int lo = 0, hi = 0;
         CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CREATE_TRY(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, lo));
+        CREATE_TRY(cudaStreamCreateWithFlags(&e->stream_copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CREATE_TRY(cudaEventCreateWithFlags(&e->copy_done[k], cudaEventDisableTiming));
+            CREATE_TRY(cudaEventCreateWithFlags(&e->stage_free[k], cudaEventDisableTiming));
+        }
         CREATE_TRY(cudaStreamCreateWithPriority(&e->stream_demod, cudaStreamNonBlocking, hi));
         // tuning knob NVX_PIPELINE: "overlap" = feed-forward demod kernels on the demod stream too (beside the next
         // cascade), "serial" = the next cascade waits for the whole demod; default = see process_block
@@ -645,22 +670,19 @@ int nvx_engine_push_device_s16(nvx_engine* e, const void* d_iq, long long n) {
 
 int nvx_engine_push_host_f32(nvx_engine* e, const float* iq, long long n) {
     if (!e || !iq) return fail(NVX_ERR_ARG, "null argument");
-    if (n <= 0 || n % nvx::kSuper != 0 || n > e->cfg.max_block) return fail(NVX_ERR_ARG, "bad block length %lld", n);
-    CU_TRY(cudaSetDevice(e->cfg.device));
-    const size_t total = (size_t)e->S * (size_t)n;
-    if (int rc = ensure_stage_f32(e, total)) return rc;
-    CU_TRY(cudaMemcpyAsync(e->stage_f32, iq, total * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
-    return process_block(e, e->stage_f32, n, false);
+    return push_host(e, iq, n, false);
 }
 
 int nvx_engine_push_host_s16(nvx_engine* e, const int16_t* iq, long long n) {
     if (!e || !iq) return fail(NVX_ERR_ARG, "null argument");
-    if (n <= 0 || n % nvx::kSuper != 0 || n > e->cfg.max_block) return fail(NVX_ERR_ARG, "bad block length %lld", n);
+    return push_host(e, iq, n, true);
+}
+
+int nvx_engine_wait_ingest(nvx_engine* e) {
+    if (!e) return fail(NVX_ERR_ARG, "null engine");
     CU_TRY(cudaSetDevice(e->cfg.device));
-    const size_t total = (size_t)e->S * (size_t)n;
-    if (int rc = ensure_stage_s16(e, total)) return rc;
-    CU_TRY(cudaMemcpyAsync(e->stage_s16, iq, total * sizeof(short2), cudaMemcpyHostToDevice, e->stream));
-    return process_block(e, e->stage_s16, n, true);
+    CU_TRY(cudaStreamSynchronize(e->stream_copy));
+    return 0;
 }
 
 int nvx_engine_sync(nvx_engine* e) {
@@ -688,6 +710,27 @@ int nvx_engine_poll_messages(nvx_engine* e, const nvx_message** msgs, size_t* co
     *msgs = e->view.data();
     *count = e->view.size();
     return rc;
+}
+
+int nvx_engine_try_poll_messages(nvx_engine* e, const nvx_message** msgs, size_t* count) {
+    if (!e || !msgs || !count) return fail(NVX_ERR_ARG, "null argument");
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->handed.swap(e->ready);
+        e->ready.clear();
+    }
+    e->view.clear();
+    for (const auto& m : e->handed) {
+        nvx_message v;
+        v.stream = m.stream; v.freq = m.freq;
+        memset(v.bbbb, 0, sizeof v.bbbb);
+        strncpy(v.bbbb, m.bbbb.c_str(), sizeof v.bbbb - 1);
+        v.text = m.text.c_str(); v.text_len = m.text.size();
+        e->view.push_back(v);
+    }
+    *msgs = e->view.data();
+    *count = e->view.size();
+    return 0;
 }
 
 int nvx_engine_set_message_callback(nvx_engine* e, nvx_message_cb cb, void* user) {

@@ -49,7 +49,7 @@ class SynthDesc(C.Structure):
 EXPORTS = (
     "nvx_default_config", "nvx_last_error", "nvx_engine_create", "nvx_engine_destroy", "nvx_engine_reset",
     "nvx_engine_push_host_f32", "nvx_engine_push_host_s16", "nvx_engine_push_device_f32", "nvx_engine_push_device_s16",
-    "nvx_engine_sync", "nvx_engine_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
+    "nvx_engine_sync", "nvx_engine_wait_ingest", "nvx_engine_poll_messages", "nvx_engine_try_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
     "nvx_engine_read_bits", "nvx_engine_read_events", "nvx_engine_enable_timing", "nvx_engine_get_stats",
     "nvx_engine_stream", "nvx_synth_fill_device", "nvx_host_assemble",
     "nvx_capture_create", "nvx_capture_destroy", "nvx_capture_write", "nvx_capture_pump", "nvx_capture_start", "nvx_capture_stop",
@@ -80,6 +80,8 @@ def load_library():
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
     L.nvx_engine_sync.argtypes = [C.c_void_p]
     L.nvx_engine_poll_messages.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Message)), C.POINTER(C.c_size_t)]
+    L.nvx_engine_try_poll_messages.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Message)), C.POINTER(C.c_size_t)]
+    L.nvx_engine_wait_ingest.argtypes = [C.c_void_p]
     L.nvx_engine_read_y3.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.nvx_engine_read_bits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.nvx_engine_read_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -191,10 +193,15 @@ class Engine:
     def sync(self):
         _check(self.L.nvx_engine_sync(self._h), allow_overflow=True)
 
-    def poll_messages(self):
+    def wait_ingest(self):
+        _check(self.L.nvx_engine_wait_ingest(self._h))
+
+    def poll_messages(self, wait: bool = True):
+        """Messages completed since the previous poll; wait=False does not sync (pipeline keeps running)."""
         msgs = C.POINTER(Message)()
         cnt = C.c_size_t()
-        _check(self.L.nvx_engine_poll_messages(self._h, C.byref(msgs), C.byref(cnt)), allow_overflow=True)
+        fn = self.L.nvx_engine_poll_messages if wait else self.L.nvx_engine_try_poll_messages
+        _check(fn(self._h, C.byref(msgs), C.byref(cnt)), allow_overflow=True)
         return [(msgs[k].stream, msgs[k].freq, msgs[k].bbbb.decode("latin-1"), C.string_at(msgs[k].text, msgs[k].text_len).decode("latin-1"))
                 for k in range(cnt.value)]
 
