@@ -510,6 +510,10 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     if (!cfg || !out) return fail(NVX_ERR_ARG, "null argument");
     if (cfg->n_streams <= 0 || cfg->max_block <= 0 || cfg->max_block % nvx::kSuper != 0)
         return fail(NVX_ERR_ARG, "n_streams must be > 0 and max_block a positive multiple of %d", nvx::kSuper);
+    if (cfg->n_streams > 32767)       // channel rows index the y dimension of the demod grids (65535 max)
+        return fail(NVX_ERR_ARG, "n_streams %d exceeds 32767 per engine: shard the streams over more engines", cfg->n_streams);
+    if (cfg->max_block / nvx::kSuper > (1 << 24))
+        return fail(NVX_ERR_ARG, "max_block %lld is too long (at most %d samples per push)", cfg->max_block, nvx::kSuper << 24);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
         return fail(NVX_ERR_CUDA, "no usable CUDA device %d (%d visible): this library has no CPU path", cfg->device, ndev);

@@ -1,0 +1,114 @@
+"""GPU edge cases of the hot path against the CPU oracle: the config-1 WAV, digital silence, full-scale input, one very
+long single-stream block (maximum time segmentation), reset, sample-format mixing, argument errors."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as ol
+from navtex_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_TOL = 1e-5
+
+
+def _check_all(eng, k, o, exact_channels=("518", "490")):
+    y3 = eng.read_y3()
+    scale = max(np.abs(o.y3["518"]).max(), np.abs(o.y3["490"]).max(), 1e-30)
+    for c, tag in enumerate(ol.CHANNELS):
+        assert np.abs(y3[k, c].astype(np.complex128) - o.y3[tag]).max() <= REL_TOL * scale, tag
+        if tag in exact_channels:
+            bits, _ = eng.read_bits(k, c)
+            assert bits == o.bits[tag], tag
+            assert eng.read_events(k, c) == o.events[tag], tag
+
+
+def test_config1_wav_file(tmp_path):
+    """BASELINE.json configs[0]: the single 518 kHz WAV (stereo s16, 252 kHz: the format wav.c / PrepWav writes,
+    capt_sched.c:87-96) -> frames -> engine, against the golden add_message calls of the unmodified reference."""
+    iq = cases.build("clean518")
+    path = str(tmp_path / "navtex518.wav")
+    synth.write_wav(path, iq)
+    frames = synth.read_wav(path)                      # interleaved I,Q shorts, as wav_read hands them over
+    n = frames.size // 2 // 280 * 280
+    eng = engine.Engine(1, n, keep_bits=True)
+    eng.push_host(np.ascontiguousarray(frames[: 2 * n].reshape(1, n, 2)))
+    msgs = eng.poll_messages()
+    g = np.load(os.path.join(GOLDEN, "clean518.npz"))
+    gold = [(0, int(f), str(b), str(t)) for f, b, t in zip(g["msg_freq"], g["msg_bbbb"], g["msg_text"])]
+    assert msgs == gold and len(gold) == 1
+    _check_all(eng, 0, ol.run_oracle(frames[: 2 * n]), exact_channels=("518",))
+    eng.close()
+
+
+def test_digital_silence_and_full_scale():
+    """All-zero input: every per-offset sum ties at 0 and the first maximum must win exactly as in the reference
+    (free-running symbol clock, bits from the 'B' > 'Y' tie rule).  Full-scale square wave: no overflow, same bar."""
+    n = 280 * 9 * 400
+    zeros = np.zeros((n, 2), dtype=np.int16)
+    t = np.arange(n)
+    square = np.stack([np.where((t // 9) % 2 == 0, 32767, -32768), np.where((t // 7) % 2 == 0, -32768, 32767)], axis=1).astype(np.int16)
+    x = np.stack([zeros, square])
+    eng = engine.Engine(2, n, keep_bits=True)
+    eng.push_host(np.ascontiguousarray(x))
+    assert eng.poll_messages() == []
+    o0 = ol.run_oracle(zeros.reshape(-1))
+    _check_all(eng, 0, o0)
+    assert len(o0.bits["518"]) > 300 and set(o0.bits["518"]) == {ord("Y")}          # ties decide 'Y' (decoder.C:125)
+    o1 = ol.run_oracle(square.reshape(-1))
+    y3 = eng.read_y3()
+    scale = max(np.abs(o1.y3["518"]).max(), np.abs(o1.y3["490"]).max())
+    for c, tag in enumerate(ol.CHANNELS):
+        assert np.abs(y3[1, c].astype(np.complex128) - o1.y3[tag]).max() <= REL_TOL * scale
+    eng.close()
+
+
+def test_one_stream_one_minute_single_block():
+    """A single stream pushed as one 60 s block: the time axis is cut into the maximum number of segments (one group
+    of 32 lanes, 31 of them TMA zero fill) and must still equal the oracle's sequential pass."""
+    rng = np.random.default_rng(41)
+    text, bbbb = synth.random_message(rng, n_lines=3, words_per_line=5)
+    em = synth.Emission(text, 14000.0, start_s=2.0, n_phasing=40, n_tail=6)
+    iq = synth.quantise_s16(synth.fsk_iq([em], 60.0, snr_db=-12.0, seed=42))
+    n = iq.size // 2
+    eng = engine.Engine(1, n, keep_bits=True)
+    eng.push_host(np.ascontiguousarray(iq.reshape(1, n, 2)))
+    msgs = eng.poll_messages()
+    o = ol.run_oracle(iq)
+    assert [m[1:] for m in msgs] == o.messages == [(518, bbbb, text)]
+    _check_all(eng, 0, o, exact_channels=("518",))
+    eng.close()
+
+
+def test_reset_reproduces_and_formats_do_not_mix():
+    iq = cases.build("noisy490")
+    n = iq.size // 2 // 280 * 280
+    x = np.ascontiguousarray(iq[: 2 * n].reshape(1, n, 2))
+    eng = engine.Engine(1, n)
+    eng.push_host(x)
+    first, y_first = eng.poll_messages(), eng.read_y3().copy()
+    with pytest.raises(engine.NvxError, match="format"):
+        eng.push_host(x.astype(np.float32))              # int16 then float without a reset
+    eng.reset()
+    eng.push_host(x.astype(np.float32))                  # after a reset either format is fine
+    assert eng.poll_messages() == first and len(first) == 1
+    assert np.array_equal(eng.read_y3().view(np.uint64), y_first.view(np.uint64))
+    eng.close()
+
+
+def test_argument_errors():
+    eng = engine.Engine(2, 2800)
+    with pytest.raises(engine.NvxError):
+        eng.push_host(np.zeros((2, 281, 2), dtype=np.float32))       # not a multiple of 280
+    with pytest.raises(engine.NvxError):
+        eng.push_host(np.zeros((2, 5600, 2), dtype=np.float32))      # longer than max_block
+    eng.close()
+    with pytest.raises(engine.NvxError):
+        engine.Engine(0, 2800)
+    with pytest.raises(engine.NvxError):
+        engine.Engine(40000, 2800)                                   # more than one engine's worth of streams
+    with pytest.raises(engine.NvxError):
+        engine.Engine(1, 2800, taps=(np.ones(2000), np.ones(47), np.ones(71)))
