@@ -642,10 +642,8 @@ cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_s
         const long long need = (work_items + per_cta - 1) / per_cta;
         return (unsigned)(need < ff_max ? (need > 0 ? need : 1) : ff_max);
     };
-    static int skip = -1;                 // NVX_DEBUG_SKIP (timing experiments only; results are then garbage): 1 = angle, 2 = sums
-    if (skip < 0) skip = getenv("NVX_DEBUG_SKIP") ? atoi(getenv("NVX_DEBUG_SKIP")) : 0;
     mark(0, s_ff);
-    if (!(skip & 1)) angle_corr_kernel<<<ff_grid((long long)((a.n_new + kTile - 1) / kTile) * a.channels, kFfTeams), kFfThreads, kFfSmem, s_ff>>>(a);
+    angle_corr_kernel<<<ff_grid((long long)((a.n_new + kTile - 1) / kTile) * a.channels, kFfTeams), kFfThreads, kFfSmem, s_ff>>>(a);
     mark(1, s_ff);
     {   // ring revolutions with an evaluation sample in [-8, n_new): samples 16 + 567 K .. 582 + 567 K
         const long long lo = a.seen - 8 - (kCorrLen + 15), hi = a.seen + a.n_new - 17;
@@ -653,7 +651,7 @@ cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_s
         if (hi >= 0 && (int)(hi / kCorrLen) >= k_lo) {
             const int n_rev = (int)(hi / kCorrLen) - k_lo + 1;
             const long long passes = (long long)((n_rev + kSlotRev - 1) / kSlotRev) * a.channels;
-            if (!(skip & 2)) offset_sum_kernel<<<ff_grid(passes, kSlots), kSumThreads, kSumSmem, s_ff>>>(a, k_lo, n_rev);
+            offset_sum_kernel<<<ff_grid(passes, kSlots), kSumThreads, kSumSmem, s_ff>>>(a, k_lo, n_rev);
         }
     }
     mark(2, s_ff);

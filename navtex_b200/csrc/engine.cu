@@ -657,7 +657,8 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         int ff_sms = sms >= 64 ? 16 : (sms >= 16 ? sms / 8 : 1);
         if (const char* env = getenv("NVX_FF_SMS")) ff_sms = atoi(env) > 0 ? atoi(env) : ff_sms;     // tuning knob
         e->ff_ctas = e->ff_on_main ? sms : ff_sms;
-        const int reserve = seq_sms + (e->ff_on_main ? 0 : ff_sms);
+        int reserve = seq_sms + (e->ff_on_main ? 0 : ff_sms);
+        if (const char* env = getenv("NVX_RESERVE_SMS")) reserve = atoi(env);                       // tuning knob
         for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, reserve, f != 0);
     }
     e->assembler.resize(e->channels);
