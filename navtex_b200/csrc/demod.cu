@@ -160,73 +160,32 @@ __device__ __forceinline__ double angle_of(float2 cur, float2 prev) {
     return atan2(im, re);
 }
 
-// ---- feed-forward kernels: persistent, one CTA per SM ---------------------------------------------------------------
-// The feed-forward kernels run beside the NEXT block's cascade kernel.  A cascade CTA has one warp per SM sub-partition
-// and no latency slack, so it must not share an SM with them; and it needs no more than ~128 SMs to saturate HBM.  So
-// they are shaped as a handful of persistent 1024-thread CTAs with a shared-memory footprint (kFfSmem) that admits
-// neither a second CTA of their kind nor a cascade / sequential-kernel CTA on the same SM, and loop over their work:
-// demod_launch decides how many SMs they get (n_ff).
-constexpr int kFfThreads = 1024;
-constexpr int kFfSmem = 120 * 1024;
-constexpr int kFfTeams = kFfThreads / kThreads;            // 128-thread teams
-
-__device__ __forceinline__ void team_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// |mask correlation| for samples [tile0, tile0 + kTile) of one channel per team iteration; every thread owns three
-// samples (strided by kThreads): independent atan2 chains
-__global__ void __launch_bounds__(kFfThreads, 1) angle_corr_kernel(const DemodArgs a) {
-    extern __shared__ __align__(16) uint8_t s_ff[];
-    const int team = threadIdx.x / kThreads, t = threadIdx.x % kThreads;
-    double* s_ang = reinterpret_cast<double*>(s_ff) + team * (kTile + 8);
-    const int tiles_per_ch = (a.n_new + kTile - 1) / kTile;
-    const long long n_tiles = (long long)tiles_per_ch * a.channels;
-    // the 900 Hz samples of the NEXT tile are fetched while this one is being computed (the kernel runs beside the
-    // cascade, whose HBM traffic makes every miss expensive): cur[u] / prv[u] = y[m], y[m - 1] of sample u, h0 / h1 = halo
-    float2 cur[kPer], prv[kPer], h0 = {}, h1 = {};
-    auto fetch = [&](long long tile, float2 (&c)[kPer], float2 (&p)[kPer], float2& g0, float2& g1) {
-        if (tile >= n_tiles) return;
-        const int ch = (int)(tile / tiles_per_ch), tile0 = (int)(tile % tiles_per_ch) * kTile;
-        const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY;     // y[m], m >= -kHistY
+// grid (tiles, channels), block kThreads: |mask correlation| for samples [tile0, tile0 + kTile); every thread owns three
+// samples (strided by kThreads) so that one resident warp per SM sub-partition still has independent work in flight
+__global__ void __launch_bounds__(kThreads) angle_corr_kernel(const DemodArgs a) {
+    __shared__ double s_ang[kTile + 8];
+    const int ch = blockIdx.y, tile0 = blockIdx.x * kTile, t = threadIdx.x;
+    const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY;     // y[m], m >= -kHistY
 #pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            const int m = tile0 + t + u * kThreads;
-            if (m < a.n_new) { c[u] = y[m]; p[u] = y[m - 1]; }
-        }
-        if (t < 8) { g0 = y[tile0 - 8 + t]; g1 = y[tile0 - 9 + t]; }
-    };
-    long long tile = (long long)blockIdx.x * kFfTeams + team;
-    fetch(tile, cur, prv, h0, h1);
-    for (; tile < n_tiles; tile += (long long)gridDim.x * kFfTeams) {
-        const int ch = (int)(tile / tiles_per_ch), tile0 = (int)(tile % tiles_per_ch) * kTile;
-        float2 ncur[kPer], nprv[kPer], nh0 = {}, nh1 = {};
-        fetch(tile + (long long)gridDim.x * kFfTeams, ncur, nprv, nh0, nh1);
+    for (int u = 0; u < kPer; ++u) {
+        const int m = tile0 + t + u * kThreads;
+        if (m < a.n_new) s_ang[8 + t + u * kThreads] = angle_of(y[m], y[m - 1]);
+    }
+    if (t < 8) s_ang[t] = angle_of(y[tile0 - 8 + t], y[tile0 - 9 + t]);
+    __syncthreads();
+    double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC;
 #pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            const int m = tile0 + t + u * kThreads;
-            if (m < a.n_new) s_ang[8 + t + u * kThreads] = angle_of(cur[u], prv[u]);
-        }
-        if (t < 8) s_ang[t] = angle_of(h0, h1);
-        team_sync(team + 1, kThreads);
-        double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC;
-#pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            const int i = t + u * kThreads, m = tile0 + i;
-            if (m >= a.n_new) break;
-            // mask {0,1,1,1,0,-1,-1,-1,0} over angles n-8 .. n, oldest first (decoder.C:161-170); s_ang[8 + i - k] = angle[m - k]
-            double c = s_ang[i + 1];
-            c = __dadd_rn(c, s_ang[i + 2]);
-            c = __dadd_rn(c, s_ang[i + 3]);
-            c = __dsub_rn(c, s_ang[i + 5]);
-            c = __dsub_rn(c, s_ang[i + 6]);
-            c = __dsub_rn(c, s_ang[i + 7]);
-            corr[m] = fabs(c);
-        }
-        team_sync(team + 1, kThreads);                       // s_ang is rewritten by the next tile
-#pragma unroll
-        for (int u = 0; u < kPer; ++u) { cur[u] = ncur[u]; prv[u] = nprv[u]; }
-        h0 = nh0; h1 = nh1;
+    for (int u = 0; u < kPer; ++u) {
+        const int i = t + u * kThreads, m = tile0 + i;
+        if (m >= a.n_new) break;
+        // mask {0,1,1,1,0,-1,-1,-1,0} over angles n-8 .. n, oldest first (decoder.C:161-170); s_ang[8 + i - k] = angle[m - k]
+        double c = s_ang[i + 1];
+        c = __dadd_rn(c, s_ang[i + 2]);
+        c = __dadd_rn(c, s_ang[i + 3]);
+        c = __dsub_rn(c, s_ang[i + 5]);
+        c = __dsub_rn(c, s_ang[i + 6]);
+        c = __dsub_rn(c, s_ang[i + 7]);
+        corr[m] = fabs(c);
     }
 }
 
@@ -270,127 +229,93 @@ __device__ __forceinline__ bool window_is_y(const float2* __restrict__ y, float*
 // exactly the nine classes j = 0..8 at the same (K, r): nine neighbouring lanes.  They exchange through a per-warp
 // shared-memory patch; lanes 0..20 then each resolve one (revolution, r) arg max (first maximum wins, j ascending,
 // seed -1.0 as decoder.C:207-215) and store the pick of that evaluation sample.
-// Warp = 3 revolutions x 9 classes (27 lanes); (channel, revolution) pairs are flattened over the warps of the
-// persistent CTAs.
-// Memory behaviour: a slot (3 warps = 9 revolutions x 9 classes) copies the ten ring revolutions its 81 threads need
-// -- one contiguous run of 5670 doubles of the channel's correlation row -- into shared memory with 8-byte cp.async
-// (coalesced, asynchronous, no register staging), so every value is read from global memory exactly once; four slots per
-// CTA are at different phases of copy / compute.
+// Warp = 3 revolutions x 9 classes (27 lanes); (channel, revolution) pairs are flattened over warps.
+constexpr int kSumWarps = 4;
 constexpr int kGroup = 7;                                  // r values in flight per thread
-constexpr int kSlotRev = 9;                                // revolutions per slot pass
-constexpr int kSlotWarps = kSlotRev * kSpb / 27;           // 3
-constexpr int kSlots = 4;
-constexpr int kSumThreads = kSlots * kSlotWarps * 32;      // 384
-constexpr int kTileLen = (kSlotRev + 1) * kCorrLen;        // 5670 doubles
-constexpr int kSumSmem = kSlots * kTileLen * 8 + kSlots * kSlotWarps * 3 * kGroup * kSpb * 8;
-
-__global__ void __launch_bounds__(kSumThreads, 1) offset_sum_kernel(const DemodArgs a, int k_lo, int n_rev) {
-    extern __shared__ __align__(16) uint8_t s_ff[];
+__global__ void __launch_bounds__(kSumWarps * 32) offset_sum_kernel(const DemodArgs a, int k_lo, int n_rev) {
+    __shared__ double s_os[kSumWarps][3][kGroup][kSpb];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = warp / kSlotWarps, wslot = warp - slot * kSlotWarps, tslot = wslot * 32 + lane;
-    double* tile = reinterpret_cast<double*>(s_ff) + slot * kTileLen;
-    double (*s_os)[kGroup][kSpb] =
-        reinterpret_cast<double (*)[kGroup][kSpb]>(s_ff + kSlots * kTileLen * 8) + (size_t)warp * 3;       // [3] per warp
     const int kk = lane / kSpb, j = lane - kk * kSpb;       // lanes 27..31: kk == 3, idle
-    const int kk2 = lane / kGroup, u2 = lane - kk2 * kGroup; // the lane that resolves arg maxima: (revolution, r offset)
-    const int passes_per_ch = (n_rev + kSlotRev - 1) / kSlotRev;
-    const long long n_pass = (long long)passes_per_ch * a.channels;
-    for (long long pass = (long long)blockIdx.x * kSlots + slot; pass < n_pass; pass += (long long)gridDim.x * kSlots) {
-        const int ch = (int)(pass / passes_per_ch);
-        const int K0 = k_lo + (int)(pass % passes_per_ch) * kSlotRev;        // first revolution of this pass
-        // tile[i] = corr sample mb + i: from the first class member of revolution K0 - 1 to the last of K0 + 8
-        const int mb = (int)(8 + (long long)kCorrLen * (K0 - 1) - a.seen);
-        const double* row = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC;
-        for (int i = tslot; i < kTileLen; i += kSlotWarps * 32) {
-            const int m = mb + i;
-            if (m >= -kHistC && m < a.n_new + kPadC) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + i);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(row + m) : "memory");
-            } else {
-                tile[i] = 0.0;                                  // outside the row: only feeds evaluations that are discarded
+    const long long unit = ((long long)blockIdx.x * kSumWarps + warp) * 3 + kk;     // (channel, revolution) pair
+    const bool mine = kk < 3 && unit < (long long)a.channels * n_rev;
+    const int ch = mine ? (int)(unit / n_rev) : 0;
+    const int K = k_lo + (mine ? (int)(unit % n_rev) : 0);
+    // block-relative sample of the evaluation r = 0 of this thread; its class members sit 8 samples earlier
+    const int m_first = (int)(16 + (long long)kCorrLen * K + j - a.seen);
+    const double* cur = a.b.corr + (size_t)ch * pitch_c(a.b.p_max) + kHistC + (m_first - 8);
+    const double* prev = cur - kCorrLen;
+    // the lane that resolves arg maxima: (revolution kk2, r offset u2) of this warp
+    const int kk2 = lane / kGroup, u2 = lane - kk2 * kGroup;
+    const long long unit2 = ((long long)blockIdx.x * kSumWarps + warp) * 3 + kk2;
+    const bool judge = kk2 < 3 && unit2 < (long long)a.channels * n_rev;
+    const int ch2 = judge ? (int)(unit2 / n_rev) : 0;
+    const int w_first = (int)(24 + (long long)kCorrLen * (k_lo + (judge ? (int)(unit2 % n_rev) : 0)) - a.seen);
+    uint8_t* picks2 = a.b.picks + (size_t)ch2 * pitch_p(a.b.p_max);     // evaluation samples of a block: e0 + 9 q
+
+    double run = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < kCorrLen / kSpb / kGroup; ++g) {
+        const int r0 = g * kGroup;
+        const int m0 = m_first + kSpb * r0;                 // sample of evaluation r0
+        double acc[kGroup];
+        if (mine && m0 < a.n_new) {
+#pragma unroll
+            for (int u = 0; u < kGroup; ++u) {
+                run = __dadd_rn(run, __ldg(cur + kSpb * (r0 + u)));
+                acc[u] = run;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kGroup; ++u) acc[u] = 0.0;
+        }
+        // only groups with a sample inside [-8, n_new) matter (arg max windows reach 8 samples back)
+        if (mine && m0 < a.n_new && m0 + kSpb * (kGroup - 1) >= -8) {
+            const double* p = prev + kSpb * (r0 + 1);
+            double v[kGroup - 1];
+#pragma unroll
+            for (int t = 0; t < kGroup - 1; ++t) v[t] = __ldg(p + kSpb * t);
+#pragma unroll
+            for (int u = 0; u < kGroup - 1; ++u) {
+#pragma unroll
+                for (int t = u; t < kGroup - 1; ++t) acc[u] = __dadd_rn(acc[u], v[t]);
+            }
+            p += kSpb * (kGroup - 1);
+            const int rest = kCorrLen / kSpb - kGroup - r0;   // 56, 49, ..., 0: prev[r0 + 7 .. 62] go to all seven
+#pragma unroll 1
+            for (int i = 0; i < rest; i += kGroup, p += kSpb * kGroup) {
+                double x[kGroup];
+#pragma unroll
+                for (int t = 0; t < kGroup; ++t) x[t] = __ldg(p + kSpb * t);
+#pragma unroll
+                for (int t = 0; t < kGroup; ++t) {
+#pragma unroll
+                    for (int u = 0; u < kGroup; ++u) acc[u] = __dadd_rn(acc[u], x[t]);
+                }
             }
         }
-        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-        team_sync(slot + 1, kSlotWarps * 32);
-
-        const int unit = wslot * 3 + kk;                        // revolution of this thread inside the pass
-        const bool mine = kk < 3 && K0 + unit < k_lo + n_rev;
-        const int K = K0 + unit;
-        // block-relative sample of the evaluation r = 0 of this thread; its class members sit 8 samples earlier
-        const int m_first = (int)(16 + (long long)kCorrLen * K + j - a.seen);
-        const double* cur = tile + kCorrLen * (unit + 1) + j;   // sample m_first - 8
-        const double* prev = cur - kCorrLen;
-        const int unit2 = wslot * 3 + kk2;
-        const bool judge = kk2 < 3 && K0 + unit2 < k_lo + n_rev;
-        const int w_first = (int)(24 + (long long)kCorrLen * (K0 + unit2) - a.seen);
-        uint8_t* picks = a.b.picks + (size_t)ch * pitch_p(a.b.p_max);     // evaluation samples of a block: e0 + 9 q
-
-        double run = 0.0;
-#pragma unroll 1
-        for (int g = 0; g < kCorrLen / kSpb / kGroup; ++g) {
-            const int r0 = g * kGroup;
-            const int m0 = m_first + kSpb * r0;                 // sample of evaluation r0
-            double acc[kGroup];
-            if (mine && m0 < a.n_new) {
+        if (kk < 3) {
 #pragma unroll
-                for (int u = 0; u < kGroup; ++u) {
-                    run = __dadd_rn(run, cur[kSpb * (r0 + u)]);
-                    acc[u] = run;
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < kGroup; ++u) acc[u] = 0.0;
+            for (int u = 0; u < kGroup; ++u) {
+                const int m = m0 + kSpb * u;
+                const bool ok = mine && m < a.n_new && a.seen + m >= kCorrLen + 7;     // ring full (decoder.C:181)
+                s_os[warp][kk][u][j] = ok ? acc[u] : 0.0;
             }
-            // only groups with a sample inside [-8, n_new) matter (arg max windows reach 8 samples back)
-            if (mine && m0 < a.n_new && m0 + kSpb * (kGroup - 1) >= -8) {
-                const double* p = prev + kSpb * (r0 + 1);
-                double v[kGroup - 1];
-#pragma unroll
-                for (int t = 0; t < kGroup - 1; ++t) v[t] = p[kSpb * t];
-#pragma unroll
-                for (int u = 0; u < kGroup - 1; ++u) {
-#pragma unroll
-                    for (int t = u; t < kGroup - 1; ++t) acc[u] = __dadd_rn(acc[u], v[t]);
-                }
-                p += kSpb * (kGroup - 1);
-                const int rest = kCorrLen / kSpb - kGroup - r0;   // 56, 49, ..., 0: prev[r0 + 7 .. 62] go to all seven
-#pragma unroll 1
-                for (int i = 0; i < rest; i += kGroup, p += kSpb * kGroup) {
-                    double x[kGroup];
-#pragma unroll
-                    for (int t = 0; t < kGroup; ++t) x[t] = p[kSpb * t];
-#pragma unroll
-                    for (int t = 0; t < kGroup; ++t) {
-#pragma unroll
-                        for (int u = 0; u < kGroup; ++u) acc[u] = __dadd_rn(acc[u], x[t]);
-                    }
-                }
-            }
-            if (kk < 3) {
-#pragma unroll
-                for (int u = 0; u < kGroup; ++u) {
-                    const int m = m0 + kSpb * u;
-                    const bool ok = mine && m < a.n_new && a.seen + m >= kCorrLen + 7;     // ring full (decoder.C:181)
-                    s_os[kk][u][j] = ok ? acc[u] : 0.0;
-                }
-            }
-            __syncwarp();
-            if (judge) {
-                const int w = w_first + kSpb * (r0 + u2);
-                if (w >= 0 && w < a.n_new && a.seen + w >= kCorrLen + 15) {
-                    double best = -1.0;
-                    int pick = 0;
-#pragma unroll
-                    for (int i = 0; i < kSpb; ++i) {
-                        const double x = s_os[kk2][u2][i];
-                        if (x > best) { best = x; pick = i; }
-                    }
-                    picks[w / kSpb] = (uint8_t)pick;
-                }
-            }
-            __syncwarp();
         }
-        team_sync(slot + 1, kSlotWarps * 32);                   // the tile is overwritten by the next pass
+        __syncwarp();
+        if (judge) {
+            const int w = w_first + kSpb * (r0 + u2);
+            if (w >= 0 && w < a.n_new && a.seen + w >= kCorrLen + 15) {
+                double best = -1.0;
+                int pick = 0;
+#pragma unroll
+                for (int i = 0; i < kSpb; ++i) {
+                    const double x = s_os[warp][kk2][u2][i];
+                    if (x > best) { best = x; pick = i; }
+                }
+                picks2[w / kSpb] = (uint8_t)pick;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -539,25 +464,19 @@ __global__ void __launch_bounds__(kSeqWarps * 32) fsm_kernel(const DemodArgs a) 
     a.ev_count[ch] = em.n;
 }
 
-// slide every history: the last H entries of [hist | new] become the next block's hist.  One 256-thread team per
-// channel at a time.
-constexpr int kCarryTeam = 256;
-__global__ void __launch_bounds__(kFfThreads, 1) carry_kernel(const DemodArgs a) {
-    extern __shared__ __align__(16) uint8_t s_ff[];
-    const int team = threadIdx.x / kCarryTeam, t = threadIdx.x % kCarryTeam;
-    double* s_c = reinterpret_cast<double*>(s_ff) + team * (kHistC + 2 * kHistY);
-    float2* s_y = reinterpret_cast<float2*>(s_c + kHistC);
-    for (int ch = blockIdx.x * (kFfThreads / kCarryTeam) + team; ch < a.channels; ch += gridDim.x * (kFfThreads / kCarryTeam)) {
-        double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max);
-        const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max);
-        float2* yn = a.y3_next + (size_t)ch * pitch_y(a.b.p_max);
-        for (int k = t; k < kHistC; k += kCarryTeam) s_c[k] = corr[k + a.n_new];
-        if (t < kHistY) s_y[t] = y[t + a.n_new];
-        team_sync(team + 1, kCarryTeam);
-        for (int k = t; k < kHistC; k += kCarryTeam) corr[k] = s_c[k];
-        if (t < kHistY) yn[t] = s_y[t];
-        team_sync(team + 1, kCarryTeam);
-    }
+// slide every history: the last H entries of [hist | new] become the next block's hist.  One CTA per channel.
+__global__ void __launch_bounds__(256) carry_kernel(const DemodArgs a) {
+    __shared__ double s_c[kHistC];
+    __shared__ float2 s_y[kHistY];
+    const int ch = blockIdx.x, t = threadIdx.x;
+    double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max);
+    const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max);
+    float2* yn = a.y3_next + (size_t)ch * pitch_y(a.b.p_max);
+    for (int k = t; k < kHistC; k += blockDim.x) s_c[k] = corr[k + a.n_new];
+    if (t < kHistY) s_y[t] = y[t + a.n_new];
+    __syncthreads();
+    for (int k = t; k < kHistC; k += blockDim.x) corr[k] = s_c[k];
+    if (t < kHistY) yn[t] = s_y[t];
 }
 
 __global__ void init_state_kernel(ClockState* clock, FsmState* fsm, int channels) {
@@ -578,7 +497,7 @@ __global__ void init_state_kernel(ClockState* clock, FsmState* fsm, int channels
 int demod_launches_per_block() { return 6; }
 size_t demod_pick_pitch(int p_max) { return pitch_p(p_max); }
 size_t demod_bit_pitch(int p_max) { return pitch_b(p_max); }
-int demod_seq_sms(int channels) {
+int demod_reserved_sms(int channels) {
     const int ctas = (channels + kSeqWarps * 32 - 1) / (kSeqWarps * 32);
     return ctas < 4 ? ctas : 4;
 }
@@ -628,34 +547,21 @@ cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t s
 cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_seq, cudaEvent_t ff_done, cudaEvent_t* marks) {
     if (a.n_new <= 0 || a.channels <= 0) return cudaSuccess;
     auto mark = [&](int k, cudaStream_t st) { if (marks) cudaEventRecord(marks[k], st); };
-    // feed-forward part: persistent CTAs, one per SM, on a.ff_ctas SMs (see the comment at kFfSmem)
-    static bool ff_attr_done = false;
-    if (!ff_attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(angle_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(offset_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSumSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmem);
-        if (e != cudaSuccess) return e;
-        ff_attr_done = true;
-    }
-    const long long ff_max = a.ff_ctas > 0 ? a.ff_ctas : 1;
-    auto ff_grid = [&](long long work_items, int per_cta) {
-        const long long need = (work_items + per_cta - 1) / per_cta;
-        return (unsigned)(need < ff_max ? (need > 0 ? need : 1) : ff_max);
-    };
+    // feed-forward part (thread = sample / ring revolution): whole-GPU kernels, ~0.3 ms per 10 s block of 2048 channels
     mark(0, s_ff);
-    angle_corr_kernel<<<ff_grid((long long)((a.n_new + kTile - 1) / kTile) * a.channels, kFfTeams), kFfThreads, kFfSmem, s_ff>>>(a);
+    angle_corr_kernel<<<dim3((a.n_new + kTile - 1) / kTile, a.channels), kThreads, 0, s_ff>>>(a);
     mark(1, s_ff);
     {   // ring revolutions with an evaluation sample in [-8, n_new): samples 16 + 567 K .. 582 + 567 K
         const long long lo = a.seen - 8 - (kCorrLen + 15), hi = a.seen + a.n_new - 17;
         const int k_lo = lo <= 0 ? 0 : (int)((lo + kCorrLen - 1) / kCorrLen);
         if (hi >= 0 && (int)(hi / kCorrLen) >= k_lo) {
             const int n_rev = (int)(hi / kCorrLen) - k_lo + 1;
-            const long long passes = (long long)((n_rev + kSlotRev - 1) / kSlotRev) * a.channels;
-            offset_sum_kernel<<<ff_grid(passes, kSlots), kSumThreads, kSumSmem, s_ff>>>(a, k_lo, n_rev);
+            const long long units = (long long)a.channels * n_rev;
+            offset_sum_kernel<<<(unsigned)((units + 3 * kSumWarps - 1) / (3 * kSumWarps)), kSumWarps * 32, 0, s_ff>>>(a, k_lo, n_rev);
         }
     }
     mark(2, s_ff);
-    carry_kernel<<<ff_grid(a.channels, kFfThreads / kCarryTeam), kFfThreads, kFfSmem, s_ff>>>(a);
+    carry_kernel<<<a.channels, 256, 0, s_ff>>>(a);
     mark(3, s_ff);
     // sequential part: few warps, latency-bound, runs beside the next block's cascade on the SMs it leaves free
     if (s_seq != s_ff) {

@@ -53,7 +53,6 @@ struct DemodArgs {
     float2* y3_next;          // buffer of the NEXT block: receives the kHistY-sample history (may equal b.y3)
     int n_new;                // new 900 Hz samples per channel in this block
     int channels;             // streams * 2
-    int ff_ctas;              // SMs the persistent feed-forward kernels may occupy (one CTA each)
     long long seen;           // 900 Hz samples consumed before this block (same for every channel)
     // per-launch outputs
     uint8_t* events;          // [channels][ev_cap]: appended characters, '\n' = line complete, 0x18 = abort
@@ -68,7 +67,7 @@ struct DemodArgs {
 size_t demod_pick_pitch(int p_max);  // row pitch of DemodBuffers::picks in bytes
 size_t demod_bit_pitch(int p_max);   // row pitch of DemodBuffers::bitpos / bitval in elements
 // SMs the sequential kernels want for themselves (the cascade grid is sized to leave them free)
-int demod_seq_sms(int channels);
+int demod_reserved_sms(int channels);
 // Queues the feed-forward kernels (angle/correlation, per-offset sums + arg max, history carry) on s_ff and the
 // sequential symbol clock, the per-bit window decisions and the SITOR-B state machine on s_seq (ordered after them
 // through ff_done when the two streams differ).  marks: optional 8 events recorded around the kernels (timing mode).

@@ -98,15 +98,13 @@ __global__ void tail_carry_kernel(const Sample* __restrict__ old_tail, const Sam
 
 }  // namespace
 
-constexpr int kBuf = 4;   // blocks in flight: cascade(i+2) | feed-forward demod(i+1) | symbol clocks + state machines + event download(i)
+constexpr int kBuf = 3;   // blocks in flight: cascade of block i+1/i+2 overlaps demod + event download of block i
 
 struct nvx_engine {
     nvx_config cfg;
     int S = 0, P_max = 0, channels = 0;
     cudaStream_t stream = nullptr;        // cascade, tail carry, ingest copies / conversion
-    cudaStream_t stream_ff = nullptr;     // feed-forward demod kernels (persistent CTAs on their own SMs), one block behind
-    cudaStream_t stream_demod = nullptr;  // sequential demod kernels + event download, two blocks behind
-    int ff_ctas = 16;                     // SMs given to the feed-forward kernels
+    cudaStream_t stream_demod = nullptr;  // demod kernels + event download, one block behind
     float2* y3buf[kBuf] = {};
     uint8_t* pickbuf[kBuf] = {};
     cudaEvent_t casc_done[kBuf] = {}, demod_done[kBuf] = {}, ff_done[kBuf] = {};
@@ -140,7 +138,7 @@ struct nvx_engine {
     int lcur = 0;
     std::vector<int> stream_tag;          // optional [S][2] message tags
     bool serial = false;                  // NVX_PIPELINE=serial: the next cascade waits for this block's whole demod
-    bool ff_on_main = true;               // feed-forward demod kernels follow the cascade on the main stream (default)
+    bool ff_on_main = true;               // feed-forward demod kernels follow the cascade on the main stream
     int target_warps[2] = {576, 576};     // resident cascade warps per sample format
     nvx::MessageAssembler assembler;
     std::vector<nvx::AssembledMessage> ready, handed;
@@ -168,7 +166,6 @@ int free_engine(nvx_engine* e) {
     if (!e) return 0;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->stream_ff) cudaStreamSynchronize(e->stream_ff);
     if (e->stream_demod) cudaStreamSynchronize(e->stream_demod);
     if (e->worker.joinable()) {
         {
@@ -202,7 +199,6 @@ int free_engine(nvx_engine* e) {
         cudaFree(e->pickbuf[k]);
     }
     if (e->stream) cudaStreamDestroy(e->stream);
-    if (e->stream_ff) cudaStreamDestroy(e->stream_ff);
     if (e->stream_demod) cudaStreamDestroy(e->stream_demod);
     delete e;
     return 0;
@@ -326,7 +322,6 @@ int sync_engine(nvx_engine* e) {
     CU_TRY(cudaSetDevice(e->cfg.device));
     CU_TRY(cudaStreamSynchronize(e->stream_copy));
     CU_TRY(cudaStreamSynchronize(e->stream));
-    CU_TRY(cudaStreamSynchronize(e->stream_ff));
     CU_TRY(cudaStreamSynchronize(e->stream_demod));
     collect_spans(e);
     wait_drained(e, e->blocks);
@@ -354,7 +349,6 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     wait_drained(e, e->blocks - kBuf + 1);          // block (blocks - kBuf) used these buffers: long finished, normally
     if (e->timing && e->ev_used > 4000) {            // bound the event pool in long timed runs
         CU_TRY(cudaStreamSynchronize(e->stream));
-        CU_TRY(cudaStreamSynchronize(e->stream_ff));
         CU_TRY(cudaStreamSynchronize(e->stream_demod));
         collect_spans(e);
     }
@@ -443,17 +437,13 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     da.n_new = n_super; da.channels = e->channels; da.seen = e->sb_abs;
     da.events = e->d_events[b]; da.ev_count = e->d_ev_count[b]; da.ev_cap = e->ev_cap;
     da.bits = e->d_bits; da.disc = e->d_disc; da.bit_count = e->d_bit_count; da.bit_cap = e->bit_cap;
-    // Default: the feed-forward demod kernels (0.3 ms of whole-GPU work) follow the cascade on the main stream; only the
-    // sequential kernels overlap the next block's cascade, on the <= 4 SMs its grid leaves free.
-    // NVX_PIPELINE=partition: three-deep pipeline on three streams and three disjoint sets of SMs -- cascade(i+2) on
-    // ~128 SMs, the persistent feed-forward kernels of block i+1 on ff_ctas SMs, the sequential kernels of block i on
-    // <= 4 SMs.  Measured equal within noise: the cascade loses beside the FP64 work what the overlap gains.
-    cudaStream_t s_ff = e->ff_on_main ? e->stream : e->stream_ff;
-    if (!e->ff_on_main) CU_TRY(cudaStreamWaitEvent(s_ff, e->casc_done[b], 0));
-    // the history carry of this block writes into the next y3 buffer, last used by block i + 1 - kBuf: its sequential
-    // kernels must be done (they are, normally)
-    if (e->blocks >= kBuf - 1) CU_TRY(cudaStreamWaitEvent(s_ff, e->demod_done[(b + 1) % kBuf], 0));
-    da.ff_ctas = e->ff_ctas;
+    // The feed-forward demod kernels are short whole-GPU kernels; beside the cascade (one warp per SM sub-partition,
+    // no latency slack) they cost it more than they take alone, so by default they follow it on the main stream and
+    // only the sequential symbol-clock / state-machine kernel (64 warps) overlaps the next block's cascade.
+    cudaStream_t s_ff = e->ff_on_main ? e->stream : e->stream_demod;
+    if (!e->ff_on_main) CU_TRY(cudaStreamWaitEvent(e->stream_demod, e->casc_done[b], 0));
+    // the history carry of this block writes into the y3 buffer block i-2 used: its symbol clock must be done (it is, normally)
+    else if (e->blocks >= kBuf - 1) CU_TRY(cudaStreamWaitEvent(e->stream, e->demod_done[(b + 1) % kBuf], 0));
     CU_TRY(demod_launch(da, s_ff, e->stream_demod, e->ff_done[b], e->timing > 1 ? marks : nullptr));
     CU_TRY(cudaMemcpyAsync(e->h_ev_count[b], e->d_ev_count[b], sizeof(int) * e->channels, cudaMemcpyDeviceToHost, e->stream_demod));
     CU_TRY(cudaMemcpyAsync(e->h_events[b], e->d_events[b], (size_t)e->channels * e->ev_cap, cudaMemcpyDeviceToHost, e->stream_demod));
@@ -589,13 +579,12 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
             CREATE_TRY(cudaEventCreateWithFlags(&e->copy_done[k], cudaEventDisableTiming));
             CREATE_TRY(cudaEventCreateWithFlags(&e->stage_free[k], cudaEventDisableTiming));
         }
-        CREATE_TRY(cudaStreamCreateWithPriority(&e->stream_ff, cudaStreamNonBlocking, hi));
         CREATE_TRY(cudaStreamCreateWithPriority(&e->stream_demod, cudaStreamNonBlocking, hi));
-        // tuning knob NVX_PIPELINE: "partition" = feed-forward demod kernels on their own stream and SMs beside the next
-        // cascade, "serial" = the next cascade waits for the whole demod; default = see process_block
+        // tuning knob NVX_PIPELINE: "overlap" = feed-forward demod kernels on the demod stream too (beside the next
+        // cascade), "serial" = the next cascade waits for the whole demod; default = see process_block
         const char* mode = getenv("NVX_PIPELINE");
+        e->ff_on_main = !(mode && !strcmp(mode, "overlap"));
         e->serial = mode && !strcmp(mode, "serial");
-        e->ff_on_main = !(mode && !strcmp(mode, "partition"));
     }
     for (int k = 0; k < kBuf; ++k) {
         CREATE_TRY(cudaEventCreateWithFlags(&e->casc_done[k], cudaEventDisableTiming));
@@ -649,18 +638,7 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     for (int f = 0; f < 2; ++f)
         for (int k = 0; k < 2; ++k)
             if (int rc = encode_rows(&e->map_tail[f][k], e->tail[f][k], nvx::kHalo, e->S, f != 0)) { free_engine(e); return rc; }
-    {   // SM budget: the cascade saturates HBM from ~128 of 148 SMs (measured: 128 / 136 / 144 SMs = 3.41 / 3.36 /
-        // 3.44 ms per block), so 16 SMs go to the feed-forward demod kernels and up to 4 to the sequential ones
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
-        const int seq_sms = nvx::demod_seq_sms(e->channels);
-        int ff_sms = sms >= 64 ? 16 : (sms >= 16 ? sms / 8 : 1);
-        if (const char* env = getenv("NVX_FF_SMS")) ff_sms = atoi(env) > 0 ? atoi(env) : ff_sms;     // tuning knob
-        e->ff_ctas = e->ff_on_main ? sms : ff_sms;
-        int reserve = seq_sms + (e->ff_on_main ? 0 : ff_sms);
-        if (const char* env = getenv("NVX_RESERVE_SMS")) reserve = atoi(env);                       // tuning knob
-        for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, reserve, f != 0);
-    }
+    for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels), f != 0);
     e->assembler.resize(e->channels);
     if (int rc = reset_state(e)) { free_engine(e); return rc; }
     e->worker = std::thread(worker_main, e);
