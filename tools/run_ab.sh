@@ -1,4 +1,7 @@
-for r in 4 12 20 4 12 20; do
-  echo "== reserve=$r"
-  NVX_RESERVE_SMS=$r python tools/quick_perf.py --steps 40 --timing 1 2>&1 | tail -1
+export NVX_PIPELINE=overlap
+for pad in 0 16000 24000 38000; do
+  echo "== overlap pad=$pad"
+  NVX_DEMOD_PAD=$pad python tools/quick_perf.py --steps 40 --timing 2 2>&1 | tail -3 | cut -c1-140
 done
+unset NVX_PIPELINE
+echo "== default"; python tools/quick_perf.py --steps 40 --timing 2 2>&1 | tail -3 | cut -c1-140
