@@ -85,3 +85,35 @@ def test_message_store_replaces_by_bbbb_and_purges(tmp_path):
     assert '""quoted""' in lines[2] and "\\n" in lines[2]
     assert st.purge(now=t0 + 100 + 72 * 3600) == 1 and len(st.rows()) == 2      # only the t0 + 60 row is older than 72 h
     st.close()
+
+
+def build_example(name, out_dir):
+    """Compile examples/<name> against the public headers and the in-tree libraries (plain gcc / g++, no nvcc)."""
+    import subprocess
+
+    src = os.path.join(ROOT, "examples", name)
+    exe = os.path.join(str(out_dir), os.path.splitext(name)[0])
+    lib_dir = os.path.join(ROOT, "navtex_b200")
+    if name.endswith(".c"):
+        cmd = ["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), src, "-L" + lib_dir, "-lnavtex_b200"]
+    else:
+        cmd = ["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), src, "-L" + lib_dir, "-lnavtex_compat",
+               "-lnavtex_b200"]
+    subprocess.run(cmd + ["-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    return exe
+
+
+def test_example_hosts_compile_as_c_and_cpp(tmp_path):
+    """navtex_b200.h is valid C11, navtex_compat.h valid C++; a host using only the reference's names links."""
+    import subprocess
+    import torch
+
+    exe = build_example("wav_decode.c", tmp_path)
+    build_example("relink_host.cpp", tmp_path)
+    if not torch.cuda.is_available():
+        from navtex_b200 import synth
+        wav = str(tmp_path / "c.wav")
+        synth.write_wav(wav, cases.build("clean518"))
+        cp = subprocess.run([exe, wav], capture_output=True, text=True)
+        assert cp.returncode == 1 and "no CPU path" in cp.stderr          # fails loudly, decodes nothing
+        assert cp.stdout == ""

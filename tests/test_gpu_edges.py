@@ -112,3 +112,23 @@ def test_argument_errors():
         engine.Engine(40000, 2800)                                   # more than one engine's worth of streams
     with pytest.raises(engine.NvxError):
         engine.Engine(1, 2800, taps=(np.ones(2000), np.ones(47), np.ones(71)))
+
+
+def test_c_and_relinked_hosts(tmp_path):
+    """The two example hosts -- plain C on the batched ABI, and a C++ host that only knows the reference's own names
+    (init_fir_filter1 / sample_in_1 / init_fir2_wrapper / add_message, nav_sched.C-style wiring) -- print the golden
+    messages of the unmodified reference."""
+    import subprocess
+
+    from test_abi import build_example
+
+    iq = cases.build("clean518")
+    g = np.load(os.path.join(GOLDEN, "clean518.npz"))
+    want = "".join("%d|%s|%d\n%s\n" % (int(f), str(b), len(str(t)), str(t)) for f, b, t in zip(g["msg_freq"], g["msg_bbbb"], g["msg_text"]))
+    wav, raw = str(tmp_path / "c.wav"), str(tmp_path / "c.s16")
+    synth.write_wav(wav, iq)
+    iq.tofile(raw)
+    out = subprocess.run([build_example("wav_decode.c", tmp_path), wav], capture_output=True, text=True, check=True)
+    assert out.stdout == want
+    out = subprocess.run([build_example("relink_host.cpp", tmp_path), raw], capture_output=True, text=True, check=True)
+    assert out.stdout == want
