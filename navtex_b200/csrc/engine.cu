@@ -1,6 +1,7 @@
 // engine.cu -- the C ABI of include/navtex_b200.h: per-GPU engine that owns the carried state of
-// S independent streams and queues, per pushed block, the fused FIR cascade, the tail carry, the
-// demod/bit-sync/FSM kernel and the event download; host side it runs the message assembler.
+// S independent streams and queues, per pushed block, the fused FIR cascade (or the three long-tap
+// stage kernels), the tail carry, the demod / bit-sync / state-machine kernels and the event
+// download; host side it runs the message assembler on a worker thread.
 //
 // Call contract it replaces: capt_sched.c:552-555 (init_dsp), :612 (init_fir2_wrapper) and the
 // consumer loop :484-528 that calls sample_in_1 once per IQ pair.

@@ -11,16 +11,18 @@
 // Mapping (B200-first, not the reference's ring buffers):
 //   * one THREAD owns one (stream, time-segment) "row"; a warp is 32 rows.  Every FIR stage
 //     runs in transposed (scatter) polyphase form: an arriving sample is multiply-added into
-//     the few output accumulators it belongs to, so the whole cascade state is 9 + 2*6 + 2*7
+//     the few output accumulators it belongs to, so the whole cascade state is 9 + 2*6 + 2*8
 //     complex partial sums in registers and no intermediate (63 kHz, 9 kHz) sample ever
 //     touches shared memory or HBM.
 //   * I and Q ride in one 64-bit register pair and every tap is one FFMA2 (fma.rn.f32x2) with
 //     the tap as a 32-bit immediate / uniform operand: 2 FMAs per lane per issue slot.
-//   * a warp's 32 rows are 32 consecutive streams at the same time segment, so the 28 samples
-//     each of them needs for one step form a [32 streams x 224 B] box of the stream-major
-//     input: ONE TMA tensor copy (cp.async.bulk.tensor.2d -> UTMALDG) per warp per step into
-//     a per-warp ring of shared-memory stages, completion tracked by one mbarrier per stage.
-//     Each lane then reads its own 224-byte row with LDS.128.
+//   * a warp's 32 rows are 32 consecutive streams at the same time segment, so the samples they
+//     need for two 28-sample steps form a [32 streams x 448 B] box of the stream-major input
+//     (224 B when the input is int16 pairs): ONE TMA tensor copy (cp.async.bulk.tensor.2d ->
+//     UTMALDG) per warp per stage into a per-warp ring of shared-memory stages, completion
+//     tracked by one mbarrier per stage.  Each lane then reads its own row with LDS.128.
+//   * variants (template flags): taps as immediates or from the constant bank (replacement tap
+//     sets), the reference's 9-entry NCO table or an exact per-stream NCO, float2 or short2 input.
 //   * time segments are made independent by recomputing a 7-superblock (1960-sample) warm-up
 //     from the raw input that precedes the segment (previous segment, or the carried tail of
 //     the previous chunk); since every 900 Hz output depends on exactly 2181 inputs
@@ -45,8 +47,7 @@ constexpr int kNcoPeriod = 9;                      // fir2cpp.C:12-14
 // (profiles/r1_staging_sweep.md): HBM efficiency of the [32 streams x B bytes] access pattern rises with B
 // (224 B: 6.2 TB/s, 448 B: 6.9 TB/s with no compute at all), the FMA pipe wants the same number of warps on each of
 // the four SM sub-partitions (4 or 8 warps per SM), and the third ring stage matters more than a second warp per
-// sub-partition.  Default: 448-byte rows (+16 B pad), 3 stages, 4 warps, 1 CTA per SM = 178 KB of shared memory,
-// which leaves room for the small demod kernels of the previous block to run alongside.
+// sub-partition.  Default: 448-byte rows (+16 B pad), 3 stages, 4 warps, 1 CTA per SM = 178 KB of shared memory.
 #ifndef NVX_STEPS_PER_STAGE
 #define NVX_STEPS_PER_STAGE 2
 #endif
