@@ -213,7 +213,7 @@ int reset_state(nvx_engine* e) {
     if (e->long_taps)
         for (int k = 0; k < 3; ++k)
             for (int q = 0; q < 2; ++q)
-                CU_TRY(cudaMemsetAsync(e->lhist[k][q], 0, (size_t)(k == 2 ? e->channels : e->S) * e->lst[k].H * sizeof(float2), e->stream));
+                CU_TRY(cudaMemsetAsync(e->lhist[k][q], 0, (size_t)(k == 0 ? e->S : e->channels) * e->lst[k].H * sizeof(float2), e->stream));
     e->lcur = 0;
     for (int k = 0; k < kBuf; ++k) {
         e->db.y3 = e->y3buf[k];
@@ -395,16 +395,16 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         const long long p1 = e->cfg.max_block / NVX_D1, p2 = e->cfg.max_block / (NVX_D1 * NVX_D2);
         LongArgs la = {};
         la.in = d_x; la.hist = e->lhist[0][cur]; la.out = e->y1buf; la.n_in = n; la.out_pitch = p1; la.out_off = 0;
-        la.rows_in = e->S; la.stage = 0; la.s16 = s16;
-        CU_TRY(long_launch(la, e->lst[0], n, e->stream));
+        la.rows_in = e->S; la.stage = 0; la.s16 = s16; la.k_abs = e->sb_abs * (kSuper / NVX_D1); la.nco = e->d_nco;
+        CU_TRY(long_launch(la, e->lst[0], n, e->stream));                 // 252 k -> 63 k, mixed: one row per channel
         CU_TRY(long_carry(e->lhist[0][cur], d_x, n, e->lhist[0][nx], e->S, e->lst[0].H, n, s16, e->stream));
         la.in = e->y1buf; la.hist = e->lhist[1][cur]; la.out = e->y2buf; la.n_in = n / NVX_D1; la.out_pitch = p2;
-        la.stage = 1; la.s16 = 0; la.k_abs = e->sb_abs * (kSuper / NVX_D1); la.nco = e->d_nco;
-        CU_TRY(long_launch(la, e->lst[1], p1, e->stream));
-        CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->S, e->lst[1].H, n / NVX_D1, 0, e->stream));
+        la.rows_in = e->channels; la.stage = 1; la.s16 = 0; la.nco = nullptr;
+        CU_TRY(long_launch(la, e->lst[1], p1, e->stream));                // 63 k -> 9 k
+        CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->channels, e->lst[1].H, n / NVX_D1, 0, e->stream));
         la.in = e->y2buf; la.hist = e->lhist[2][cur]; la.out = e->y3buf[b]; la.n_in = n / (NVX_D1 * NVX_D2);
-        la.out_pitch = ca.y3_pitch; la.out_off = ca.y3_off; la.rows_in = e->channels; la.stage = 2; la.nco = nullptr;
-        CU_TRY(long_launch(la, e->lst[2], p2, e->stream));
+        la.out_pitch = ca.y3_pitch; la.out_off = ca.y3_off; la.stage = 2;
+        CU_TRY(long_launch(la, e->lst[2], p2, e->stream));                // 9 k -> 900
         CU_TRY(long_carry(e->lhist[2][cur], e->y2buf, p2, e->lhist[2][nx], e->channels, e->lst[2].H, la.n_in, 0, e->stream));
         e->lcur = nx;
         e->stats.aux_launches += 5;
@@ -625,8 +625,8 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
                                          cfg->h3 ? cfg->h3 : d3, e->lst[2].T, e->stream));
         for (int k = 0; k < 3; ++k)
             for (int q = 0; q < 2; ++q)
-                CREATE_TRY(cudaMalloc(&e->lhist[k][q], (size_t)(k == 2 ? e->channels : e->S) * e->lst[k].H * sizeof(float2)));
-        CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->S * (cfg->max_block / NVX_D1) * sizeof(float2)));
+                CREATE_TRY(cudaMalloc(&e->lhist[k][q], (size_t)(k == 0 ? e->S : e->channels) * e->lst[k].H * sizeof(float2)));
+        CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->channels * (cfg->max_block / NVX_D1) * sizeof(float2)));
         CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));
     } else {
         CREATE_TRY(nvx::cascade_upload_constants(cfg->h1, cfg->h2, cfg->h3, e->stream));

@@ -31,59 +31,46 @@ __device__ __forceinline__ float2 load_sample(const LongArgs& a, int row, long l
 template <int D>
 __device__ __forceinline__ int slot(int f) { return f + f / (kLongR * D); }
 
-// grid (tiles, output rows); STAGE 1 (the second stage) has two output rows (channels) per input row and mixes while staging
+// grid (tiles, input rows).  STAGE 0 (the first stage) writes TWO output rows per input row: its 63 kHz outputs rotated by
+// each channel's NCO (fir2cpp.C:112-128), so that the second stage is a plain FIR over channel rows.
 template <int D, int STAGE>
 __global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a, const int J, const long long in_pitch) {
     extern __shared__ __align__(16) float2 s_x[];
     const int H = D * J;
     const int F = D * (kLongTile + J - 1);                    // inputs staged per tile
-    const int row_out = blockIdx.y;
-    const int row_in = STAGE == 1 ? row_out >> 1 : row_out;
-    const int ch = row_out & 1;
+    const int row_in = blockIdx.y;
     const long long k0 = (long long)blockIdx.x * kLongTile;  // first output of the tile
     const long long n_out = a.n_in / D;
     const long long g0 = (long long)D * (k0 - J + 1);        // first input the tile needs (oldest tap of output k0)
 
-    // ---- stage the tile; stage 2 rotates by the channel's NCO on the way in ----
-    NcoParam np = {};
-    int k9 = 0, kden = 0;                                     // NCO clock of the tile's first input, reduced once
-    if (STAGE == 1) {
-        if (a.nco) np = a.nco[row_in];
-        long long k = (a.k_abs + g0) % kNcoPeriod, kd = (a.k_abs + g0) % kNcoDen;
-        k9 = (int)(k < 0 ? k + kNcoPeriod : k);
-        kden = (int)(kd < 0 ? kd + kNcoDen : kd);
-    }
-    constexpr int kBatch = 8;                                 // loads in flight per thread (the staging is latency-bound)
-    for (int base = 0; base < F; base += kLongThreads * kBatch) {
-        float2 v[kBatch];
+    // ---- stage the tile: a pure copy, so float2 sources go through cp.async (every load of the tile in flight at once);
+    // int16 input is converted on the way and keeps the register path ----
+    if (a.s16) {
+        constexpr int kBatch = 8;
+        for (int base = 0; base < F; base += kLongThreads * kBatch) {
+            float2 v[kBatch];
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            const int f = base + i * kLongThreads + (int)threadIdx.x;
-            v[i] = f < F ? load_sample(a, row_in, in_pitch, H, g0 + f) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            const int f = base + i * kLongThreads + (int)threadIdx.x;
-            if (f >= F) break;
-            float2 x = v[i];
-            if (STAGE == 1) {
-                float2 rot;
-                if (a.nco) {
-                    const long long k = (kden + f) % kNcoDen;
-                    const int ph = (int)((k * np.num[ch]) % kNcoDen);
-                    float t = (float)ph * (2.0f / kNcoDen);
-                    if (t > 1.0f) t -= 2.0f;
-                    float sn, cs;
-                    sincospif(t, &sn, &cs);
-                    rot = make_float2(cs, -sn);
-                } else {
-                    rot = c_long_nco[(k9 + f) % kNcoPeriod];
-                    if (ch) rot.y = -rot.y;                   // "490": conjugate rotation (fir2cpp.C:121-124)
-                }
-                x = make_float2(fmaf(-x.y, rot.y, x.x * rot.x), fmaf(x.x, rot.y, x.y * rot.x));
+            for (int i = 0; i < kBatch; ++i) {
+                const int f = base + i * kLongThreads + (int)threadIdx.x;
+                v[i] = f < F ? load_sample(a, row_in, in_pitch, H, g0 + f) : make_float2(0.f, 0.f);
             }
-            s_x[slot<D>(f)] = x;
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                const int f = base + i * kLongThreads + (int)threadIdx.x;
+                if (f < F) s_x[slot<D>(f)] = v[i];
+            }
         }
+    } else {
+        const float2* blk = static_cast<const float2*>(a.in) + (size_t)row_in * in_pitch;
+        const float2* hist = a.hist + (size_t)row_in * H + H;
+        for (int f = threadIdx.x; f < F; f += kLongThreads) {
+            const long long g = g0 + f;
+            float2* dst = s_x + slot<D>(f);
+            if (g >= a.n_in) { *dst = make_float2(0.f, 0.f); continue; }
+            const float2* src = g < 0 ? hist + g : blk + g;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
@@ -122,10 +109,46 @@ __global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a
             }
         }
     }
-    float2* out = a.out + (size_t)row_out * a.out_pitch + a.out_off + k0 + (long long)kLongR * t;
+    if (STAGE == 0) {
+        // NCO mix: output k sits at 63 kHz clock tick k_abs + k; channel c gets y1 * (cos - j sin)(2 pi tick f_c / 63000)
+        float2* out0 = a.out + (size_t)(2 * row_in) * a.out_pitch + a.out_off + k0 + (long long)kLongR * t;
+        float2* out1 = out0 + a.out_pitch;
+        NcoParam np = {};
+        if (a.nco) np = a.nco[row_in];
+        const long long tick0 = a.k_abs + k0 + (long long)kLongR * t;
+        long long r9 = tick0 % kNcoPeriod, rden = tick0 % kNcoDen;
+        int k9 = (int)(r9 < 0 ? r9 + kNcoPeriod : r9), kden = (int)(rden < 0 ? rden + kNcoDen : rden);
 #pragma unroll
-    for (int u = 0; u < kLongR; ++u)
-        if (k0 + (long long)kLongR * t + u < n_out) out[u] = acc[u];
+        for (int u = 0; u < kLongR; ++u) {
+            float2 rot[2];
+            if (a.nco) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int ph = (int)(((long long)kden * np.num[c]) % kNcoDen);
+                    float tt = (float)ph * (2.0f / kNcoDen);
+                    if (tt > 1.0f) tt -= 2.0f;
+                    float sn, cs;
+                    sincospif(tt, &sn, &cs);
+                    rot[c] = make_float2(cs, -sn);
+                }
+            } else {
+                rot[0] = c_long_nco[k9];
+                rot[1] = make_float2(rot[0].x, -rot[0].y);     // "490": conjugate rotation (fir2cpp.C:121-124)
+            }
+            if (k0 + (long long)kLongR * t + u < n_out) {
+                const float2 y = acc[u];
+                out0[u] = make_float2(fmaf(-y.y, rot[0].y, y.x * rot[0].x), fmaf(y.x, rot[0].y, y.y * rot[0].x));
+                out1[u] = make_float2(fmaf(-y.y, rot[1].y, y.x * rot[1].x), fmaf(y.x, rot[1].y, y.y * rot[1].x));
+            }
+            if (++k9 == kNcoPeriod) k9 = 0;
+            if (++kden == kNcoDen) kden = 0;
+        }
+    } else {
+        float2* out = a.out + (size_t)row_in * a.out_pitch + a.out_off + k0 + (long long)kLongR * t;
+#pragma unroll
+        for (int u = 0; u < kLongR; ++u)
+            if (k0 + (long long)kLongR * t + u < n_out) out[u] = acc[u];
+    }
 }
 
 template <typename Sample>
@@ -156,8 +179,7 @@ cudaError_t launch_one(const LongArgs& a, const LongStage& st, long long in_pitc
         attr = smem;
     }
     const long long n_out = a.n_in / D;
-    const int rows_out = STAGE == 1 ? 2 * a.rows_in : a.rows_in;
-    fir_long_kernel<D, STAGE><<<dim3((unsigned)((n_out + kLongTile - 1) / kLongTile), (unsigned)rows_out), kLongThreads, smem, stream>>>(
+    fir_long_kernel<D, STAGE><<<dim3((unsigned)((n_out + kLongTile - 1) / kLongTile), (unsigned)a.rows_in), kLongThreads, smem, stream>>>(
         a, st.J, in_pitch);
     return cudaGetLastError();
 }

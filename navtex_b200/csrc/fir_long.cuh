@@ -12,8 +12,9 @@
 //     de-interleaved by decimation phase (x_p[m] = x[D m + p]) so that lanes read consecutive addresses;
 //   * a thread owns R = 8 consecutive outputs; per phase it slides an R-wide register window over x_p and applies the
 //     taps of that phase (warp-uniform constant-bank operands) as packed FFMA2 on (I, Q): R * R FFMA2 per R loads;
-//   * the stage-2 kernel applies the NCO rotation while staging (9-entry table of the reference or the exact per-stream
-//     phase of the general NCO).
+//   * the stage-1 kernel applies the NCO rotation of both channels in its epilogue (9-entry table of the reference or
+//     the exact per-stream phase of the general NCO) and writes one 63 kHz row per channel, so stages 2 and 3 are
+//     plain FIRs over channel rows.
 // History between blocks is carried per stage (last H inputs of each row), not recomputed.
 #pragma once
 #include <cuda_runtime.h>
@@ -38,14 +39,14 @@ struct LongStage {
 struct LongArgs {
     const void* in;           // [rows_in][in_pitch] float2 (or short2 for stage 1 with s16 input), this block
     const float2* hist;       // [rows_in][H] float2: the H samples that preceded the block (always float2)
-    float2* out;              // [rows_out][out_pitch], written at out_off + k
+    float2* out;              // [rows_out][out_pitch], written at out_off + k; stage 1: rows_out = 2 rows_in (one per channel)
     long long n_in;           // input samples per row in this block (multiple of D)
     long long out_pitch, out_off;
-    int rows_in;              // streams (stage 1, 2) or channels (stage 3)
+    int rows_in;              // streams (stage 1) or channels (stages 2, 3)
     int stage;                // 0, 1, 2
     int s16;                  // stage 1 only: input block is short2
-    long long k_abs;          // stage 2: absolute index of the block's first input sample (63 kHz clock), for the NCO
-    const NcoParam* nco;      // stage 2: per-stream general NCO or null (reference table)
+    long long k_abs;          // stage 1: absolute index of the block's first OUTPUT sample (63 kHz clock), for the NCO
+    const NcoParam* nco;      // stage 1: per-stream general NCO or null (reference table)
 };
 
 LongStage long_stage(int D, int T);
