@@ -53,7 +53,9 @@ typedef struct {
     int freq_tag[2];            /* tags handed to add_message for channel 0 (+14 kHz) / 1 (-14 kHz); 0,0 = 518,490 */
     /* optional replacement tap sets (NULL = reference taps).  With n1 = n2 = n3 = 0 they have the reference lengths
      * 37 / 47 / 71 and run through the fused cascade kernel; other lengths (1 .. 1024, e.g. the 255-tap stress designs)
-     * select the long-tap path: one register-tiled FIR kernel per stage, intermediates in HBM */
+     * select the long-tap path: one register-tiled FIR kernel per stage, intermediates in HBM.
+     * Tap sets live in the device's constant bank, which all engines of a process on that device share: engines that
+     * are alive at the same time on one device must use the same tap sets (the last create wins) */
     const double *h1, *h2, *h3;
     int keep_bits;              /* record 'B'/'Y' decisions and discriminator sums for nvx_engine_read_bits */
     int first_stream_id;        /* global id of stream 0 (multi-GPU sharding; only used to label messages) */
