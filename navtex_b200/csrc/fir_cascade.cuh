@@ -70,10 +70,10 @@ constexpr int kNcoPeriod = 9;                      // fir2cpp.C:12-14
 #define NVX_S16_ROW_PAD_BYTES 16
 #endif
 #ifndef NVX_S16_STAGES
-#define NVX_S16_STAGES 3
+#define NVX_S16_STAGES 2
 #endif
 #ifndef NVX_S16_WARPS_PER_CTA
-#define NVX_S16_WARPS_PER_CTA 8
+#define NVX_S16_WARPS_PER_CTA 12
 #endif
 constexpr int kCtasPerSm = NVX_CTAS_PER_SM;
 // Staging geometry per input sample format.  float2 input: 8 B / sample, 2 steps = 448 B (+16 B pad) per row.
@@ -82,7 +82,8 @@ constexpr int kCtasPerSm = NVX_CTAS_PER_SM;
 // int16 variant is FP32-issue-bound, not HBM-bound (4.06 B / sample), so short rows cost it nothing, while a loop body
 // of more than two steps would outgrow the 32 KB L1.5 instruction cache -- with one warp per SM sub-partition an
 // instruction fetch from L2 is not hidden (measured: 5 steps per stage = 5.3 ms, 2 steps = 3.3 ms per block).  Being
-// issue-bound it also wants a second warp per sub-partition: 8 warps x 3 stages = 2.9 ms (4 warps x 6 stages: 3.27 ms).
+// issue-bound it also wants more warps per sub-partition: 12 warps x 2 stages = 2.77 ms, 8 x 3 = 2.90 ms, 16 x 1 = 2.81 ms,
+// 4 warps x 6 stages = 3.27 ms.
 template <bool kS16>
 struct InFmt {
     static constexpr int kSteps = kS16 ? NVX_S16_STEPS_PER_STAGE : NVX_STEPS_PER_STAGE;   // 28-sample steps per TMA box row
