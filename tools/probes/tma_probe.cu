@@ -15,6 +15,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 struct Args {
     CUtensorMap map;
     int groups, segs, steps_per_seg, box_floats, step_floats, stages, warps;
+    int split;      // boxes per stage: the row is fetched as `split` boxes of box_floats / split floats each (swizzle experiments)
     float* sink;
 };
 
@@ -39,8 +40,11 @@ __global__ void probe(const __grid_constant__ Args a) {
         if (lane == 0) {
             const uint32_t bar = bar0 + 8 * stage;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
-            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(wbase_s + stage * stage_pitch), "l"(&a.map), "r"((int)(col0 + (long long)t * a.step_floats)), "r"(row0), "r"(bar) : "memory");
+            const int part = a.box_floats / a.split;
+            for (int b = 0; b < a.split; ++b)
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(wbase_s + stage * stage_pitch + b * 32 * part * 4), "l"(&a.map),
+                               "r"((int)(col0 + (long long)t * a.step_floats) + b * part), "r"(row0), "r"(bar) : "memory");
         }
     };
     for (int s = 0; s < a.stages; ++s) if (s < a.steps_per_seg) issue(s, s);
@@ -72,18 +76,18 @@ int main() {
     EncodeTiledFn enc = (EncodeTiledFn)fn;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    struct Cfg { int step_floats, box_floats, stages, warps, ctas_per_sm, promo; };
+    struct Cfg { int step_floats, box_floats, stages, warps, ctas_per_sm, promo, split; };
     const Cfg cfgs[] = {
-        {56, 56, 3, 4, 2, 2},  {56, 56, 3, 4, 2, 0},  {56, 56, 3, 4, 2, 1},  {56, 60, 3, 4, 2, 2},
-        {56, 56, 4, 7, 1, 2},  {56, 56, 6, 4, 1, 2},  {56, 56, 2, 6, 2, 2},
-        {112, 112, 3, 2, 2, 2}, {112, 116, 3, 2, 2, 2}, {112, 112, 2, 3, 2, 2}, {112, 112, 2, 6, 1, 2},
-        {224, 224, 2, 3, 1, 2}, {224, 224, 3, 2, 1, 2}, {224, 224, 2, 2, 2, 1},
+        {112, 112, 3, 4, 1, 2, 1}, {112, 112, 4, 4, 1, 2, 1}, {112, 112, 4, 4, 1, 2, 7}, {112, 112, 3, 4, 1, 2, 7}, {112, 128, 3, 4, 1, 2, 4}, {112, 128, 3, 4, 1, 2, 1},
+        {56, 56, 3, 4, 2, 2, 1},  {56, 56, 6, 4, 1, 2, 1},
+        {112, 112, 3, 2, 2, 2, 1}, {112, 116, 3, 2, 2, 2, 1},
+        {224, 224, 2, 3, 1, 2, 1}, {224, 224, 3, 2, 1, 2, 1},
     };
     for (const Cfg& c : cfgs) {
         Args a;
         cuuint64_t dims[2] = {(cuuint64_t)(2 * n), (cuuint64_t)S};
         cuuint64_t strides[1] = {(cuuint64_t)(n * 8)};
-        cuuint32_t box[2] = {(cuuint32_t)c.box_floats, 32};
+        cuuint32_t box[2] = {(cuuint32_t)(c.box_floats / c.split), 32};
         cuuint32_t es[2] = {1, 1};
         CUtensorMapL2promotion promo = c.promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : c.promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
         CUresult r = enc(&a.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -94,7 +98,7 @@ int main() {
         a.segs = total_warps / a.groups;
         const long long total_steps = 2 * n / c.step_floats;
         a.steps_per_seg = (int)(total_steps / a.segs);
-        a.box_floats = c.box_floats; a.step_floats = c.step_floats; a.stages = c.stages; a.warps = c.warps; a.sink = sink;
+        a.box_floats = c.box_floats; a.step_floats = c.step_floats; a.stages = c.stages; a.warps = c.warps; a.sink = sink; a.split = c.split;
         const int stage_pitch = (32 * c.box_floats * 4 + 127) & ~127;
         const size_t smem = (size_t)c.warps * c.stages * stage_pitch + c.warps * c.stages * 8;
         const int grid = (a.groups * a.segs + c.warps - 1) / c.warps;
@@ -108,8 +112,8 @@ int main() {
             if (it && ms < best) best = ms;
         }
         const double bytes = (double)a.groups * a.segs * 32.0 * a.steps_per_seg * c.step_floats * 4.0;
-        printf("row %4d B (box %4d B) stages %d warps/cta %d ctas/sm %d promo %d smem/cta %6zu segs %3d: %.3f ms  %.0f GB/s\n", c.step_floats * 4,
-               c.box_floats * 4, c.stages, c.warps, c.ctas_per_sm, c.promo, smem, a.segs, best, bytes / best / 1e6);
+        printf("row %4d B (box %4d B x %d) stages %d warps/cta %d ctas/sm %d promo %d smem/cta %6zu segs %3d: %.3f ms  %.0f GB/s\n", c.step_floats * 4,
+               c.box_floats / c.split * 4, c.split, c.stages, c.warps, c.ctas_per_sm, c.promo, smem, a.segs, best, bytes / best / 1e6);
     }
     return 0;
 }
