@@ -51,9 +51,11 @@ typedef struct {
     int n_streams;              /* S */
     long long max_block;        /* largest n a push will carry (samples per stream) */
     int freq_tag[2];            /* tags handed to add_message for channel 0 (+14 kHz) / 1 (-14 kHz); 0,0 = 518,490 */
-    /* optional replacement tap sets (NULL = reference taps).  With n1 = n2 = n3 = 0 they have the reference lengths
-     * 37 / 47 / 71 and run through the fused cascade kernel; other lengths (1 .. 1024, e.g. the 255-tap stress designs)
-     * select the long-tap path: one register-tiled FIR kernel per stage, intermediates in HBM.
+    /* optional replacement tap sets (NULL = reference taps), lengths n1 / n2 / n3 (0 = the reference length 37 / 47 / 71).
+     * Sets of up to 37 / 47 / 71 taps and "medium" sets of up to 61 / 75 / 111 taps run through the fused cascade kernel
+     * (zero-padded to the class; the medium class is where it turns from HBM-bound to FP32-bound); longer ones (up to
+     * 1024 per stage, e.g. the 255-tap stress designs) take the long-tap path: one register-tiled FIR kernel per stage,
+     * intermediates in HBM.
      * Tap sets live in the device's constant bank, which all engines of a process on that device share: engines that
      * are alive at the same time on one device must use the same tap sets (the last create wins) */
     const double *h1, *h2, *h3;

@@ -27,9 +27,12 @@
 
 namespace nvx {
 int cascade_box_elems(bool s16);
-cudaError_t cascade_upload_constants(const double* h1, const double* h2, const double* h3, cudaStream_t stream);
-cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, bool s16, cudaStream_t stream);
-int cascade_target_warps(int device, int reserved_sms, bool s16);
+int cascade_tap_class(int n1, int n2, int n3);
+int cascade_warm_super(int tap_class);
+cudaError_t cascade_upload_constants(int tap_class, const double* h1, int n1, const double* h2, int n2, const double* h3, int n3,
+                                     cudaStream_t stream);
+cudaError_t cascade_launch(const CascadeArgs& a, int tap_class, bool custom_taps, bool s16, cudaStream_t stream);
+int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class);
 }  // namespace nvx
 
 namespace {
@@ -81,20 +84,20 @@ int encode_rows(CUtensorMap* map, const void* base, long long cols, long long ro
     return 0;
 }
 
-// new_tail[s] = last kHalo samples of (old_tail[s] ++ x[s][0..n)); kPer samples (16 bytes) per thread
+// new_tail[s] = last `halo` samples of (old_tail[s] ++ x[s][0..n)); kPer samples (16 bytes) per thread
 template <typename Sample>
 __global__ void tail_carry_kernel(const Sample* __restrict__ old_tail, const Sample* __restrict__ x, Sample* __restrict__ new_tail,
-                                  int streams, long long n) {
+                                  int streams, long long n, int halo) {
     constexpr int kPer = 16 / (int)sizeof(Sample);
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per = nvx::kHalo / kPer;
+    const long long per = halo / kPer;
     if (idx >= per * streams) return;
     const int s = (int)(idx / per);
     const long long k = (idx % per) * kPer;
-    const long long p = n - nvx::kHalo + k;                                      // n and kHalo are multiples of 4
+    const long long p = n - halo + k;                                            // n and halo are multiples of 280
     const int4* src = p >= 0 ? reinterpret_cast<const int4*>(x + (size_t)s * n + p)
-                             : reinterpret_cast<const int4*>(old_tail + (size_t)s * nvx::kHalo + (nvx::kHalo + p));
-    *reinterpret_cast<int4*>(new_tail + (size_t)s * nvx::kHalo + k) = *src;
+                             : reinterpret_cast<const int4*>(old_tail + (size_t)s * halo + (halo + p));
+    *reinterpret_cast<int4*>(new_tail + (size_t)s * halo + k) = *src;
 }
 
 }  // namespace
@@ -111,7 +114,9 @@ struct nvx_engine {
     cudaEvent_t casc_done[kBuf] = {}, demod_done[kBuf] = {}, ff_done[kBuf] = {};
     long long blocks = 0;
     int last_buf = 0;
-    // carried input tail, ping-pong, in the sample format being pushed: [S][kHalo] float2 or short2
+    int tap_class = 0;                    // fused-kernel tap-length class (fir_cascade.cuh), -1 = long-tap path
+    int halo = 1960;                      // carried input samples per stream: 280 x the class's warm-up superblocks
+    // carried input tail, ping-pong, in the sample format being pushed: [S][halo] float2 or short2
     void* tail[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [format][ping-pong]
     CUtensorMap map_tail[2][2];
     int tail_cur = 0;
@@ -208,7 +213,7 @@ int free_engine(nvx_engine* e) {
 int reset_state(nvx_engine* e) {
     for (int f = 0; f < 2; ++f)
         for (int k = 0; k < 2; ++k)
-            CU_TRY(cudaMemsetAsync(e->tail[f][k], 0, (size_t)e->S * nvx::kHalo * (f ? sizeof(short2) : sizeof(float2)), e->stream));
+            CU_TRY(cudaMemsetAsync(e->tail[f][k], 0, (size_t)e->S * e->halo * (f ? sizeof(short2) : sizeof(float2)), e->stream));
     e->fmt = -1;
     if (e->long_taps)
         for (int k = 0; k < 3; ++k)
@@ -409,20 +414,20 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         e->lcur = nx;
         e->stats.aux_launches += 5;
     } else {
-        CU_TRY(cascade_launch(ca, e->custom_taps, s16, e->stream));
+        CU_TRY(cascade_launch(ca, e->tap_class, e->custom_taps, s16, e->stream));
     }
     if (e->timing) CU_TRY(cudaEventRecord(t1, e->stream));
 
     const int nxt = e->tail_cur ^ 1;
     if (!e->long_taps) {
-        const long long work = (long long)e->S * (kHalo / (s16 ? 4 : 2));
+        const long long work = (long long)e->S * (e->halo / (s16 ? 4 : 2));
         const unsigned grid = (unsigned)((work + 255) / 256);
         if (s16)
             tail_carry_kernel<short2><<<grid, 256, 0, e->stream>>>(static_cast<const short2*>(e->tail[1][e->tail_cur]), static_cast<const short2*>(d_x),
-                                                                   static_cast<short2*>(e->tail[1][nxt]), e->S, n);
+                                                                   static_cast<short2*>(e->tail[1][nxt]), e->S, n, e->halo);
         else
             tail_carry_kernel<float2><<<grid, 256, 0, e->stream>>>(static_cast<const float2*>(e->tail[0][e->tail_cur]), static_cast<const float2*>(d_x),
-                                                                   static_cast<float2*>(e->tail[0][nxt]), e->S, n);
+                                                                   static_cast<float2*>(e->tail[0][nxt]), e->S, n, e->halo);
         CU_TRY(cudaGetLastError());
     }
     e->tail_cur = nxt;
@@ -546,18 +551,21 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     e->channels = 2 * e->S;
     e->P_max = (int)(cfg->max_block / nvx::kSuper);
     e->custom_taps = cfg->h1 || cfg->h2 || cfg->h3;
-    e->long_taps = cfg->n1 || cfg->n2 || cfg->n3;
+    // tap counts: reference lengths unless given; sets up to 37/47/71 and up to 61/75/111 run through the fused kernel
+    // (zero-padded to the class), longer ones through the long-tap path
+    const int n[3] = {cfg->n1 ? cfg->n1 : NVX_T1, cfg->n2 ? cfg->n2 : NVX_T2, cfg->n3 ? cfg->n3 : NVX_T3};
+    if ((cfg->n1 && !cfg->h1) || (cfg->n2 && !cfg->h2) || (cfg->n3 && !cfg->h3)) {
+        delete e;
+        return fail(NVX_ERR_ARG, "a tap count was given without its tap array");
+    }
+    for (int k = 0; k < 3; ++k)
+        if (n[k] < 1 || n[k] > nvx::kLongMaxTaps) { delete e; return fail(NVX_ERR_ARG, "tap count %d outside 1..%d", n[k], nvx::kLongMaxTaps); }
+    e->tap_class = nvx::cascade_tap_class(n[0], n[1], n[2]);
+    e->long_taps = e->tap_class < 0;
+    e->halo = nvx::kSuper * nvx::cascade_warm_super(e->tap_class);
     if (e->long_taps) {
-        const int n[3] = {cfg->n1 ? cfg->n1 : NVX_T1, cfg->n2 ? cfg->n2 : NVX_T2, cfg->n3 ? cfg->n3 : NVX_T3};
         const int D[3] = {NVX_D1, NVX_D2, NVX_D3};
-        if ((cfg->n1 && !cfg->h1) || (cfg->n2 && !cfg->h2) || (cfg->n3 && !cfg->h3)) {
-            delete e;
-            return fail(NVX_ERR_ARG, "a tap count was given without its tap array");
-        }
-        for (int k = 0; k < 3; ++k) {
-            if (n[k] < 1 || n[k] > nvx::kLongMaxTaps) { delete e; return fail(NVX_ERR_ARG, "tap count %d outside 1..%d", n[k], nvx::kLongMaxTaps); }
-            e->lst[k] = nvx::long_stage(D[k], n[k]);
-        }
+        for (int k = 0; k < 3; ++k) e->lst[k] = nvx::long_stage(D[k], n[k]);
     }
     // per block and channel: at most one character plus one abort per 14 bits ... generous bound
     e->ev_cap = 2 * (e->P_max / 63 + 2) + 8;
@@ -594,7 +602,7 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     }
     for (int f = 0; f < 2; ++f)
         for (int k = 0; k < 2; ++k)
-            CREATE_TRY(cudaMalloc(&e->tail[f][k], (size_t)e->S * nvx::kHalo * (f ? sizeof(short2) : sizeof(float2))));
+            CREATE_TRY(cudaMalloc(&e->tail[f][k], (size_t)e->S * e->halo * (f ? sizeof(short2) : sizeof(float2))));
     e->db.p_max = e->P_max;
     for (int k = 0; k < kBuf; ++k) CREATE_TRY(cudaMalloc(&e->y3buf[k], (size_t)e->channels * (nvx::kHistY + e->P_max) * sizeof(float2)));
     CREATE_TRY(cudaMalloc(&e->db.corr, (size_t)e->channels * (nvx::kHistC + e->P_max + nvx::kPadC) * sizeof(double)));
@@ -629,7 +637,7 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->channels * (cfg->max_block / NVX_D1) * sizeof(float2)));
         CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));
     } else {
-        CREATE_TRY(nvx::cascade_upload_constants(cfg->h1, cfg->h2, cfg->h3, e->stream));
+        CREATE_TRY(nvx::cascade_upload_constants(e->tap_class, cfg->h1, n[0], cfg->h2, n[1], cfg->h3, n[2], e->stream));
     }
     if (!nco.empty()) {
         CREATE_TRY(cudaMalloc(&e->d_nco, nco.size() * sizeof(nvx::NcoParam)));
@@ -638,8 +646,8 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
 #undef CREATE_TRY
     for (int f = 0; f < 2; ++f)
         for (int k = 0; k < 2; ++k)
-            if (int rc = encode_rows(&e->map_tail[f][k], e->tail[f][k], nvx::kHalo, e->S, f != 0)) { free_engine(e); return rc; }
-    for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels), f != 0);
+            if (int rc = encode_rows(&e->map_tail[f][k], e->tail[f][k], e->halo, e->S, f != 0)) { free_engine(e); return rc; }
+    for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels), f != 0, e->tap_class);
     e->assembler.resize(e->channels);
     if (int rc = reset_state(e)) { free_engine(e); return rc; }
     e->worker = std::thread(worker_main, e);

@@ -7,9 +7,11 @@
 
 namespace nvx {
 
-template <bool kImm, bool kGenNco, bool kS16>
-__global__ void __launch_bounds__(InFmt<kS16>::kWarps * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
-    using F = InFmt<kS16>;
+template <bool kImm, bool kGenNco, bool kS16, int kClass>
+__global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
+    using F = InFmt<kS16, kClass>;
+    using G = Geo<kClass>;
+    constexpr int kWarmSuper = G::kWarm, kHalo = G::kWarm * kSuper, kLive1 = G::kLive1, kLive2 = G::kLive2, kLive3 = G::kLive3;
     constexpr int kWarpsPerCta = F::kWarps;
     constexpr int kStages = F::kStages, kStageBytes = F::kStageBytes, kStepsPerStage = F::kSteps, kStageIn = F::kStageIn;
     constexpr int kRowBytes = F::kRowBytes, kStepBytes = F::kStepBytes, kEl = F::kElemsPerSample;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(InFmt<kS16>::kWarps * 32, kCtasPerSm) fir_casc
     for (int s = 0; s < kStages; ++s)
         if (s < warp_stages) issue(s, s);
 
-    CascadeState st;
+    CascadeState<kClass> st;
 #pragma unroll
     for (int j = 0; j < kLive1; ++j) st.a1[j] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(InFmt<kS16>::kWarps * 32, kCtasPerSm) fir_casc
                     if (nco_idx[c] >= kNcoDen) nco_idx[c] -= kNcoDen;
                 }
             }
-            cascade_step<kImm, kGenNco, kS16>(st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3, nl);
+            cascade_step<kImm, kGenNco, kS16, kClass>(st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3, nl);
             phase += 7;
             if (phase >= kNcoPeriod) phase -= kNcoPeriod;
         }
@@ -130,37 +132,55 @@ __global__ void __launch_bounds__(InFmt<kS16>::kWarps * 32, kCtasPerSm) fir_casc
     }
 }
 
-size_t cascade_smem_bytes(bool s16) { return s16 ? InFmt<true>::kSmemBytes : InFmt<false>::kSmemBytes; }
 int cascade_box_elems(bool s16) { return s16 ? InFmt<true>::kBoxElems : InFmt<false>::kBoxElems; }
 
-static void fill_constants(const double* h1, const double* h2, const double* h3, TapSet* t, NcoTable* n) {
+// pad a tap set with zeros at the old end up to the class length (a shorter FIR is the same FIR with zero taps)
+template <int kClass>
+static void fill_taps(const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, TapSet<kClass>* t) {
+    using G = Geo<kClass>;
+    for (int i = 0; i < G::T1 + 3; ++i) t->h1[i] = i < n1 ? (float)h1[i] : 0.f;
+    for (int i = 0; i < G::T2 + 1; ++i) t->h2[i] = i < n2 ? (float)h2[i] : 0.f;
+    for (int r = 0; r < NVX_D3; ++r)
+        for (int j = 0; j < (int)(sizeof t->h3t[0] / sizeof(float)); ++j) {
+            const int i = 10 * j + 9 - r;
+            t->h3t[r][j] = i < n3 ? (float)h3[i] : 0.f;
+        }
+}
+
+// tap class a set of lengths needs, or -1 if it takes the long-tap path
+int cascade_tap_class(int n1, int n2, int n3) {
+    if (n1 <= Geo<0>::T1 && n2 <= Geo<0>::T2 && n3 <= Geo<0>::T3) return 0;
+    if (n1 <= Geo<1>::T1 && n2 <= Geo<1>::T2 && n3 <= Geo<1>::T3) return 1;
+    return -1;
+}
+int cascade_warm_super(int tap_class) { return tap_class == 1 ? Geo<1>::kWarm : Geo<0>::kWarm; }
+
+cudaError_t cascade_upload_constants(int tap_class, const double* h1, int n1, const double* h2, int n2, const double* h3, int n3,
+                                     cudaStream_t stream) {
     static const double d1[NVX_T1] = {NVX_H1_VALUES};
     static const double d2[NVX_T2] = {NVX_H2_VALUES};
     static const double d3[NVX_T3] = {NVX_H3_VALUES};
-    if (!h1) h1 = d1;
-    if (!h2) h2 = d2;
-    if (!h3) h3 = d3;
-    for (int i = 0; i < NVX_T1; ++i) t->h1[i] = (float)h1[i];
-    for (int i = 0; i < NVX_T2; ++i) t->h2[i] = (float)h2[i];
-    for (int r = 0; r < NVX_D3; ++r)
-        for (int j = 0; j < 8; ++j) {
-            const int i = 10 * j + 9 - r;
-            t->h3t[r][j] = i < NVX_T3 ? (float)h3[i] : 0.f;
-        }
+    if (!h1) { h1 = d1; n1 = NVX_T1; }
+    if (!h2) { h2 = d2; n2 = NVX_T2; }
+    if (!h3) { h3 = d3; n3 = NVX_T3; }
+    cudaError_t e;
+    if (tap_class == 1) {
+        TapSet<1> t = {};
+        fill_taps<1>(h1, n1, h2, n2, h3, n3, &t);
+        e = cudaMemcpyToSymbolAsync(c_taps1, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
+    } else {
+        TapSet<0> t = {};
+        fill_taps<0>(h1, n1, h2, n2, h3, n3, &t);
+        e = cudaMemcpyToSymbolAsync(c_taps0, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
+    }
+    if (e != cudaSuccess) return e;
+    NcoTable n = {};
     for (int i = 0; i < kNcoPeriod + NVX_D2; ++i) {
         const int k = i % kNcoPeriod;
         // same expression as fir2cpp.C:105-106, rounded once to float
-        n->w[i].x = (float)cos((2 * M_PI * k * 14000) / 63000);
-        n->w[i].y = (float)-sin((2 * M_PI * k * 14000) / 63000);
+        n.w[i].x = (float)cos((2 * M_PI * k * 14000) / 63000);
+        n.w[i].y = (float)-sin((2 * M_PI * k * 14000) / 63000);
     }
-}
-
-cudaError_t cascade_upload_constants(const double* h1, const double* h2, const double* h3, cudaStream_t stream) {
-    TapSet t = {};
-    NcoTable n = {};
-    fill_constants(h1, h2, h3, &t, &n);
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_taps, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbolAsync(c_nco, &n, sizeof n, 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(stream);
@@ -168,44 +188,48 @@ cudaError_t cascade_upload_constants(const double* h1, const double* h2, const d
 
 // warps that are resident at once across the device, leaving `reserved_sms` SMs to the sequential demod kernels:
 // the host sizes the grid to at most one full wave
-template <bool kS16>
+template <bool kS16, int kClass>
 static int target_warps_fmt(int device, int reserved_sms) {
+    using F = InFmt<kS16, kClass>;
     int sms = 148, per_sm = kCtasPerSm;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    auto kern = fir_cascade_kernel<true, false, kS16>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, InFmt<kS16>::kSmemBytes);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, InFmt<kS16>::kWarps * 32, InFmt<kS16>::kSmemBytes) != cudaSuccess ||
-        per_sm < 1)
+    auto kern = fir_cascade_kernel<false, false, kS16, kClass>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::kSmemBytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, F::kWarps * 32, F::kSmemBytes) != cudaSuccess || per_sm < 1)
         per_sm = kCtasPerSm;
     if (sms - reserved_sms >= 8) sms -= reserved_sms;
-    return sms * per_sm * InFmt<kS16>::kWarps;
+    return sms * per_sm * F::kWarps;
 }
-int cascade_target_warps(int device, int reserved_sms, bool s16) {
-    return s16 ? target_warps_fmt<true>(device, reserved_sms) : target_warps_fmt<false>(device, reserved_sms);
+int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class) {
+    if (tap_class == 1) return s16 ? target_warps_fmt<true, 1>(device, reserved_sms) : target_warps_fmt<false, 1>(device, reserved_sms);
+    return s16 ? target_warps_fmt<true, 0>(device, reserved_sms) : target_warps_fmt<false, 0>(device, reserved_sms);
 }
 
-template <bool kS16>
+template <bool kS16, int kClass>
 static cudaError_t launch_fmt(const CascadeArgs& a, bool custom_taps, cudaStream_t stream) {
     static bool attr_set[4] = {false, false, false, false};
-    const size_t smem = InFmt<kS16>::kSmemBytes;
+    const size_t smem = InFmt<kS16, kClass>::kSmemBytes;
     const bool gen = a.nco != nullptr;
-    auto kern = gen ? (custom_taps ? fir_cascade_kernel<false, true, kS16> : fir_cascade_kernel<true, true, kS16>)
-                    : (custom_taps ? fir_cascade_kernel<false, false, kS16> : fir_cascade_kernel<true, false, kS16>);
-    const int which = (gen ? 2 : 0) + (custom_taps ? 1 : 0);
+    // immediates only for the reference taps themselves; every other set (class 0 or 1) reads the constant bank
+    constexpr bool kCanImm = kClass == 0;
+    auto kern = gen ? ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, true, kS16, kClass> : fir_cascade_kernel<kCanImm, true, kS16, kClass>)
+                    : ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, false, kS16, kClass> : fir_cascade_kernel<kCanImm, false, kS16, kClass>);
+    const int which = (gen ? 2 : 0) + ((custom_taps || !kCanImm) ? 1 : 0);
     if (!attr_set[which]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set[which] = true;
     }
-    constexpr int kWarpsPerCta = InFmt<kS16>::kWarps;
+    constexpr int kWarpsPerCta = InFmt<kS16, kClass>::kWarps;
     const long long warps = (long long)((a.streams + 31) / 32) * a.segs;
     const unsigned grid = (unsigned)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
     kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t cascade_launch(const CascadeArgs& a, bool custom_taps, bool s16, cudaStream_t stream) {
-    return s16 ? launch_fmt<true>(a, custom_taps, stream) : launch_fmt<false>(a, custom_taps, stream);
+cudaError_t cascade_launch(const CascadeArgs& a, int tap_class, bool custom_taps, bool s16, cudaStream_t stream) {
+    if (tap_class == 1) return s16 ? launch_fmt<true, 1>(a, true, stream) : launch_fmt<false, 1>(a, true, stream);
+    return s16 ? launch_fmt<true, 0>(a, custom_taps, stream) : launch_fmt<false, 0>(a, custom_taps, stream);
 }
 
 }  // namespace nvx

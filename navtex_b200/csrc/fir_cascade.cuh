@@ -39,8 +39,8 @@ namespace nvx {
 constexpr int kSuper = NVX_D1 * NVX_D2 * NVX_D3;   // 280 inputs per 900 Hz output
 constexpr int kStepIn = NVX_D1 * NVX_D2;           // 28 inputs per 9 kHz output ("step")
 constexpr int kStepsPerSuper = NVX_D3;             // 10
-constexpr int kWarmSuper = 7;                      // ceil(1901 / 280)
-constexpr int kHalo = kWarmSuper * kSuper;         // 1960 carried input samples per stream
+// warm-up superblocks / carried input samples per stream are per tap-length class: Geo<>::kWarm (7 -> 1960 samples for the
+// reference lengths: ceil(1901 / 280))
 constexpr int kNcoPeriod = 9;                      // fir2cpp.C:12-14
 // Tunables (see DESIGN.md "input staging"): how many 28-sample steps one TMA box carries per stream row, how many
 // extra floats pad each row in shared memory (bank-conflict control), ring depth and CTA shape.  Measured on B200
@@ -84,7 +84,7 @@ constexpr int kCtasPerSm = NVX_CTAS_PER_SM;
 // instruction fetch from L2 is not hidden (measured: 5 steps per stage = 5.3 ms, 2 steps = 3.3 ms per block).  Being
 // issue-bound it also wants more warps per sub-partition: 12 warps x 2 stages = 2.77 ms, 8 x 3 = 2.90 ms, 16 x 1 = 2.81 ms,
 // 4 warps x 6 stages = 3.27 ms.
-template <bool kS16>
+template <bool kS16, int kClass = 0>
 struct InFmt {
     static constexpr int kSteps = kS16 ? NVX_S16_STEPS_PER_STAGE : NVX_STEPS_PER_STAGE;   // 28-sample steps per TMA box row
     static constexpr int kSampleBytes = kS16 ? 4 : 8;
@@ -94,25 +94,44 @@ struct InFmt {
     static constexpr int kBoxElems = kRowBytes / 4;                                       // TMA box width in 32-bit elements (pad over-fetched)
     static constexpr int kElemsPerSample = kSampleBytes / 4;
     static constexpr int kStageBytes = 32 * kRowBytes;                                    // per warp per stage
-    static constexpr int kStages = kS16 ? NVX_S16_STAGES : NVX_STAGES;
-    static constexpr int kWarps = kS16 ? NVX_S16_WARPS_PER_CTA : NVX_WARPS_PER_CTA;      // per CTA
+    // the medium tap class needs ~250 registers per thread: 4 warps per CTA for either format
+    static constexpr int kStages = kS16 ? (kClass == 0 ? NVX_S16_STAGES : 6) : NVX_STAGES;
+    static constexpr int kWarps = kS16 ? (kClass == 0 ? NVX_S16_WARPS_PER_CTA : 4) : NVX_WARPS_PER_CTA;      // per CTA
     static constexpr int kSmemBytes = kWarps * kStages * kStageBytes + kWarps * kStages * 8;
     static_assert(kStepsPerSuper % kSteps == 0, "a stage must not straddle superblocks");
     static_assert(kRowBytes % 16 == 0 && kStageBytes % 128 == 0 && kBoxElems <= 256, "TMA box alignment");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
-constexpr int kLive1 = 9, kLive2 = 6, kLive3 = 8;  // partial sums carried between steps
+// Tap-length classes of the fused kernel.  Class 0 = the reference lengths 37 / 47 / 71 (taps may be immediates); class 1 =
+// "medium" replacement sets up to 61 / 75 / 111 taps (1.6x the reference: ~83 flop per input sample, which is where the
+// kernel turns from HBM-bound to FP32-bound).  Shorter sets are zero-padded at the old end; longer ones take the long-tap
+// path (fir_long.cu).  Everything the kernel needs follows from the three lengths:
+template <int kClass> struct TapClass;
+template <> struct TapClass<0> { static constexpr int T1 = NVX_T1, T2 = NVX_T2, T3 = NVX_T3; };
+template <> struct TapClass<1> { static constexpr int T1 = 61, T2 = 75, T3 = 111; };
+constexpr int kTapClasses = 2;
+template <int kClass>
+struct Geo {
+    static constexpr int T1 = TapClass<kClass>::T1, T2 = TapClass<kClass>::T2, T3 = TapClass<kClass>::T3;
+    // partial sums carried between 28-sample steps (transposed form): outputs still waiting for newer samples
+    static constexpr int kLive1 = (T1 - 1) / NVX_D1, kLive2 = (T2 - 1) / NVX_D2, kLive3 = (T3 - 1) / NVX_D3 + 1;
+    // a 900 Hz output depends on (T3 - 1) 28 + (T2 - 1) 4 + T1 input samples, 280 of them in its own superblock
+    static constexpr int kWarm = ((T3 - 1) * kStepIn + (T2 - 1) * NVX_D1 + T1 - kSuper + kSuper - 1) / kSuper;
+};
+static_assert(Geo<0>::kLive1 == 9 && Geo<0>::kLive2 == 6 && Geo<0>::kLive3 == 8 && Geo<0>::kWarm == 7, "reference geometry");
+constexpr int kMaxWarm = Geo<kTapClasses - 1>::kWarm;
 
 __device__ constexpr double kH1[NVX_T1] = {NVX_H1_VALUES};
 __device__ constexpr double kH2[NVX_T2] = {NVX_H2_VALUES};
 
-// runtime tap sets of the reference lengths (constant bank, uniform operands)
+// runtime tap sets (constant bank, uniform operands), zero-padded to the class lengths
+template <int kClass>
 struct TapSet {
-    float h1[NVX_T1 + 3];
-    float h2[NVX_T2 + 1];
-    // stage-3 taps regrouped per step position: h3t[r][j] = h3[10 j + 9 - r] (0 where that index is > 70),
-    // so the 8 taps one step needs are two aligned 16-byte uniform loads
-    float h3t[NVX_D3][8];
+    float h1[Geo<kClass>::T1 + 3];
+    float h2[Geo<kClass>::T2 + 1];
+    // stage-3 taps regrouped per step position: h3t[r][j] = h3[10 j + 9 - r] (0 where that index is beyond the set),
+    // so the taps one step needs are a few aligned 16-byte uniform loads
+    float h3t[NVX_D3][(Geo<kClass>::kLive3 + 3) / 4 * 4];
 };
 // (cos, -sin) of 2 pi k 14000 / 63000, k = 0..8, repeated so that [phase + q], q < 7 needs no wrap
 struct NcoTable { float2 w[kNcoPeriod + NVX_D2]; };
@@ -129,7 +148,7 @@ struct NcoParam {
 
 struct CascadeArgs {
     CUtensorMap map_x;    // 32-bit view [S][2 n] (float2 input) or [S][n] (short2 input) of this chunk, box InFmt::kBoxElems x 32
-    CUtensorMap map_tail; // same view of [S][kHalo]: the kHalo samples that preceded the chunk (zeros at start)
+    CUtensorMap map_tail; // same view of [S][halo]: the halo = 280 kWarm samples that preceded the chunk (zeros at start)
     float2* y3;           // [S][2][y3_pitch] 900 Hz output; this chunk's samples start at y3_off
     long long n;          // samples per stream in this chunk (multiple of kSuper)
     int streams;
@@ -144,8 +163,12 @@ struct CascadeArgs {
 };
 
 #ifdef NVX_CASCADE_DEVICE_CODE
-__constant__ TapSet c_taps;
+__constant__ TapSet<0> c_taps0;
+__constant__ TapSet<1> c_taps1;
 __constant__ NcoTable c_nco;
+template <int kClass> __device__ __forceinline__ const TapSet<kClass>& class_taps();
+template <> __device__ __forceinline__ const TapSet<0>& class_taps<0>() { return c_taps0; }
+template <> __device__ __forceinline__ const TapSet<1>& class_taps<1>() { return c_taps1; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -172,15 +195,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-template <bool kImm> __device__ __forceinline__ float tap1(int i) { return kImm ? (float)kH1[i] : c_taps.h1[i]; }
-template <bool kImm> __device__ __forceinline__ float tap2(int i) { return kImm ? (float)kH2[i] : c_taps.h2[i]; }
+template <bool kImm, int kClass> __device__ __forceinline__ float tap1(int i) { return kImm ? (float)kH1[i] : class_taps<kClass>().h1[i]; }
+template <bool kImm, int kClass> __device__ __forceinline__ float tap2(int i) { return kImm ? (float)kH2[i] : class_taps<kClass>().h2[i]; }
 
 __device__ __forceinline__ float2 fma2(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
 
+template <int kClass>
 struct CascadeState {
-    float2 a1[kLive1];
-    float2 a2[2][kLive2];
-    float2 a3[2][kLive3];
+    float2 a1[Geo<kClass>::kLive1];
+    float2 a2[2][Geo<kClass>::kLive2];
+    float2 a3[2][Geo<kClass>::kLive3];
 };
 
 // One step: 28 inputs of one row -> 7 stage-1 outputs -> mix -> one stage-2 output per channel ->
@@ -201,9 +225,12 @@ __device__ __forceinline__ float2 iq_of(int packed) {
     return __fadd2_rn(biased, make_float2(-8421376.0f, -8421376.0f));
 }
 
-template <bool kImm, bool kGenNco, bool kS16>
-__device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __restrict__ row, int nco_phase,
+template <bool kImm, bool kGenNco, bool kS16, int kClass>
+__device__ __forceinline__ void cascade_step(CascadeState<kClass>& st, const float4* __restrict__ row, int nco_phase,
                                              const int r10, float2 (&y3)[2], NcoLane& nl) {
+    using G = Geo<kClass>;
+    constexpr int kLive1 = G::kLive1, kLive2 = G::kLive2, kLive3 = G::kLive3;
+    static_assert(!kImm || kClass == 0, "immediate taps are the reference set");
     float2 w[kLive1 + NVX_D2];
 #pragma unroll
     for (int j = 0; j < kLive1; ++j) w[j] = st.a1[j];
@@ -233,7 +260,7 @@ __device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __r
 #pragma unroll
         for (int r = 0; r < NVX_D1; ++r) {
 #pragma unroll
-            for (int j = 0; 4 * j + 3 - r < NVX_T1; ++j) w[q + j] = fma2(xs[r], tap1<kImm>(4 * j + 3 - r), w[q + j]);
+            for (int j = 0; 4 * j + 3 - r < G::T1; ++j) w[q + j] = fma2(xs[r], tap1<kImm, kClass>(4 * j + 3 - r), w[q + j]);
         }
         const float2 y1 = w[q];
         // NCO mix (fir2cpp.C:115-124): ch0 = y1 * (re + j im), ch1 = y1 * (re - j im), (re, im) = (cos, -sin)
@@ -255,7 +282,7 @@ __device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __r
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
-            for (int j = 0; 7 * j + 6 - q < NVX_T2; ++j) b[c][j] = fma2(m[c], tap2<kImm>(7 * j + 6 - q), b[c][j]);
+            for (int j = 0; 7 * j + 6 - q < G::T2; ++j) b[c][j] = fma2(m[c], tap2<kImm, kClass>(7 * j + 6 - q), b[c][j]);
         }
     }
 #pragma unroll
@@ -266,10 +293,10 @@ __device__ __forceinline__ void cascade_step(CascadeState& st, const float4* __r
         const float2 y2 = b[c][0];
 #pragma unroll
         for (int j = 0; j < kLive2; ++j) st.a2[c][j] = b[c][j + 1];
-        // stage 3: sample 10p + r10 feeds outputs p + j with tap 10 j + 9 - r10 (table row r10; j = 7 only
-        // carries a non-zero tap when r10 == 9)
+        // stage 3: sample 10p + r10 feeds outputs p + j with tap 10 j + 9 - r10 (table row r10; the last j only
+        // carries a non-zero tap for the largest r10)
 #pragma unroll
-        for (int j = 0; j < kLive3; ++j) st.a3[c][j] = fma2(y2, c_taps.h3t[r10][j], st.a3[c][j]);
+        for (int j = 0; j < kLive3; ++j) st.a3[c][j] = fma2(y2, class_taps<kClass>().h3t[r10][j], st.a3[c][j]);
     }
     if (r10 == NVX_D3 - 1) {
 #pragma unroll

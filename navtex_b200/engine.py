@@ -148,8 +148,8 @@ class Engine:
         if taps is not None:
             self._taps = [np.ascontiguousarray(t, dtype=np.float64) for t in taps]
             cfg.h1, cfg.h2, cfg.h3 = (t.ctypes.data_as(C.POINTER(C.c_double)) for t in self._taps)
-            if [len(t) for t in self._taps] != [37, 47, 71]:       # other lengths: the long-tap path
-                cfg.n1, cfg.n2, cfg.n3 = (len(t) for t in self._taps)
+            # up to 37/47/71 and up to 61/75/111 taps: fused kernel (zero-padded); longer: the long-tap path
+            cfg.n1, cfg.n2, cfg.n3 = (len(t) for t in self._taps)
         if nco_hz is not None:           # [S, 2] per-stream channel offsets in Hz
             self._nco = np.ascontiguousarray(nco_hz, dtype=np.float64).reshape(n_streams, 2)
             cfg.nco_hz = self._nco.ctypes.data_as(C.POINTER(C.c_double))

@@ -27,7 +27,9 @@ def _capture(text, offset, seconds, snr, seed):
     return synth.quantise_s16(synth.fsk_iq([em], seconds, snr_db=snr, seed=seed))
 
 
-@pytest.mark.parametrize("lengths", [(255, 255, 255), (101, 383, 129), (37, 47, 500)])
+# (255, ...), (101, ...), (37, 47, 500): long-tap path; (61, 75, 111), (45, 47, 90): the fused kernel's medium class;
+# (21, 31, 51): shorter than the reference, zero-padded into the reference class
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (101, 383, 129), (37, 47, 500), (61, 75, 111), (45, 47, 90), (21, 31, 51)])
 def test_long_taps_against_restated_oracle(lengths):
     taps = designs(*lengths)
     seconds = 11.0
@@ -59,9 +61,11 @@ def test_long_taps_against_restated_oracle(lengths):
     eng.close()
 
 
-def test_long_taps_blocking_and_format_invariance():
-    """Histories are carried per stage: any blocking, float or int16 input, gives bit-identical 900 Hz samples."""
-    taps = designs(255, 255, 255)
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (61, 75, 111)])
+def test_long_taps_blocking_and_format_invariance(lengths):
+    """Histories are carried per stage (long path) / recomputed from a longer input tail (medium class): any blocking,
+    float or int16 input, gives bit-identical 900 Hz samples."""
+    taps = designs(*lengths)
     n = 252000 * 2
     rng = np.random.default_rng(23)
     x = np.rint(rng.normal(0, 3000, size=(2, n, 2))).astype(np.int16)
