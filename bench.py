@@ -417,6 +417,8 @@ def main():
         "ms_per_step": float(t16.item()) / k16, "kernel": "nvx::fir_cascade_kernel<true,false,true> (short2 rows by TMA, PRMT/FADD2 conversion)",
         "kernel_ms": casc16_ms, "algorithmic_bytes_per_sample": 4.0 + 16.0 / 280,
         "achieved_gbs": S * BLOCK * (4.0 + 16.0 / 280) / (casc16_ms * 1e-3) / 1e9, "bound": "fp32 issue (not HBM)",
+        # 55.5 algorithmic flop per input sample against 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.5 TFLOP/s
+        "fp32_tflops": S * BLOCK * 55.5 / (casc16_ms * 1e-3) / 1e12, "fp32_frac_of_peak": S * BLOCK * 55.5 / (casc16_ms * 1e-3) / 74.5e12,
         "decoded_exact": sum(1 for e in expect if e in got16),
     }
     eng16.close()
