@@ -503,8 +503,7 @@ int demod_reserved_sms(int channels) {
 }
 
 cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t stream) {
-    static bool tables_done = false;
-    if (!tables_done) {
+    {   // constant-bank tables are per device: (re)loaded with every engine create / reset
         // CCIR 476 tables as (code, letters, figures); see nav_b_sm.h:60-83 -- every other code is invalid '_'.
         static const struct { unsigned char code; char l, f; } codes[] = {
             {0x07, 'p', 'p'}, {0x0b, 'J', 'b'}, {0x0d, 'W', '2'}, {0x0e, 'A', '-'}, {0x13, 'F', '*'},
@@ -534,7 +533,6 @@ cudaError_t demod_init_state(const DemodBuffers& b, int channels, cudaStream_t s
         for (int i = 0; i < 5; ++i) { trd[i] = tr[i]; tid[i] = ti[i]; }
         if ((e = cudaMemcpyToSymbol(c_tone_rd, trd, sizeof trd)) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbol(c_tone_id, tid, sizeof tid)) != cudaSuccess) return e;
-        tables_done = true;
     }
     cudaError_t e;
     if ((e = cudaMemsetAsync(b.y3, 0, sizeof(float2) * (size_t)channels * (kHistY + b.p_max), stream)) != cudaSuccess) return e;
@@ -569,12 +567,10 @@ cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_s
         if (e != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(s_seq, ff_done, 0)) != cudaSuccess) return e;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    {   // per device, and a few hundred nanoseconds: not cached
         cudaError_t e = cudaFuncSetAttribute(symbol_clock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const unsigned seq_ctas = (a.channels + kSeqWarps * 32 - 1) / (kSeqWarps * 32);
     mark(4, s_seq);

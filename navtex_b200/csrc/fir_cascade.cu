@@ -207,18 +207,15 @@ int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class) 
 
 template <bool kS16, int kClass>
 static cudaError_t launch_fmt(const CascadeArgs& a, bool custom_taps, cudaStream_t stream) {
-    static bool attr_set[4] = {false, false, false, false};
     const size_t smem = InFmt<kS16, kClass>::kSmemBytes;
     const bool gen = a.nco != nullptr;
     // immediates only for the reference taps themselves; every other set (class 0 or 1) reads the constant bank
     constexpr bool kCanImm = kClass == 0;
     auto kern = gen ? ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, true, kS16, kClass> : fir_cascade_kernel<kCanImm, true, kS16, kClass>)
                     : ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, false, kS16, kClass> : fir_cascade_kernel<kCanImm, false, kS16, kClass>);
-    const int which = (gen ? 2 : 0) + ((custom_taps || !kCanImm) ? 1 : 0);
-    if (!attr_set[which]) {
+    {   // function attributes are per device: set on every launch (cheap) rather than cached process-wide
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set[which] = true;
     }
     constexpr int kWarpsPerCta = InFmt<kS16, kClass>::kWarps;
     const long long warps = (long long)((a.streams + 31) / 32) * a.segs;

@@ -172,11 +172,9 @@ template <int D, int STAGE>
 cudaError_t launch_one(const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream) {
     const int F = D * (kLongTile + st.J - 1);
     const size_t smem = (size_t)(F + F / (kLongR * D) + 2) * sizeof(float2);
-    static size_t attr = 0;
-    if (smem > attr) {
+    {   // per device: not cached
         cudaError_t e = cudaFuncSetAttribute(fir_long_kernel<D, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr = smem;
     }
     const long long n_out = a.n_in / D;
     fir_long_kernel<D, STAGE><<<dim3((unsigned)((n_out + kLongTile - 1) / kLongTile), (unsigned)a.rows_in), kLongThreads, smem, stream>>>(

@@ -132,3 +132,23 @@ def test_c_and_relinked_hosts(tmp_path):
     assert out.stdout == want
     out = subprocess.run([build_example("relink_host.cpp", tmp_path), raw], capture_output=True, text=True, check=True)
     assert out.stdout == want
+
+
+def test_two_engines_on_two_devices_in_one_process():
+    """One process, one engine per GPU: function attributes and constant-bank tables are per device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    iq = cases.build("clean518")
+    n = iq.size // 2 // 280 * 280
+    x = np.ascontiguousarray(iq[: 2 * n].reshape(1, n, 2))
+    engs = [engine.Engine(1, n, device=d, first_stream_id=10 * d) for d in (0, 1)]
+    for e in engs:
+        e.push_host(x)
+    got = [e.poll_messages() for e in engs]
+    assert [m[1:] for m in got[0]] == [m[1:] for m in got[1]] and len(got[0]) == 1
+    assert got[0][0][0] == 0 and got[1][0][0] == 10
+    assert np.array_equal(engs[0].read_y3().view(np.uint64), engs[1].read_y3().view(np.uint64))
+    for e in engs:
+        e.close()
