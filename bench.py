@@ -105,6 +105,31 @@ class ClockSampler:
                 "samples": len(inside), "reasons": reasons}
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and so its pinned host buffers: first touch) on the CPUs of the NUMA node its GPU hangs off.
+    Matters for the e2e arm at N > 1, where every GPU pulls 55 GB/s out of host memory.  No-op when the topology is not
+    visible (containers without sysfs NUMA info)."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.startswith("0000"):
+            bdf = bdf[4:]                      # nvidia-smi prints an 8-digit domain, sysfs uses 4
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        use = cpus & os.sched_getaffinity(0)
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return node, len(use)
+    except Exception:
+        return None
+
+
 def build_workload(torch, device, rank):
     """1024 distinct synthetic captures for this rank, generated on the device (untimed)."""
     import numpy as np
@@ -322,6 +347,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU chain)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -469,7 +495,8 @@ def main():
     e2e_exact = sum(1 for m in e2e_msgs if (m[0], m[1], m[2], m[3]) in expect_set)
     e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * ne * 4, "d2h_bytes_per_step": 2 * S * (ev_cap + 4),
            "input": f"int16 IQ in pinned host memory, [{S} streams][{ne} samples] per step, consecutive blocks of the same captures",
-           "ms_per_step": float(te.item()) * 1e3 / args.steps}
+           "ms_per_step": float(te.item()) * 1e3 / args.steps,
+           "numa_binding": ("node %d, %d cpus" % numa) if numa else None}
     e2e_eng.close()
 
     if rank != 0:
