@@ -85,8 +85,9 @@ def test_long_taps_blocking_and_format_invariance(lengths):
         assert np.array_equal(y.view(np.uint64), ref[:, :, : y.shape[2]].view(np.uint64)), blk
 
 
-def test_long_taps_with_per_stream_nco():
-    taps = designs(255, 255, 255)
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (61, 75, 111)])
+def test_long_taps_with_per_stream_nco(lengths):
+    taps = designs(*lengths)
     seconds = 11.0
     n = int(seconds * 252000)
     rng = np.random.default_rng(25)
