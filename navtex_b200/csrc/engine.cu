@@ -142,6 +142,7 @@ struct nvx_engine {
     float2* lhist[3][2] = {};             // [stage][ping-pong]: [rows][H]
     float2 *y1buf = nullptr, *y2buf = nullptr;
     int lcur = 0;
+    nvx::LongTcStage* ltc[2] = {nullptr, nullptr};   // tensor-core variants of stages 1 and 2 (null: CUDA-core kernel)
     std::vector<int> stream_tag;          // optional [S][2] message tags
     bool serial = false;                  // NVX_PIPELINE=serial: the next cascade waits for this block's whole demod
     bool ff_on_main = true;               // feed-forward demod kernels follow the cascade on the main stream
@@ -196,6 +197,7 @@ int free_engine(nvx_engine* e) {
     cudaFree(e->d_nco);
     for (int k = 0; k < 3; ++k) { cudaFree(e->lhist[k][0]); cudaFree(e->lhist[k][1]); }
     cudaFree(e->y1buf); cudaFree(e->y2buf);
+    nvx::long_tc_free(e->ltc[0]); nvx::long_tc_free(e->ltc[1]);
     for (int k = 0; k < kBuf; ++k) {
         cudaFree(e->y3buf[k]); cudaFree(e->d_events[k]); cudaFree(e->d_ev_count[k]);
         cudaFreeHost(e->h_events[k]); cudaFreeHost(e->h_ev_count[k]);
@@ -401,11 +403,13 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         LongArgs la = {};
         la.in = d_x; la.hist = e->lhist[0][cur]; la.out = e->y1buf; la.n_in = n; la.out_pitch = p1; la.out_off = 0;
         la.rows_in = e->S; la.stage = 0; la.s16 = s16; la.k_abs = e->sb_abs * (kSuper / NVX_D1); la.nco = e->d_nco;
-        CU_TRY(long_launch(la, e->lst[0], n, e->stream));                 // 252 k -> 63 k, mixed: one row per channel
+        CU_TRY(e->ltc[0] ? long_tc_launch(e->ltc[0], la, e->lst[0], n, e->stream)
+                         : long_launch(la, e->lst[0], n, e->stream));  // 252 k -> 63 k, mixed: one row per channel
         CU_TRY(long_carry(e->lhist[0][cur], d_x, n, e->lhist[0][nx], e->S, e->lst[0].H, n, s16, e->stream));
         la.in = e->y1buf; la.hist = e->lhist[1][cur]; la.out = e->y2buf; la.n_in = n / NVX_D1; la.out_pitch = p2;
         la.rows_in = e->channels; la.stage = 1; la.s16 = 0; la.nco = nullptr;
-        CU_TRY(long_launch(la, e->lst[1], p1, e->stream));                // 63 k -> 9 k
+        CU_TRY(e->ltc[1] ? long_tc_launch(e->ltc[1], la, e->lst[1], p1, e->stream)
+                         : long_launch(la, e->lst[1], p1, e->stream));  // 63 k -> 9 k
         CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->channels, e->lst[1].H, n / NVX_D1, 0, e->stream));
         la.in = e->y2buf; la.hist = e->lhist[2][cur]; la.out = e->y3buf[b]; la.n_in = n / (NVX_D1 * NVX_D2);
         la.out_pitch = ca.y3_pitch; la.out_off = ca.y3_off; la.stage = 2;
@@ -634,6 +638,9 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         for (int k = 0; k < 3; ++k)
             for (int q = 0; q < 2; ++q)
                 CREATE_TRY(cudaMalloc(&e->lhist[k][q], (size_t)(k == 0 ? e->S : e->channels) * e->lst[k].H * sizeof(float2)));
+        // NVX_LONG_TC=1: stage 1 on the tensor cores (fir_long_tc.cu; opt-in while it trails the CUDA-core kernel at <= 255 taps)
+        if (getenv("NVX_LONG_TC") && atoi(getenv("NVX_LONG_TC")) & 1)
+            e->ltc[0] = nvx::long_tc_prepare(NVX_D1, e->lst[0].T, cfg->h1 ? cfg->h1 : d1, e->stream);
         CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->channels * (cfg->max_block / NVX_D1) * sizeof(float2)));
         CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));
     } else {

@@ -56,4 +56,11 @@ cudaError_t long_launch(const LongArgs& a, const LongStage& st, long long in_pit
 cudaError_t long_carry(const float2* old_hist, const void* block, long long pitch, float2* new_hist, int rows, int H, long long n,
                        int s16, cudaStream_t stream);
 
+// ---- tensor-core variant of stages 1 and 2 (fir_long_tc.cu): tcgen05 3xTF32 Toeplitz GEMM, same contract as long_launch ----
+struct LongTcStage;
+// builds the Toeplitz operand of one stage (D = 4 or 7, T taps) on the device; nullptr when the stage does not fit the kernel
+LongTcStage* long_tc_prepare(int D, int T, const double* h, cudaStream_t stream);
+void long_tc_free(LongTcStage* s);
+cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream);
+
 }  // namespace nvx

@@ -3,6 +3,8 @@ than fir1cpp.C:8 / fir2cpp.C:22 / fir3cpp.h:16) through the long-tap path (one r
 
 The unmodified reference cannot run other tap sets, so parity is against the C restatement of the three stages
 (oracle/navtex_oracle.c, h1/h2/h3 parameters), which is pinned to the compiled reference at the default taps."""
+import os
+
 import numpy as np
 import pytest
 from scipy import signal
@@ -59,6 +61,42 @@ def test_long_taps_against_restated_oracle(lengths):
         assert o.messages == [want[s]]
         assert [m[1:] for m in msgs if m[0] == s] == [want[s]]
     eng.close()
+
+
+@pytest.fixture
+def tensor_core_stage1(monkeypatch):
+    """Stage 1 of the long-tap path on the tensor cores (fir_long_tc.cu; the engine reads NVX_LONG_TC when it is created)."""
+    monkeypatch.setenv("NVX_LONG_TC", "1")
+
+
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (127, 255, 90), (511, 255, 255)])
+def test_long_taps_tensor_core_stage1(tensor_core_stage1, lengths):
+    """tcgen05 3xTF32 Toeplitz GEMM for stage 1: same 1e-5 bar, bits and messages against the restated oracle; int16 input
+    and a ragged stream count (3 of a 128-row tile) go through the general loader, float input through the fast one."""
+    test_long_taps_against_restated_oracle(lengths)
+    taps = designs(*lengths)
+    n = 252000 * 2
+    rng = np.random.default_rng(27)
+    x = np.rint(rng.normal(0, 3000, size=(130, n, 2))).astype(np.float32)
+    ref = engine.Engine(130, n, taps=taps)
+    ref.push_host(x)
+    want = ref.read_y3()
+    ref.close()
+    scale = np.abs(want).max()
+    for blk in (280 * 333, 2520 * 40):            # blockings move the tile boundaries: equal to rounding, not bit for bit
+        eng = engine.Engine(130, blk, taps=taps)
+        ys = []
+        for a in range(0, n // blk * blk, blk):
+            eng.push_host(np.ascontiguousarray(x[:, a:a + blk]))
+            ys.append(eng.read_y3())
+        eng.close()
+        y = np.concatenate(ys, axis=2)
+        assert np.abs(y - want[:, :, : y.shape[2]]).max() <= REL_TOL * scale, blk
+    os.environ["NVX_LONG_TC"] = "0"               # and against the CUDA-core stage 1 on the same input
+    cc = engine.Engine(130, n, taps=taps)
+    cc.push_host(x)
+    assert np.abs(cc.read_y3() - want).max() <= REL_TOL * scale
+    cc.close()
 
 
 @pytest.mark.parametrize("lengths", [(255, 255, 255), (61, 75, 111)])
