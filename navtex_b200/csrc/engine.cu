@@ -403,8 +403,9 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         LongArgs la = {};
         la.in = d_x; la.hist = e->lhist[0][cur]; la.out = e->y1buf; la.n_in = n; la.out_pitch = p1; la.out_off = 0;
         la.rows_in = e->S; la.stage = 0; la.s16 = s16; la.k_abs = e->sb_abs * (kSuper / NVX_D1); la.nco = e->d_nco;
-        CU_TRY(e->ltc[0] ? long_tc_launch(e->ltc[0], la, e->lst[0], n, e->stream)
-                         : long_launch(la, e->lst[0], n, e->stream));  // 252 k -> 63 k, mixed: one row per channel
+        cudaError_t tc = e->ltc[0] ? long_tc_launch(e->ltc[0], la, e->lst[0], n, e->stream) : cudaErrorNotSupported;
+        if (tc == cudaErrorNotSupported) tc = long_launch(la, e->lst[0], n, e->stream);   // 252 k -> 63 k, mixed: one row per channel
+        CU_TRY(tc);
         CU_TRY(long_carry(e->lhist[0][cur], d_x, n, e->lhist[0][nx], e->S, e->lst[0].H, n, s16, e->stream));
         la.in = e->y1buf; la.hist = e->lhist[1][cur]; la.out = e->y2buf; la.n_in = n / NVX_D1; la.out_pitch = p2;
         la.rows_in = e->channels; la.stage = 1; la.s16 = 0; la.nco = nullptr;

@@ -1,5 +1,5 @@
 // fir_long_tc.cu -- the first long-tap decimating FIR stage (252 k -> 63 k, D = 4) on the 5th-generation tensor cores
-// (tcgen05 + TMEM).
+// (tcgen05 + TMEM + TMA).
 //
 // Same arithmetic definition as fir_long.cu / the reference stage (fir1cpp.C:80-136):
 //     y[k] = sum_{i < T} h[i] x[D (k + 1) - 1 - i].
@@ -14,17 +14,29 @@
 // Precision: the north star's 1e-5 bar rules out plain TF32 (10-bit mantissa), so every product is the 3xTF32 split
 // x_hi h_hi + x_lo h_hi + x_hi h_lo accumulated in FP32 in TMEM (measured 1.5e-6 relative to the FP64 oracle).
 //
-// One CTA = 13 warps, persistent over a contiguous range of (row block, output tile) work items:
-//   * warps 0..7, converters: per 32-sample K chunk read [128 rows x 32 samples] from global memory (coalesced 8-byte
-//     loads, the next chunk in flight while this one is converted; history / block edge / int16 go through a slower general
-//     loader), de-interleave I and Q, split into TF32 high and low parts and write the four K-major operand tiles in the
-//     tensor core's SWIZZLE_128B layout (a strided TMA box cannot de-interleave: the swizzle span limits the box to 16
-//     samples per plane) into a ring of operand sets guarded by full / empty mbarriers;
-//   * warp 8, issuer: one thread issues the 2 planes x 3 terms x 4 k-steps tcgen05.mma.kind::tf32 (M = 128, N) per chunk and
-//     commits them to the set's empty barrier; the last chunk of a tile also commits to the tile barrier;
-//   * warps 9..12, epilogue: read the tile's 2 N accumulator columns (tcgen05.ld), release the TMEM buffer (two
-//     buffers: tile t + 1 accumulates while tile t is read), apply the NCO rotation of both channels (fir2cpp.C:112-128)
-//     and store one 63 kHz row per channel.
+// Measured on B200 (tools/probes/umma_rate.cu, umma_ts_probe.cu): one tcgen05.mma.kind::tf32 with M = 128, K = 8 costs
+// ~70 cycles for ANY N <= 128, and with both operands in shared memory the operand reads (8 KB per instruction at N = 128)
+// plus the converters' stores saturate the 128 B/clk shared-memory pipe.  Hence: wide tiles (N = 128 / 64), and the DATA
+// operand lives in tensor memory -- the converters write it with tcgen05.st -- so shared memory only serves the band matrix
+// reads and a deep ring of raw input.
+//
+// One CTA = 15 warps, persistent over a contiguous range of (row block, output tile) work items:
+//   * warps 9..10, loaders: stream the raw input window of each tile through a ring of [128 rows x 128 B] slots with 16-byte
+//     cp.async copies completing on the slot's mbarrier (128-byte XOR swizzle so that a thread can read ITS row
+//     conflict-free; rows past the last stream and samples past the block end are zero-filled).  A TMA box per slot was
+//     measured first: 128-byte box rows cap the TMA unit near 4 TB/s chip-wide (profiles/r1_staging_sweep.md D), below what
+//     this kernel re-reads from L2.  Tiles that touch the carried history skip the copies and the converters call the general
+//     loader instead; the ring protocol is the same;
+//   * warps 0..7, converters: thread = row (TMEM lane) x half of the 32-sample chunk; reads its 16 samples from the slot,
+//     de-interleaves I and Q, splits them into TF32 high and low parts and writes the four A tiles (I_hi, I_lo, Q_hi,
+//     Q_lo; 32 columns each, two sets) into tensor memory with tcgen05.st;
+//   * warp 8, issuer: one thread issues the 2 planes x 3 terms x 4 k-steps tcgen05.mma.kind::tf32 (A in TMEM, B = band
+//     matrix in shared memory) per chunk and commits them to the A set's empty barrier; the last chunk of a tile also commits
+//     to the tile barrier;
+//   * warps 11..14, epilogue: read the tile's 2 N accumulator columns (tcgen05.ld), release the accumulators (two buffers
+//     at N = 64: tile t + 1 accumulates while tile t is read), apply the NCO rotation of both channels
+//     (fir2cpp.C:112-128) and store one 63 kHz row per channel.
+// TMEM map (512 columns): [0, 256) accumulators, [256, 512) two A sets of 4 x 32 columns.
 // The accumulation order inside the tensor core is fixed per tile position, so results are deterministic for a given
 // blocking but not bit-identical across blockings (tile boundaries move); the tests hold this path to the 1e-5 bar.
 #include <cuda.h>
@@ -47,14 +59,19 @@ constexpr int kKB = 32;                    // floats per 128-byte swizzle row = 
 constexpr int kUmmaK = 8;                  // tf32: 32 bytes per instruction along K
 constexpr int kConvWarps = 8;
 constexpr int kIssuerWarp = kConvWarps;
-constexpr int kEpiWarp0 = kConvWarps + 1;
-constexpr int kTcThreads = 32 * (kConvWarps + 1 + 4);
-constexpr int kOpBytes = kRows * 128;      // one [128 rows x 128 B] operand tile
-constexpr int kSetBytes = 4 * kOpBytes;    // {I_hi, I_lo, Q_hi, Q_lo}
-constexpr int kMaxSets = 4;
+constexpr int kLoaderWarp0 = kConvWarps + 1;
+constexpr int kLoaderWarps = 2;
+constexpr int kEpiWarp0 = kLoaderWarp0 + kLoaderWarps;
+constexpr int kTcThreads = 32 * (kConvWarps + 1 + kLoaderWarps + 4);
+constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 128 B]
+constexpr int kMaxSlots = 8;
+constexpr int kEpiBytes = 32 * 33 * 8;     // epilogue staging tile: [32 rows][32 + 1 outputs] float2
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kTcD = NVX_D1;
 constexpr int kShift = kKB / kTcD;         // band rows per chunk
+constexpr uint32_t kAccCols = 256;         // accumulators: columns [0, 256)
+constexpr uint32_t kACol0 = 256;           // A sets: columns [256, 512)
+constexpr uint32_t kSetCols = 128;         // {I_hi, I_lo, Q_hi, Q_lo} x 32 columns
 
 __constant__ float2 c_tc_nco[kNcoPeriod];  // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
 
@@ -65,7 +82,7 @@ struct TcArgs {
     float2* out;
     long long n_in, in_pitch, out_pitch, out_off, k_abs;
     const NcoParam* nco;
-    int rows, s16, T, H, chunks, J, sets, box_rows;
+    int rows, s16, T, H, chunks, J, slots, box_rows, dbg, row_blocks;
     long long tiles_per_block;             // output tiles per row block
     long long work;                        // row blocks * tiles_per_block
 };
@@ -85,15 +102,20 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 
-// general loader for tiles that touch the carried history, the block end, missing rows or int16 input
+// general loader for tiles that touch the carried history
 __device__ __noinline__ float2 tc_load(const TcArgs& a, int row, long long g) {
     if (row >= a.rows || g >= a.n_in) return make_float2(0.f, 0.f);
     if (g < 0) return a.hist[(size_t)row * a.H + (a.H + g)];
@@ -116,40 +138,55 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
 }
 
-// mbarriers: [0] band matrix loaded; then per operand set full (converters -> issuer) and empty (tensor core -> converters);
-// per TMEM buffer tile accumulated (tensor core -> epilogue) and accumulators read (epilogue -> issuer)
-enum { kBarG = 0, kBarFull = 1, kBarEmpty = kBarFull + kMaxSets, kBarTile = kBarEmpty + kMaxSets, kBarTmemFree = kBarTile + 2, kBars = kBarTmemFree + 2 };
+// mbarriers: band matrix loaded; per raw slot full (TMA -> converters) / empty (converters -> producer); per A set full
+// (converters -> issuer) / empty (tensor core -> converters); per accumulator buffer tile accumulated (tensor core ->
+// epilogue) / accumulators read (epilogue -> issuer)
+enum {
+    kBarG = 0,
+    kBarRawFull = 1,
+    kBarRawEmpty = kBarRawFull + kMaxSlots,
+    kBarAFull = kBarRawEmpty + kMaxSlots,
+    kBarAEmpty = kBarAFull + 2,
+    kBarTile = kBarAEmpty + 2,
+    kBarTmemFree = kBarTile + 2,
+    kBars = kBarTmemFree + 2
+};
 
-// LD: how the converters read global memory (0: ld.global.nc, 1: ld.global.cg, 2: ld.global.cs)
-template <int LD>
-__device__ __forceinline__ float2 ld_in(const float2* p) {
-    if constexpr (LD == 1) return __ldcg(p);
-    else if constexpr (LD == 2) return __ldcs(p);
-    else return __ldg(p);
+// round to TF32 (10-bit mantissa, nearest, ties away) with integer ops; the remainder is exact in FP32
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
 }
 
-template <int N, int LD>
+template <int N>
 __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int kAccBufs = 2 * N * 2 <= (int)kAccCols ? 2 : 1;      // accumulator buffers of 2 N columns
     const int g_bytes = a.J * 128;                          // one part of the band matrix (a multiple of 1024)
     uint8_t* s_gh = smem;
     uint8_t* s_gl = smem + g_bytes;
-    uint8_t* s_op = smem + 2 * g_bytes;                     // ring of operand sets
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_op + a.sets * kSetBytes);
+    uint8_t* s_raw = smem + 2 * g_bytes;                    // ring of raw-input slots
+    uint8_t* s_epi = s_raw + a.slots * kSlotBytes;          // one staging tile per epilogue warp
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 4 * kEpiBytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars);
     const uint32_t bar0 = s_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t kCols = 4 * N;                       // 2 buffers x (I | Q) accumulator columns: 128 or 256, a power of two
+    // float2 input: a slot is 16 samples and each half of the converters owns one slot of a chunk; short2: 32 samples, shared
+    const int slots_per_chunk = a.s16 ? 1 : 2;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kBars; ++i) {
-            const int count = (i >= kBarFull && i < kBarFull + kMaxSets) ? kConvWarps : (i >= kBarTmemFree ? 4 : 1);
+            int count = 1;
+            if (i >= kBarRawFull && i < kBarRawFull + kMaxSlots) count = 32 * kLoaderWarps;
+            if (i >= kBarRawEmpty && i < kBarRawEmpty + kMaxSlots) count = kConvWarps / slots_per_chunk;
+            if (i >= kBarAFull && i < kBarAFull + 2) count = kConvWarps;
+            if (i >= kBarTmemFree) count = 4;
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(count));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(kCols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -157,11 +194,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
 
-    // contiguous share of the work items: consecutive tiles of a row block overlap in most of their inputs (L2)
-    const long long per = (a.work + gridDim.x - 1) / gridDim.x;
-    const long long w_lo = (long long)blockIdx.x * per, w_hi = w_lo + per < a.work ? w_lo + per : a.work;
+    // work item w = (output tile w / row_blocks, row block w % row_blocks), CTAs take w = blockIdx, blockIdx + grid, ...: at any
+    // moment the CTAs sweep the same few tiles of every row, so the pages in use stay few and neighbouring tiles' overlapping
+    // windows meet in L2 (measured equal to one contiguous range of tiles per CTA)
+    const long long w_lo = blockIdx.x, w_hi = a.work;
+    const int w_step = gridDim.x;
 
-    if (warp == kIssuerWarp) {
+    if (warp >= kLoaderWarp0 && warp < kLoaderWarp0 + kLoaderWarps) {
+        // loaders: 16-byte cp.async pieces (L1 bypassed), zero fill past the last stream / the block end, written in the
+        // 128-byte-swizzled slot layout: piece (row r, unit u) -> r * 128 + ((u ^ (r % 8)) * 16)
+        const int tid = (warp - kLoaderWarp0) * 32 + lane;
+        constexpr int kLoaders = 32 * kLoaderWarps;
+        const int units = 8 * slots_per_chunk;                    // 16-byte pieces per row per chunk
+        const int u16 = tid % units, r0 = tid / units, r_step = kLoaders / units;
+        const int esz = a.s16 ? 4 : 8;                            // bytes per sample
+        const int per_piece = 16 / esz;                           // samples per piece
+        int slot = 0;
+        uint32_t ph = 0;
+        for (long long w = w_lo; w < w_hi; w += w_step) {
+            const int rb = (int)(w % a.row_blocks);
+            const long long n0 = (w / a.row_blocks) * N;
+            const long long t_base = (long long)kTcD * n0 + kTcD - a.T;      // first input of the tile's window (block-relative)
+            const bool fast = t_base >= 0 && !(a.dbg & 1);
+            for (int c = 0; c < a.chunks; ++c) {
+                bar_wait(bar0 + 8 * (kBarRawEmpty + slot), ph ^ 1);
+                if (slots_per_chunk == 2) bar_wait(bar0 + 8 * (kBarRawEmpty + slot + 1), ph ^ 1);
+                if (fast) {
+                    const long long t = t_base + (long long)c * kKB + u16 * per_piece;       // first sample of this thread's pieces
+                    const bool t_ok = t + per_piece <= a.n_in;
+                    const uint8_t* src = static_cast<const uint8_t*>(a.in) + ((size_t)(rb * kRows + r0) * a.in_pitch + t) * esz;
+                    const size_t src_step = (size_t)r_step * a.in_pitch * esz;
+                    const uint32_t dst0 = s_u32(s_raw + (slot + (u16 >> 3)) * kSlotBytes);
+#pragma unroll 4
+                    for (int r = r0; r < kRows; r += r_step, src += src_step) {
+                        const uint32_t dst = dst0 + r * 128 + (((u16 & 7) ^ (r & 7)) << 4);
+                        const int bytes = (t_ok && rb * kRows + r < a.rows) ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(bytes ? src : static_cast<const uint8_t*>(a.in)), "r"(bytes) : "memory");
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * (kBarRawFull + slot)) : "memory");
+                    if (slots_per_chunk == 2)
+                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * (kBarRawFull + slot + 1)) : "memory");
+                } else {
+                    bar_arrive(bar0 + 8 * (kBarRawFull + slot));               // the converters load this part themselves
+                    if (slots_per_chunk == 2) bar_arrive(bar0 + 8 * (kBarRawFull + slot + 1));
+                }
+                slot += slots_per_chunk;
+                if (slot >= a.slots) { slot = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == kIssuerWarp) {
         if (lane == 0) {
             // the constant band matrix, once per CTA (TMA boxes of box_rows <= 256 rows, a divisor of J)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * kBarG), "r"(2 * g_bytes) : "memory");
@@ -175,163 +256,180 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             // n_dim = N >> 3 at [17,23), m_dim = 128 >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
             bar_wait(bar0 + 8 * kBarG, 0);
-            int s = 0;
-            uint32_t ph = 0, tile = 0;
-            for (long long w = w_lo; w < w_hi; ++w, ++tile) {
-                const uint32_t buf = tile & 1;
-                bar_wait(bar0 + 8 * (kBarTmemFree + buf), ((tile >> 1) & 1) ^ 1);     // the epilogue has read this buffer's last tile
+            uint32_t s = 0, ph = 0, tile = 0;
+            for (long long w = w_lo; w < w_hi; w += w_step, ++tile) {
+                const uint32_t buf = kAccBufs == 2 ? (tile & 1) : 0, use = kAccBufs == 2 ? (tile >> 1) : tile;
+                bar_wait(bar0 + 8 * (kBarTmemFree + buf), (use & 1) ^ 1);     // the epilogue has read this buffer's last tile
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t acc = tmem + buf * 2 * N;
                 for (int c = 0; c < a.chunks; ++c) {
-                    bar_wait(bar0 + 8 * (kBarFull + s), ph);
+                    bar_wait(bar0 + 8 * (kBarAFull + s), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t op = s_u32(s_op + s * kSetBytes);
+                    const uint32_t at = tmem + kACol0 + s * kSetCols;
                     const uint32_t goff = (uint32_t)(a.chunks - 1 - c) * (kShift * 128);      // chunk c of B = G shifted by whole atoms
                     const uint32_t gh = s_u32(s_gh) + goff, gl = s_u32(s_gl) + goff;
+                    if (!(a.dbg & 4))
 #pragma unroll
                     for (int p = 0; p < 2; ++p)
 #pragma unroll
                         for (int term = 0; term < 3; ++term)              // x_hi h_hi, x_lo h_hi, x_hi h_lo
 #pragma unroll
                             for (int k = 0; k < kKB / kUmmaK; ++k)
-                                umma_tf32(acc + p * N, umma_desc(op + (2 * p + (term == 1 ? 1 : 0)) * kOpBytes + k * kUmmaK * 4),
-                                          umma_desc((term == 2 ? gl : gh) + k * kUmmaK * 4), idesc, (c | term | k) ? 1u : 0u);
-                    umma_commit(bar0 + 8 * (kBarEmpty + s));
+                                umma_ts_tf32(acc + p * N, at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
+                                             umma_desc((term == 2 ? gl : gh) + k * kUmmaK * 4), idesc, (c | term | k) ? 1u : 0u);
+                    umma_commit(bar0 + 8 * (kBarAEmpty + s));
                     if (c == a.chunks - 1) umma_commit(bar0 + 8 * (kBarTile + buf));
-                    if (++s == a.sets) { s = 0; ph ^= 1; }
+                    if (++s == 2) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp < kConvWarps) {
-        // Thread -> column k = lane of rows r = 8 i + warp, i < 16: element (r, k) of a SWIZZLE_128B K-major tile lives at
-        // (r / 8) * 1024 + (r % 8) * 128 + (((k / 4) ^ (r % 8)) * 16) + (k % 4) * 4 = i * 1024 + a per-thread constant
-        const int off0 = warp * 128 + ((((lane >> 2) ^ warp) << 4) | ((lane & 3) << 2));
-        int s = 0;
-        uint32_t ph = 0;
-        for (long long w = w_lo; w < w_hi; ++w) {
-            const int rb = (int)(w / a.tiles_per_block);
-            const long long n0 = (w % a.tiles_per_block) * N;                 // first output of the tile
-            const long long t_base = (long long)kTcD * n0 + kTcD - a.T;      // first input of its window (block-relative, may be < 0)
-            // interior tiles (the common case) read the block directly; edge tiles go through the general loader
-            const bool fast = !a.s16 && t_base >= 0 && t_base + (long long)a.chunks * kKB <= a.n_in && (rb + 1) * kRows <= a.rows;
-            const float2* src = static_cast<const float2*>(a.in) + (size_t)(rb * kRows + warp) * a.in_pitch + t_base + lane;
-            const size_t row_step = (size_t)8 * a.in_pitch;
-            auto fetch = [&](int c, float2 (&x)[16]) {
-                if (fast) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) x[i] = ld_in<LD>(src + i * row_step + c * kKB);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) x[i] = tc_load(a, rb * kRows + 8 * i + warp, t_base + (long long)c * kKB + lane);
-                }
-            };
-            float2 x[16];
-            fetch(0, x);
+        // thread = TMEM lane = row 32 q + lane of the tile, samples [16 kh, 16 kh + 16) of every chunk
+        const int q = warp & 3, kh = warp >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + kACol0 + kh * 16;
+        int slot = a.s16 ? 0 : kh;                          // float2: this half's slot of chunk 0
+        uint32_t sph = 0, s = 0, ph = 0;
+        for (long long w = w_lo; w < w_hi; w += w_step) {
+            const int rb = (int)(w % a.row_blocks);
+            const long long n0 = (w / a.row_blocks) * N;
+            const long long t_base = (long long)kTcD * n0 + kTcD - a.T;
+            const bool fast = t_base >= 0 && !(a.dbg & 1);
             for (int c = 0; c < a.chunks; ++c) {
-                float2 xn[16];
-                if (c + 1 < a.chunks) fetch(c + 1, xn);          // in flight while chunk c is converted
-                bar_wait(bar0 + 8 * (kBarEmpty + s), ph ^ 1);    // the MMAs that read this set are done
-                uint8_t* op = s_op + s * kSetBytes + off0;
+                bar_wait(bar0 + 8 * (kBarRawFull + slot), sph);                 // raw samples landed
+                bar_wait(bar0 + 8 * (kBarAEmpty + s), ph ^ 1);                  // the MMAs that read this A set are done
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint8_t* row = s_raw + slot * kSlotBytes + r * 128;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    // round to TF32 (10-bit mantissa, nearest, ties away) with integer ops; the remainder is exact in FP32
-                    const float hi = __uint_as_float((__float_as_uint(x[i].x) + 0x1000u) & 0xFFFFE000u);
-                    const float hq = __uint_as_float((__float_as_uint(x[i].y) + 0x1000u) & 0xFFFFE000u);
-                    *reinterpret_cast<float*>(op + 0 * kOpBytes + i * 1024) = hi;
-                    *reinterpret_cast<float*>(op + 1 * kOpBytes + i * 1024) = x[i].x - hi;
-                    *reinterpret_cast<float*>(op + 2 * kOpBytes + i * 1024) = hq;
-                    *reinterpret_cast<float*>(op + 3 * kOpBytes + i * 1024) = x[i].y - hq;
+                for (int ks = 0; ks < 2; ++ks) {                                // 8 samples = one MMA k-step
+                    float ih[8], il[8], qh[8], ql[8];
+                    if (fast) {
+                        if (a.s16) {                                            // 16-byte units 4 kh + 2 ks, + 1: 4 samples each
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int4 v = *reinterpret_cast<const int4*>(row + (((4 * kh + 2 * ks + u) ^ (r & 7)) << 4));
+                                const int wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    split_tf32((float)(short)(wv[j] & 0xFFFF), ih[4 * u + j], il[4 * u + j]);
+                                    split_tf32((float)(wv[j] >> 16), qh[4 * u + j], ql[4 * u + j]);
+                                }
+                            }
+                        } else {                                                // 16-byte units 4 ks .. 4 ks + 3: 2 samples each
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float4 v = *reinterpret_cast<const float4*>(row + (((4 * ks + u) ^ (r & 7)) << 4));
+                                split_tf32(v.x, ih[2 * u], il[2 * u]);
+                                split_tf32(v.y, qh[2 * u], ql[2 * u]);
+                                split_tf32(v.z, ih[2 * u + 1], il[2 * u + 1]);
+                                split_tf32(v.w, qh[2 * u + 1], ql[2 * u + 1]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 v = tc_load(a, rb * kRows + r, t_base + (long long)c * kKB + kh * 16 + ks * 8 + j);
+                            split_tf32(v.x, ih[j], il[j]);
+                            split_tf32(v.y, qh[j], ql[j]);
+                        }
+                    }
+                    const uint32_t col = lane_base + s * kSetCols + ks * 8;
+                    if (!(a.dbg & 2)) {
+                    tmem_st8(col + 0 * 32, ih);
+                    tmem_st8(col + 1 * 32, il);
+                    tmem_st8(col + 2 * 32, qh);
+                    tmem_st8(col + 3 * 32, ql);
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = xn[i];
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) bar_arrive(bar0 + 8 * (kBarFull + s));
-                if (++s == a.sets) { s = 0; ph ^= 1; }
+                if (lane == 0) {
+                    bar_arrive(bar0 + 8 * (kBarAFull + s));
+                    bar_arrive(bar0 + 8 * (kBarRawEmpty + slot));
+                }
+                if (++s == 2) { s = 0; ph ^= 1; }
+                slot += slots_per_chunk;
+                if (slot >= a.slots) { slot -= a.slots; sph ^= 1; }
             }
         }
     } else {
         // epilogue warp: TMEM lanes 32 q .. 32 q + 31 (q = warp % 4, the lanes this warp may address) = rows of the tile
         const int q = warp & 3;
         const long long n_out = a.n_in / kTcD;
-        const bool vec = ((a.out_pitch | a.out_off) & 1) == 0;      // 16-byte stores of output pairs
+        float2* stg = reinterpret_cast<float2*>(s_epi + (warp - kEpiWarp0) * kEpiBytes);      // [32 rows][32 + 1 outputs], warp-private
         uint32_t tile = 0;
-        for (long long w = w_lo; w < w_hi; ++w, ++tile) {
-            const int rb = (int)(w / a.tiles_per_block);
-            const long long n0 = (w % a.tiles_per_block) * N;
-            const uint32_t buf = tile & 1;
+        for (long long w = w_lo; w < w_hi; w += w_step, ++tile) {
+            const int rb = (int)(w % a.row_blocks);
+            const long long n0 = (w / a.row_blocks) * N;
+            const uint32_t buf = kAccBufs == 2 ? (tile & 1) : 0, use = kAccBufs == 2 ? (tile >> 1) : tile;
             const int row = rb * kRows + q * 32 + lane;
-            bar_wait(bar0 + 8 * (kBarTile + buf), (tile >> 1) & 1);
+            bar_wait(bar0 + 8 * (kBarTile + buf), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * 2 * N;
             NcoParam np = {};
             if (a.nco && row < a.rows) np = a.nco[row];
 #pragma unroll 1
             for (int h = 0; h < N / 32; ++h) {
-                uint32_t vi[32], vq[32];
+                uint32_t vi[32] = {}, vq[32] = {};
+                if (!(a.dbg & 8)) {
                 tmem_ld32(taddr + h * 32, vi);
                 tmem_ld32(taddr + N + h * 32, vq);
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (h == N / 32 - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     __syncwarp();
                     if (lane == 0) bar_arrive(bar0 + 8 * (kBarTmemFree + buf));      // the accumulators may be overwritten
                 }
-                if (row >= a.rows) continue;
-                // NCO mix: output k sits at 63 kHz clock tick k_abs + k; channel c gets y * (cos - j sin)(2 pi tick f_c / 63000)
+                // NCO mix: output k sits at 63 kHz clock tick k_abs + k; channel c gets y * (cos - j sin)(2 pi tick f_c / 63000).
+                // One channel at a time: lane = row mixes its 32 outputs into the staging tile, then lane = output and every
+                // store instruction writes 256 contiguous bytes of one row (16 bytes x 32 rows per instruction measured 3x slower)
                 const long long nh = n0 + h * 32;
-                float2* out0 = a.out + (size_t)(2 * row) * a.out_pitch + a.out_off + nh;
-                float2* out1 = out0 + a.out_pitch;
                 const long long tick0 = a.k_abs + nh;
-                long long r9 = tick0 % kNcoPeriod, rden = tick0 % kNcoDen;
-                int k9 = (int)(r9 < 0 ? r9 + kNcoPeriod : r9), kden = (int)(rden < 0 ? rden + kNcoDen : rden);
-                float2 prev0 = make_float2(0.f, 0.f), prev1 = prev0;
+                const long long r9 = tick0 % kNcoPeriod, rden = tick0 % kNcoDen;
+                const int k9_0 = (int)(r9 < 0 ? r9 + kNcoPeriod : r9), kden_0 = (int)(rden < 0 ? rden + kNcoDen : rden);
+                const int row0 = rb * kRows + q * 32;
+                const int r_max = a.rows - row0 < 32 ? a.rows - row0 : 32;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    int k9 = k9_0, kden = kden_0;
+                    const int num = c ? np.num[1] : np.num[0];
+                    const float conj = c ? -1.f : 1.f;                   // "490": conjugate rotation (fir2cpp.C:121-124)
 #pragma unroll
-                for (int n = 0; n < 32; ++n) {
-                    float2 rot[2];
-                    if (a.nco) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int phs = (int)(((long long)kden * np.num[c]) % kNcoDen);
+                    for (int n = 0; n < 32; ++n) {
+                        float2 rot;
+                        if (a.nco) {
+                            const int phs = (int)(((long long)kden * num) % kNcoDen);
                             float tt = (float)phs * (2.0f / kNcoDen);
                             if (tt > 1.0f) tt -= 2.0f;
                             float sn, cs;
                             sincospif(tt, &sn, &cs);
-                            rot[c] = make_float2(cs, -sn);
-                        }
-                    } else {
-                        rot[0] = c_tc_nco[k9];
-                        rot[1] = make_float2(rot[0].x, -rot[0].y);       // "490": conjugate rotation (fir2cpp.C:121-124)
-                    }
-                    const float2 y = make_float2(__uint_as_float(vi[n]), __uint_as_float(vq[n]));
-                    const float2 o0 = make_float2(fmaf(-y.y, rot[0].y, y.x * rot[0].x), fmaf(y.x, rot[0].y, y.y * rot[0].x));
-                    const float2 o1 = make_float2(fmaf(-y.y, rot[1].y, y.x * rot[1].x), fmaf(y.x, rot[1].y, y.y * rot[1].x));
-                    if (vec) {
-                        if (n & 1) {
-                            if (nh + n < n_out) {
-                                *reinterpret_cast<float4*>(out0 + n - 1) = make_float4(prev0.x, prev0.y, o0.x, o0.y);
-                                *reinterpret_cast<float4*>(out1 + n - 1) = make_float4(prev1.x, prev1.y, o1.x, o1.y);
-                            } else if (nh + n - 1 < n_out) {
-                                out0[n - 1] = prev0;
-                                out1[n - 1] = prev1;
-                            }
+                            rot = make_float2(cs, -sn);
                         } else {
-                            prev0 = o0;
-                            prev1 = o1;
+                            rot = c_tc_nco[k9];
+                            rot.y *= conj;
                         }
-                    } else if (nh + n < n_out) {
-                        out0[n] = o0;
-                        out1[n] = o1;
+                        const float2 y = make_float2(__uint_as_float(vi[n]), __uint_as_float(vq[n]));
+                        stg[lane * 33 + n] = make_float2(fmaf(-y.y, rot.y, y.x * rot.x), fmaf(y.x, rot.y, y.y * rot.x));
+                        if (++k9 == kNcoPeriod) k9 = 0;
+                        if (++kden == kNcoDen) kden = 0;
                     }
-                    if (++k9 == kNcoPeriod) k9 = 0;
-                    if (++kden == kNcoDen) kden = 0;
+                    __syncwarp();
+                    if (nh + lane < n_out) {
+                        float2* dst = a.out + (size_t)(2 * row0 + c) * a.out_pitch + a.out_off + nh + lane;
+                        const size_t row_step = (size_t)2 * a.out_pitch;
+#pragma unroll 4
+                        for (int r = 0; r < r_max; ++r) dst[r * row_step] = stg[r * 33 + lane];
+                    }
+                    __syncwarp();
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kCols));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -348,33 +446,28 @@ float tf32_rna(float x) {                  // round to nearest, ties away, 10-bi
 
 int tc_chunks(int N, int T) { return (kTcD * (N - 1) + T + kKB - 1) / kKB; }
 int tc_band_rows(int N, int T) { return N + kShift * (tc_chunks(N, T) - 1); }
-size_t tc_smem(int N, int T, int sets) { return (size_t)2 * tc_band_rows(N, T) * 128 + (size_t)sets * kSetBytes + kBars * 8 + 16; }
+size_t tc_smem(int N, int T, int slots) { return (size_t)2 * tc_band_rows(N, T) * 128 + (size_t)slots * kSlotBytes + 4 * kEpiBytes + kBars * 8 + 16; }
 int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 rows, dividing J
     int best = 1;
     for (int d = 1; d <= 32; ++d)
         if ((J / 8) % d == 0) best = d;
     return 8 * best;
 }
-int tc_sets(int N, int T) {                // operand sets that fit beside the band matrix (0: the stage does not fit)
-    for (int sets = kMaxSets; sets >= 2; --sets)
-        if (tc_smem(N, T, sets) <= (size_t)kSmemLimit) return sets;
+int tc_slots(int N, int T) {               // raw-input slots that fit beside the band matrix: even, >= 4 (0: the stage does not fit)
+    for (int slots = kMaxSlots; slots >= 4; slots -= 2)
+        if (tc_smem(N, T, slots) <= (size_t)kSmemLimit) return slots;
     return 0;
 }
 
-template <int N, int LD>
-cudaError_t launch_tc2(TcArgs& a, int sms, cudaStream_t stream) {
-    a.sets = tc_sets(N, a.T);
-    const size_t smem = tc_smem(N, a.T, a.sets);
-    cudaError_t e = cudaFuncSetAttribute(fir_tc_kernel<N, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const long long grid = a.work < sms ? a.work : sms;
-    fir_tc_kernel<N, LD><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
-    return cudaGetLastError();
-}
 template <int N>
 cudaError_t launch_tc(TcArgs& a, int sms, cudaStream_t stream) {
-    static const int ld = getenv("NVX_TC_LD") ? atoi(getenv("NVX_TC_LD")) : 0;
-    return ld == 1 ? launch_tc2<N, 1>(a, sms, stream) : ld == 2 ? launch_tc2<N, 2>(a, sms, stream) : launch_tc2<N, 0>(a, sms, stream);
+    a.slots = tc_slots(N, a.T);
+    const size_t smem = tc_smem(N, a.T, a.slots);
+    cudaError_t e = cudaFuncSetAttribute(fir_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long grid = a.work < sms ? a.work : sms;
+    fir_tc_kernel<N><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -383,11 +476,11 @@ cudaError_t launch_tc(TcArgs& a, int sms, cudaStream_t stream) {
 // number of outputs)
 int long_tc_tile(int D, int T) {
     if (D != kTcD) return 0;
-    // one tcgen05.mma (M = 128, K = 8) with both operands in shared memory costs ~75 cycles for any N <= 128
-    // (tools/probes/umma_rate.cu), so the widest tile whose band matrix fits wins
+    // one tcgen05.mma (M = 128, K = 8) costs ~70 cycles for any N <= 128 (tools/probes/umma_rate.cu, umma_ts_probe.cu), so wide
+    // tiles win as long as the band matrix leaves room for the raw-input ring
     int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : 128;
     for (int N : {128, 64, 32})
-        if (N <= want && tc_sets(N, T)) return N;
+        if (N <= want && tc_slots(N, T)) return N;
     return 0;
 }
 
@@ -395,10 +488,14 @@ struct LongTcStage {
     int D = 0, T = 0, N = 0, chunks = 0, J = 0, box_rows = 0;
     float *d_gh = nullptr, *d_gl = nullptr;
     CUtensorMap map_gh, map_gl;
+    EncodeTiledFn enc = nullptr;
 };
 
 // builds the band matrix of the stage on the device; returns nullptr if the stage does not fit the tensor-core kernel
-LongTcStage* long_tc_prepare(int D, int T, const double* h, cudaStream_t stream) {
+LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t stream) {
+    // zero taps appended at the old end until the tile windows start on a whole 32-byte sector (4 samples): the TMA unit needs
+    // 16-byte aligned box origins, and aligned rows cost 8 sectors instead of 9
+    const int T = (T_taps + 3) & ~3;
     const int N = long_tc_tile(D, T);
     if (!N) return nullptr;
     void* fn = nullptr;
@@ -414,7 +511,7 @@ LongTcStage* long_tc_prepare(int D, int T, const double* h, cudaStream_t stream)
         for (int k = 0; k < kKB; ++k) {
             // row j of G is output n = j - 8 (chunks - 1 - c) of chunk c: tap index D n + T - 1 - (32 c + k)
             const int i = D * (j - kShift * (s->chunks - 1)) + T - 1 - k;
-            if (i >= 0 && i < T) {
+            if (i >= 0 && i < T_taps) {
                 const float t = (float)h[i];
                 gh[(size_t)j * kKB + k] = tf32_rna(t);
                 gl[(size_t)j * kKB + k] = t - tf32_rna(t);
@@ -429,7 +526,7 @@ LongTcStage* long_tc_prepare(int D, int T, const double* h, cudaStream_t stream)
     ok = ok && cudaMemcpyToSymbolAsync(c_tc_nco, nco, sizeof nco, 0, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
     if (ok) {
-        EncodeTiledFn enc = (EncodeTiledFn)fn;
+        EncodeTiledFn enc = s->enc = (EncodeTiledFn)fn;
         cuuint64_t dims[2] = {(cuuint64_t)kKB, (cuuint64_t)s->J};
         cuuint64_t strides[1] = {(cuuint64_t)kKB * 4};
         cuuint32_t box[2] = {kKB, (cuuint32_t)s->box_rows};
@@ -453,16 +550,21 @@ void long_tc_free(LongTcStage* s) {
     delete s;
 }
 
-// same contract as long_launch (fir_long.cu) for stage 0
+// same contract as long_launch (fir_long.cu) for stage 0; cudaErrorNotSupported = this block cannot be described to the TMA
+// unit (misaligned pointer or pitch): the caller falls back to long_launch
 cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongStage& st, long long in_pitch, cudaStream_t stream) {
     TcArgs a;
     a.map_gh = s->map_gh; a.map_gl = s->map_gl;
     a.in = la.in; a.hist = la.hist; a.out = la.out;
     a.n_in = la.n_in; a.in_pitch = in_pitch; a.out_pitch = la.out_pitch; a.out_off = la.out_off; a.k_abs = la.k_abs;
-    a.nco = la.nco; a.rows = la.rows_in; a.s16 = la.s16; a.T = s->T; a.H = st.H; a.chunks = s->chunks; a.J = s->J; a.sets = 2; a.box_rows = s->box_rows;
+    a.nco = la.nco; a.rows = la.rows_in; a.s16 = la.s16; a.T = s->T; a.H = st.H; a.chunks = s->chunks; a.J = s->J; a.slots = 4; a.box_rows = s->box_rows;
+    a.dbg = getenv("NVX_TC_DBG") ? atoi(getenv("NVX_TC_DBG")) : 0;
+    // 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by construction)
+    if (((uintptr_t)la.in & 15) || ((in_pitch * (la.s16 ? 4 : 8)) & 15)) return cudaErrorNotSupported;
     const long long n_out = la.n_in / s->D;
     a.tiles_per_block = (n_out + s->N - 1) / s->N;
-    a.work = (long long)((la.rows_in + kRows - 1) / kRows) * a.tiles_per_block;
+    a.row_blocks = (la.rows_in + kRows - 1) / kRows;
+    a.work = (long long)a.row_blocks * a.tiles_per_block;
     if (a.work <= 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
