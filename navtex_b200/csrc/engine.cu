@@ -639,8 +639,9 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         for (int k = 0; k < 3; ++k)
             for (int q = 0; q < 2; ++q)
                 CREATE_TRY(cudaMalloc(&e->lhist[k][q], (size_t)(k == 0 ? e->S : e->channels) * e->lst[k].H * sizeof(float2)));
-        // NVX_LONG_TC=1: stage 1 on the tensor cores (fir_long_tc.cu; opt-in while it trails the CUDA-core kernel at <= 255 taps)
-        if (getenv("NVX_LONG_TC") && atoi(getenv("NVX_LONG_TC")) & 1)
+        // stage 1 on the tensor cores where the band matrix fits (fir_long_tc.cu); NVX_LONG_TC=0 keeps the CUDA-core kernel,
+        // whose output is bit-identical across blockings
+        if (!(getenv("NVX_LONG_TC") && atoi(getenv("NVX_LONG_TC")) == 0))
             e->ltc[0] = nvx::long_tc_prepare(NVX_D1, e->lst[0].T, cfg->h1 ? cfg->h1 : d1, e->stream);
         CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->channels * (cfg->max_block / NVX_D1) * sizeof(float2)));
         CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));

@@ -20,12 +20,13 @@
 // operand lives in tensor memory -- the converters write it with tcgen05.st -- so shared memory only serves the band matrix
 // reads and a deep ring of raw input.
 //
-// One CTA = 15 warps, persistent over a contiguous range of (row block, output tile) work items:
-//   * warps 9..10, loaders: stream the raw input window of each tile through a ring of [128 rows x 128 B] slots with 16-byte
+// One CTA = 16 warps, persistent over a contiguous range of (row block, output tile) work items:
+//   * warps 9..11, loaders: stream the raw input window of each tile through a ring of [128 rows x 128 B] slots with 16-byte
 //     cp.async copies completing on the slot's mbarrier (128-byte XOR swizzle so that a thread can read ITS row
 //     conflict-free; rows past the last stream and samples past the block end are zero-filled).  A TMA box per slot was
 //     measured first: 128-byte box rows cap the TMA unit near 4 TB/s chip-wide (profiles/r1_staging_sweep.md D), below what
-//     this kernel re-reads from L2.  Tiles that touch the carried history skip the copies and the converters call the general
+//     this kernel re-reads from L2, and one 1-D bulk copy per row costs ~63 cycles of the TMA unit each, whatever its size
+//     (2.8x slower end to end).  Tiles that touch the carried history skip the copies and the converters call the general
 //     loader instead; the ring protocol is the same;
 //   * warps 0..7, converters: thread = row (TMEM lane) x half of the 32-sample chunk; reads its 16 samples from the slot,
 //     de-interleaves I and Q, splits them into TF32 high and low parts and writes the four A tiles (I_hi, I_lo, Q_hi,
@@ -33,7 +34,7 @@
 //   * warp 8, issuer: one thread issues the 2 planes x 3 terms x 4 k-steps tcgen05.mma.kind::tf32 (A in TMEM, B = band
 //     matrix in shared memory) per chunk and commits them to the A set's empty barrier; the last chunk of a tile also commits
 //     to the tile barrier;
-//   * warps 11..14, epilogue: read the tile's 2 N accumulator columns (tcgen05.ld), release the accumulators (two buffers
+//   * warps 12..15, epilogue: read the tile's 2 N accumulator columns (tcgen05.ld), release the accumulators (two buffers
 //     at N = 64: tile t + 1 accumulates while tile t is read), apply the NCO rotation of both channels
 //     (fir2cpp.C:112-128) and store one 63 kHz row per channel.
 // TMEM map (512 columns): [0, 256) accumulators, [256, 512) two A sets of 4 x 32 columns.
@@ -60,7 +61,7 @@ constexpr int kUmmaK = 8;                  // tf32: 32 bytes per instruction alo
 constexpr int kConvWarps = 8;
 constexpr int kIssuerWarp = kConvWarps;
 constexpr int kLoaderWarp0 = kConvWarps + 1;
-constexpr int kLoaderWarps = 2;
+constexpr int kLoaderWarps = 3;
 constexpr int kEpiWarp0 = kLoaderWarp0 + kLoaderWarps;
 constexpr int kTcThreads = 32 * (kConvWarps + 1 + kLoaderWarps + 4);
 constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 128 B]
@@ -82,7 +83,7 @@ struct TcArgs {
     float2* out;
     long long n_in, in_pitch, out_pitch, out_off, k_abs;
     const NcoParam* nco;
-    int rows, s16, T, H, chunks, J, slots, box_rows, dbg, row_blocks;
+    int rows, s16, T, H, chunks, J, slots, box_rows;
     long long tiles_per_block;             // output tiles per row block
     long long work;                        // row blocks * tiles_per_block
 };
@@ -194,11 +195,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
 
-    // work item w = (output tile w / row_blocks, row block w % row_blocks), CTAs take w = blockIdx, blockIdx + grid, ...: at any
-    // moment the CTAs sweep the same few tiles of every row, so the pages in use stay few and neighbouring tiles' overlapping
-    // windows meet in L2 (measured equal to one contiguous range of tiles per CTA)
-    const long long w_lo = blockIdx.x, w_hi = a.work;
-    const int w_step = gridDim.x;
+    // a contiguous range of work items per CTA: consecutive tiles of a row block overlap in a third to two thirds of their
+    // inputs, which the CTA's own previous tile left in L2 (DRAM reads 1.02x the input; interleaving the tiles over the CTAs
+    // was measured at 1.86x and 5 % slower)
+    const long long per = (a.work + gridDim.x - 1) / gridDim.x;
+    const long long w_lo = (long long)blockIdx.x * per, w_hi = w_lo + per < a.work ? w_lo + per : a.work;
 
     if (warp >= kLoaderWarp0 && warp < kLoaderWarp0 + kLoaderWarps) {
         // loaders: 16-byte cp.async pieces (L1 bypassed), zero fill past the last stream / the block end, written in the
@@ -211,11 +212,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         const int per_piece = 16 / esz;                           // samples per piece
         int slot = 0;
         uint32_t ph = 0;
-        for (long long w = w_lo; w < w_hi; w += w_step) {
-            const int rb = (int)(w % a.row_blocks);
-            const long long n0 = (w / a.row_blocks) * N;
+        for (long long w = w_lo; w < w_hi; ++w) {
+            const int rb = (int)(w / a.tiles_per_block);
+            const long long n0 = (w % a.tiles_per_block) * N;
             const long long t_base = (long long)kTcD * n0 + kTcD - a.T;      // first input of the tile's window (block-relative)
-            const bool fast = t_base >= 0 && !(a.dbg & 1);
+            const bool fast = t_base >= 0;
             for (int c = 0; c < a.chunks; ++c) {
                 bar_wait(bar0 + 8 * (kBarRawEmpty + slot), ph ^ 1);
                 if (slots_per_chunk == 2) bar_wait(bar0 + 8 * (kBarRawEmpty + slot + 1), ph ^ 1);
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
             bar_wait(bar0 + 8 * kBarG, 0);
             uint32_t s = 0, ph = 0, tile = 0;
-            for (long long w = w_lo; w < w_hi; w += w_step, ++tile) {
+            for (long long w = w_lo; w < w_hi; ++w, ++tile) {
                 const uint32_t buf = kAccBufs == 2 ? (tile & 1) : 0, use = kAccBufs == 2 ? (tile >> 1) : tile;
                 bar_wait(bar0 + 8 * (kBarTmemFree + buf), (use & 1) ^ 1);     // the epilogue has read this buffer's last tile
                 asm volatile("tcgen05.fence::after_thread_sync;");
@@ -268,7 +269,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                     const uint32_t at = tmem + kACol0 + s * kSetCols;
                     const uint32_t goff = (uint32_t)(a.chunks - 1 - c) * (kShift * 128);      // chunk c of B = G shifted by whole atoms
                     const uint32_t gh = s_u32(s_gh) + goff, gl = s_u32(s_gl) + goff;
-                    if (!(a.dbg & 4))
 #pragma unroll
                     for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -290,11 +290,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + kACol0 + kh * 16;
         int slot = a.s16 ? 0 : kh;                          // float2: this half's slot of chunk 0
         uint32_t sph = 0, s = 0, ph = 0;
-        for (long long w = w_lo; w < w_hi; w += w_step) {
-            const int rb = (int)(w % a.row_blocks);
-            const long long n0 = (w / a.row_blocks) * N;
+        for (long long w = w_lo; w < w_hi; ++w) {
+            const int rb = (int)(w / a.tiles_per_block);
+            const long long n0 = (w % a.tiles_per_block) * N;
             const long long t_base = (long long)kTcD * n0 + kTcD - a.T;
-            const bool fast = t_base >= 0 && !(a.dbg & 1);
+            const bool fast = t_base >= 0;
             for (int c = 0; c < a.chunks; ++c) {
                 bar_wait(bar0 + 8 * (kBarRawFull + slot), sph);                 // raw samples landed
                 bar_wait(bar0 + 8 * (kBarAEmpty + s), ph ^ 1);                  // the MMAs that read this A set are done
@@ -334,12 +334,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                         }
                     }
                     const uint32_t col = lane_base + s * kSetCols + ks * 8;
-                    if (!(a.dbg & 2)) {
                     tmem_st8(col + 0 * 32, ih);
                     tmem_st8(col + 1 * 32, il);
                     tmem_st8(col + 2 * 32, qh);
                     tmem_st8(col + 3 * 32, ql);
-                    }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;");
@@ -359,9 +357,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         const long long n_out = a.n_in / kTcD;
         float2* stg = reinterpret_cast<float2*>(s_epi + (warp - kEpiWarp0) * kEpiBytes);      // [32 rows][32 + 1 outputs], warp-private
         uint32_t tile = 0;
-        for (long long w = w_lo; w < w_hi; w += w_step, ++tile) {
-            const int rb = (int)(w % a.row_blocks);
-            const long long n0 = (w / a.row_blocks) * N;
+        for (long long w = w_lo; w < w_hi; ++w, ++tile) {
+            const int rb = (int)(w / a.tiles_per_block);
+            const long long n0 = (w % a.tiles_per_block) * N;
             const uint32_t buf = kAccBufs == 2 ? (tile & 1) : 0, use = kAccBufs == 2 ? (tile >> 1) : tile;
             const int row = rb * kRows + q * 32 + lane;
             bar_wait(bar0 + 8 * (kBarTile + buf), use & 1);
@@ -371,11 +369,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             if (a.nco && row < a.rows) np = a.nco[row];
 #pragma unroll 1
             for (int h = 0; h < N / 32; ++h) {
-                uint32_t vi[32] = {}, vq[32] = {};
-                if (!(a.dbg & 8)) {
+                uint32_t vi[32], vq[32];
                 tmem_ld32(taddr + h * 32, vi);
                 tmem_ld32(taddr + N + h * 32, vq);
-                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (h == N / 32 - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -478,7 +474,7 @@ int long_tc_tile(int D, int T) {
     if (D != kTcD) return 0;
     // one tcgen05.mma (M = 128, K = 8) costs ~70 cycles for any N <= 128 (tools/probes/umma_rate.cu, umma_ts_probe.cu), so wide
     // tiles win as long as the band matrix leaves room for the raw-input ring
-    int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : 128;
+    int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : 64;
     for (int N : {128, 64, 32})
         if (N <= want && tc_slots(N, T)) return N;
     return 0;
@@ -558,13 +554,11 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     a.in = la.in; a.hist = la.hist; a.out = la.out;
     a.n_in = la.n_in; a.in_pitch = in_pitch; a.out_pitch = la.out_pitch; a.out_off = la.out_off; a.k_abs = la.k_abs;
     a.nco = la.nco; a.rows = la.rows_in; a.s16 = la.s16; a.T = s->T; a.H = st.H; a.chunks = s->chunks; a.J = s->J; a.slots = 4; a.box_rows = s->box_rows;
-    a.dbg = getenv("NVX_TC_DBG") ? atoi(getenv("NVX_TC_DBG")) : 0;
     // 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by construction)
     if (((uintptr_t)la.in & 15) || ((in_pitch * (la.s16 ? 4 : 8)) & 15)) return cudaErrorNotSupported;
     const long long n_out = la.n_in / s->D;
     a.tiles_per_block = (n_out + s->N - 1) / s->N;
-    a.row_blocks = (la.rows_in + kRows - 1) / kRows;
-    a.work = (long long)a.row_blocks * a.tiles_per_block;
+    a.work = (long long)((la.rows_in + kRows - 1) / kRows) * a.tiles_per_block;
     if (a.work <= 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

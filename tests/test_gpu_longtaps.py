@@ -3,8 +3,6 @@ than fir1cpp.C:8 / fir2cpp.C:22 / fir3cpp.h:16) through the long-tap path (one r
 
 The unmodified reference cannot run other tap sets, so parity is against the C restatement of the three stages
 (oracle/navtex_oracle.c, h1/h2/h3 parameters), which is pinned to the compiled reference at the default taps."""
-import os
-
 import numpy as np
 import pytest
 from scipy import signal
@@ -64,16 +62,22 @@ def test_long_taps_against_restated_oracle(lengths):
 
 
 @pytest.fixture
-def tensor_core_stage1(monkeypatch):
-    """Stage 1 of the long-tap path on the tensor cores (fir_long_tc.cu; the engine reads NVX_LONG_TC when it is created)."""
-    monkeypatch.setenv("NVX_LONG_TC", "1")
+def cuda_core_stage1(monkeypatch):
+    """Stage 1 of the long-tap path on the CUDA-core kernel (the engine reads NVX_LONG_TC when it is created; by default
+    stage 1 runs on the tensor cores, fir_long_tc.cu)."""
+    monkeypatch.setenv("NVX_LONG_TC", "0")
 
 
-@pytest.mark.parametrize("lengths", [(255, 255, 255), (127, 255, 90), (511, 255, 255)])
-def test_long_taps_tensor_core_stage1(tensor_core_stage1, lengths):
-    """tcgen05 3xTF32 Toeplitz GEMM for stage 1: same 1e-5 bar, bits and messages against the restated oracle; int16 input
-    and a ragged stream count (3 of a 128-row tile) go through the general loader, float input through the fast one."""
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (101, 383, 129)])
+def test_long_taps_cuda_core_stage1(cuda_core_stage1, lengths):
     test_long_taps_against_restated_oracle(lengths)
+
+
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (127, 255, 90), (511, 255, 255), (1000, 47, 71)])
+def test_long_taps_tensor_core_stage1(monkeypatch, lengths):
+    """tcgen05 3xTF32 Toeplitz GEMM for stage 1 (the default; 1000 taps loads the band matrix in many TMA boxes): same 1e-5 bar as the
+    oracle tests above; here a ragged stream count (130 = one full 128-row tile + 2), float input, and blockings that move the
+    tile boundaries -- equal to rounding, not bit for bit -- and the CUDA-core stage 1 on the same input."""
     taps = designs(*lengths)
     n = 252000 * 2
     rng = np.random.default_rng(27)
@@ -92,7 +96,7 @@ def test_long_taps_tensor_core_stage1(tensor_core_stage1, lengths):
         eng.close()
         y = np.concatenate(ys, axis=2)
         assert np.abs(y - want[:, :, : y.shape[2]]).max() <= REL_TOL * scale, blk
-    os.environ["NVX_LONG_TC"] = "0"               # and against the CUDA-core stage 1 on the same input
+    monkeypatch.setenv("NVX_LONG_TC", "0")        # and against the CUDA-core stage 1 on the same input
     cc = engine.Engine(130, n, taps=taps)
     cc.push_host(x)
     assert np.abs(cc.read_y3() - want).max() <= REL_TOL * scale
@@ -100,9 +104,9 @@ def test_long_taps_tensor_core_stage1(tensor_core_stage1, lengths):
 
 
 @pytest.mark.parametrize("lengths", [(255, 255, 255), (61, 75, 111)])
-def test_long_taps_blocking_and_format_invariance(lengths):
-    """Histories are carried per stage (long path) / recomputed from a longer input tail (medium class): any blocking,
-    float or int16 input, gives bit-identical 900 Hz samples."""
+def test_long_taps_blocking_and_format_invariance(cuda_core_stage1, lengths):
+    """Histories are carried per stage (long path, CUDA-core kernels) / recomputed from a longer input tail (medium class):
+    any blocking, float or int16 input, gives bit-identical 900 Hz samples."""
     taps = designs(*lengths)
     n = 252000 * 2
     rng = np.random.default_rng(23)
