@@ -34,10 +34,10 @@
 //   * warp 8, issuer: one thread issues the 2 planes x 3 terms x 4 k-steps tcgen05.mma.kind::tf32 (A in TMEM, B = band
 //     matrix in shared memory) per chunk and commits them to the A set's empty barrier; the last chunk of a tile also commits
 //     to the tile barrier;
-//   * warps 12..15, epilogue: read the tile's 2 N accumulator columns (tcgen05.ld), release the accumulators (two buffers
-//     at N = 64: tile t + 1 accumulates while tile t is read), apply the NCO rotation of both channels
-//     (fir2cpp.C:112-128) and store one 63 kHz row per channel.
-// TMEM map (512 columns): [0, 256) accumulators, [256, 512) two A sets of 4 x 32 columns.
+//   * warps 12..15, epilogue: dump the tile's 2 N accumulator columns to shared memory (tcgen05.ld, lane = row) and release
+//     the accumulators at once, then, lane = output, apply the NCO rotation of both channels (fir2cpp.C:112-128) and store
+//     one 63 kHz row per channel, 256 contiguous bytes per instruction.
+// TMEM map (512 columns): [0, 2 N) accumulators, [128, 512) three A sets of 4 x 32 columns.
 // The accumulation order inside the tensor core is fixed per tile position, so results are deterministic for a given
 // blocking but not bit-identical across blockings (tile boundaries move); the tests hold this path to the 1e-5 bar.
 #include <cuda.h>
@@ -66,12 +66,11 @@ constexpr int kEpiWarp0 = kLoaderWarp0 + kLoaderWarps;
 constexpr int kTcThreads = 32 * (kConvWarps + 1 + kLoaderWarps + 4);
 constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 128 B]
 constexpr int kMaxSlots = 8;
-constexpr int kEpiBytes = 32 * 33 * 8;     // epilogue staging tile: [32 rows][32 + 1 outputs] float2
+constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 N + 4] floats (row pitch = 4 words mod 32: conflict-free)
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kTcD = NVX_D1;
 constexpr int kShift = kKB / kTcD;         // band rows per chunk
-constexpr uint32_t kAccCols = 256;         // accumulators: columns [0, 256)
-constexpr uint32_t kACol0 = 256;           // A sets: columns [256, 512)
+constexpr int kMaxSets = 3;                // A sets in tensor memory
 constexpr uint32_t kSetCols = 128;         // {I_hi, I_lo, Q_hi, Q_lo} x 32 columns
 
 __constant__ float2 c_tc_nco[kNcoPeriod];  // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
@@ -140,17 +139,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // mbarriers: band matrix loaded; per raw slot full (TMA -> converters) / empty (converters -> producer); per A set full
-// (converters -> issuer) / empty (tensor core -> converters); per accumulator buffer tile accumulated (tensor core ->
-// epilogue) / accumulators read (epilogue -> issuer)
+// (converters -> issuer) / empty (tensor core -> converters); tile accumulated (tensor core -> epilogue) / accumulators
+// dumped (epilogue -> issuer)
 enum {
     kBarG = 0,
     kBarRawFull = 1,
     kBarRawEmpty = kBarRawFull + kMaxSlots,
     kBarAFull = kBarRawEmpty + kMaxSlots,
-    kBarAEmpty = kBarAFull + 2,
-    kBarTile = kBarAEmpty + 2,
-    kBarTmemFree = kBarTile + 2,
-    kBars = kBarTmemFree + 2
+    kBarAEmpty = kBarAFull + kMaxSets,
+    kBarTile = kBarAEmpty + kMaxSets,
+    kBarTmemFree = kBarTile + 1,
+    kBars = kBarTmemFree + 1
 };
 
 // round to TF32 (10-bit mantissa, nearest, ties away) with integer ops; the remainder is exact in FP32
@@ -162,13 +161,20 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 template <int N>
 __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int kAccBufs = 2 * N * 2 <= (int)kAccCols ? 2 : 1;      // accumulator buffers of 2 N columns
+    // TMEM map: accumulators (I | Q) in columns [0, 2 N), A sets of 128 columns at the top.  Three A sets, not two plus a
+    // second accumulator buffer: the round trip "MMAs of a set done -> converters refill it -> next MMAs issued" takes ~3200
+    // cycles against ~1450 cycles of MMAs per chunk, so two sets leave the tensor core idle a third of the time, while the
+    // accumulators are only held for the few hundred cycles the epilogue needs to dump them to shared memory.
+    constexpr int kSets = (512 - 2 * N) / (int)kSetCols < kMaxSets ? (512 - 2 * N) / (int)kSetCols : kMaxSets;
+    constexpr uint32_t kACol0 = 512 - kSets * kSetCols;
+    constexpr int kDumpPitch = 2 * N + kDumpPad;             // floats per dump row
     const int g_bytes = a.J * 128;                          // one part of the band matrix (a multiple of 1024)
     uint8_t* s_gh = smem;
     uint8_t* s_gl = smem + g_bytes;
     uint8_t* s_raw = smem + 2 * g_bytes;                    // ring of raw-input slots
-    uint8_t* s_epi = s_raw + a.slots * kSlotBytes;          // one staging tile per epilogue warp
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 4 * kEpiBytes);
+    float* s_dump = reinterpret_cast<float*>(s_raw + a.slots * kSlotBytes);      // the tile's accumulators, [row][I cols | Q cols]
+    float2* s_nco = reinterpret_cast<float2*>(s_dump + kRows * kDumpPitch);      // the 9-entry reference NCO table
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_nco + 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars);
     const uint32_t bar0 = s_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,12 +186,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             int count = 1;
             if (i >= kBarRawFull && i < kBarRawFull + kMaxSlots) count = 32 * kLoaderWarps;
             if (i >= kBarRawEmpty && i < kBarRawEmpty + kMaxSlots) count = kConvWarps / slots_per_chunk;
-            if (i >= kBarAFull && i < kBarAFull + 2) count = kConvWarps;
+            if (i >= kBarAFull && i < kBarAFull + kMaxSets) count = kConvWarps;
             if (i >= kBarTmemFree) count = 4;
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(count));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < kNcoPeriod) s_nco[threadIdx.x] = c_tc_nco[threadIdx.x];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -259,10 +266,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             bar_wait(bar0 + 8 * kBarG, 0);
             uint32_t s = 0, ph = 0, tile = 0;
             for (long long w = w_lo; w < w_hi; ++w, ++tile) {
-                const uint32_t buf = kAccBufs == 2 ? (tile & 1) : 0, use = kAccBufs == 2 ? (tile >> 1) : tile;
-                bar_wait(bar0 + 8 * (kBarTmemFree + buf), (use & 1) ^ 1);     // the epilogue has read this buffer's last tile
+                bar_wait(bar0 + 8 * kBarTmemFree, (tile & 1) ^ 1);            // the epilogue has dumped the previous tile
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t acc = tmem + buf * 2 * N;
+                const uint32_t acc = tmem;
                 for (int c = 0; c < a.chunks; ++c) {
                     bar_wait(bar0 + 8 * (kBarAFull + s), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -278,8 +284,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                                 umma_ts_tf32(acc + p * N, at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
                                              umma_desc((term == 2 ? gl : gh) + k * kUmmaK * 4), idesc, (c | term | k) ? 1u : 0u);
                     umma_commit(bar0 + 8 * (kBarAEmpty + s));
-                    if (c == a.chunks - 1) umma_commit(bar0 + 8 * (kBarTile + buf));
-                    if (++s == 2) { s = 0; ph ^= 1; }
+                    if (c == a.chunks - 1) umma_commit(bar0 + 8 * kBarTile);
+                    if (++s == kSets) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -346,81 +352,77 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                     bar_arrive(bar0 + 8 * (kBarAFull + s));
                     bar_arrive(bar0 + 8 * (kBarRawEmpty + slot));
                 }
-                if (++s == 2) { s = 0; ph ^= 1; }
+                if (++s == kSets) { s = 0; ph ^= 1; }
                 slot += slots_per_chunk;
                 if (slot >= a.slots) { slot -= a.slots; sph ^= 1; }
             }
         }
     } else {
-        // epilogue warp: TMEM lanes 32 q .. 32 q + 31 (q = warp % 4, the lanes this warp may address) = rows of the tile
+        // epilogue warp: TMEM lanes 32 q .. 32 q + 31 (q = warp % 4, the lanes this warp may address) = rows of the tile.
+        // Phase 1, lane = row: dump the row's 2 N accumulator columns to shared memory and release the accumulators.
+        // Phase 2, lane = output: per row read (I, Q), apply the NCO rotation of both channels -- output k sits at 63 kHz
+        // clock tick k_abs + k; channel c gets y * (cos - j sin)(2 pi tick f_c / 63000), fir2cpp.C:112-128 -- and store 256
+        // contiguous bytes per instruction (one row per lane was measured 1.5x slower for the whole kernel).
         const int q = warp & 3;
         const long long n_out = a.n_in / kTcD;
-        float2* stg = reinterpret_cast<float2*>(s_epi + (warp - kEpiWarp0) * kEpiBytes);      // [32 rows][32 + 1 outputs], warp-private
+        float* my_row = s_dump + (q * 32 + lane) * kDumpPitch;
+        const float* rows0 = s_dump + (q * 32) * kDumpPitch;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t tile = 0;
         for (long long w = w_lo; w < w_hi; ++w, ++tile) {
             const int rb = (int)(w / a.tiles_per_block);
             const long long n0 = (w % a.tiles_per_block) * N;
-            const uint32_t buf = kAccBufs == 2 ? (tile & 1) : 0, use = kAccBufs == 2 ? (tile >> 1) : tile;
-            const int row = rb * kRows + q * 32 + lane;
-            bar_wait(bar0 + 8 * (kBarTile + buf), use & 1);
+            bar_wait(bar0 + 8 * kBarTile, tile & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * 2 * N;
-            NcoParam np = {};
-            if (a.nco && row < a.rows) np = a.nco[row];
+#pragma unroll 1
+            for (int h = 0; h < 2 * N / 32; ++h) {
+                uint32_t v[32];
+                tmem_ld32(taddr + h * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(my_row + h * 32 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) bar_arrive(bar0 + 8 * kBarTmemFree);          // the accumulators may be overwritten
+            const int row0 = rb * kRows + q * 32;
+            const int r_max = a.rows - row0 < 32 ? a.rows - row0 : 32;
 #pragma unroll 1
             for (int h = 0; h < N / 32; ++h) {
-                uint32_t vi[32], vq[32];
-                tmem_ld32(taddr + h * 32, vi);
-                tmem_ld32(taddr + N + h * 32, vq);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (h == N / 32 - 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    __syncwarp();
-                    if (lane == 0) bar_arrive(bar0 + 8 * (kBarTmemFree + buf));      // the accumulators may be overwritten
-                }
-                // NCO mix: output k sits at 63 kHz clock tick k_abs + k; channel c gets y * (cos - j sin)(2 pi tick f_c / 63000).
-                // One channel at a time: lane = row mixes its 32 outputs into the staging tile, then lane = output and every
-                // store instruction writes 256 contiguous bytes of one row (16 bytes x 32 rows per instruction measured 3x slower)
-                const long long nh = n0 + h * 32;
-                const long long tick0 = a.k_abs + nh;
-                const long long r9 = tick0 % kNcoPeriod, rden = tick0 % kNcoDen;
-                const int k9_0 = (int)(r9 < 0 ? r9 + kNcoPeriod : r9), kden_0 = (int)(rden < 0 ? rden + kNcoDen : rden);
-                const int row0 = rb * kRows + q * 32;
-                const int r_max = a.rows - row0 < 32 ? a.rows - row0 : 32;
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    int k9 = k9_0, kden = kden_0;
-                    const int num = c ? np.num[1] : np.num[0];
-                    const float conj = c ? -1.f : 1.f;                   // "490": conjugate rotation (fir2cpp.C:121-124)
+                const int n = h * 32 + lane;
+                if (n0 + n >= n_out) continue;
+                const long long tick = a.k_abs + n0 + n;
+                float2* dst = a.out + (size_t)(2 * row0) * a.out_pitch + a.out_off + n0 + n;
+                if (a.nco) {
+                    const long long rden = tick % kNcoDen;
+                    const long long kden = rden < 0 ? rden + kNcoDen : rden;
+#pragma unroll 2
+                    for (int r = 0; r < r_max; ++r, dst += 2 * a.out_pitch) {
+                        const NcoParam np = a.nco[row0 + r];
+                        const float2 y = make_float2(rows0[r * kDumpPitch + n], rows0[r * kDumpPitch + N + n]);
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) {
-                        float2 rot;
-                        if (a.nco) {
-                            const int phs = (int)(((long long)kden * num) % kNcoDen);
+                        for (int c = 0; c < 2; ++c) {
+                            const int phs = (int)((kden * np.num[c]) % kNcoDen);
                             float tt = (float)phs * (2.0f / kNcoDen);
                             if (tt > 1.0f) tt -= 2.0f;
                             float sn, cs;
                             sincospif(tt, &sn, &cs);
-                            rot = make_float2(cs, -sn);
-                        } else {
-                            rot = c_tc_nco[k9];
-                            rot.y *= conj;
+                            dst[c * a.out_pitch] = make_float2(fmaf(y.y, sn, y.x * cs), fmaf(-y.x, sn, y.y * cs));
                         }
-                        const float2 y = make_float2(__uint_as_float(vi[n]), __uint_as_float(vq[n]));
-                        stg[lane * 33 + n] = make_float2(fmaf(-y.y, rot.y, y.x * rot.x), fmaf(y.x, rot.y, y.y * rot.x));
-                        if (++k9 == kNcoPeriod) k9 = 0;
-                        if (++kden == kNcoDen) kden = 0;
                     }
-                    __syncwarp();
-                    if (nh + lane < n_out) {
-                        float2* dst = a.out + (size_t)(2 * row0 + c) * a.out_pitch + a.out_off + nh + lane;
-                        const size_t row_step = (size_t)2 * a.out_pitch;
+                } else {
+                    const long long r9 = tick % kNcoPeriod;
+                    const float2 rot = s_nco[r9 < 0 ? r9 + kNcoPeriod : r9];       // (cos, -sin); "490" uses the conjugate (fir2cpp.C:121-124)
 #pragma unroll 4
-                        for (int r = 0; r < r_max; ++r) dst[r * row_step] = stg[r * 33 + lane];
+                    for (int r = 0; r < r_max; ++r, dst += 2 * a.out_pitch) {
+                        const float2 y = make_float2(rows0[r * kDumpPitch + n], rows0[r * kDumpPitch + N + n]);
+                        dst[0] = make_float2(fmaf(-y.y, rot.y, y.x * rot.x), fmaf(y.x, rot.y, y.y * rot.x));
+                        dst[a.out_pitch] = make_float2(fmaf(y.y, rot.y, y.x * rot.x), fmaf(-y.x, rot.y, y.y * rot.x));
                     }
-                    __syncwarp();
                 }
             }
+            __syncwarp();                                   // the dump rows are overwritten by the next tile
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -442,7 +444,9 @@ float tf32_rna(float x) {                  // round to nearest, ties away, 10-bi
 
 int tc_chunks(int N, int T) { return (kTcD * (N - 1) + T + kKB - 1) / kKB; }
 int tc_band_rows(int N, int T) { return N + kShift * (tc_chunks(N, T) - 1); }
-size_t tc_smem(int N, int T, int slots) { return (size_t)2 * tc_band_rows(N, T) * 128 + (size_t)slots * kSlotBytes + 4 * kEpiBytes + kBars * 8 + 16; }
+size_t tc_smem(int N, int T, int slots) {
+    return (size_t)2 * tc_band_rows(N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * N + kDumpPad) * 4 + 128 + kBars * 8 + 16;
+}
 int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 rows, dividing J
     int best = 1;
     for (int d = 1; d <= 32; ++d)
@@ -475,7 +479,7 @@ int long_tc_tile(int D, int T) {
     // one tcgen05.mma (M = 128, K = 8) costs ~70 cycles for any N <= 128 (tools/probes/umma_rate.cu, umma_ts_probe.cu), so wide
     // tiles win as long as the band matrix leaves room for the raw-input ring
     int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : 64;
-    for (int N : {128, 64, 32})
+    for (int N : {64, 32})
         if (N <= want && tc_slots(N, T)) return N;
     return 0;
 }
@@ -563,7 +567,7 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return s->N == 128 ? launch_tc<128>(a, sms, stream) : s->N == 64 ? launch_tc<64>(a, sms, stream) : launch_tc<32>(a, sms, stream);
+    return s->N == 64 ? launch_tc<64>(a, sms, stream) : launch_tc<32>(a, sms, stream);
 }
 
 }  // namespace nvx

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128, 1) probe(const float* a, const float* b, 
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_ts(tmem + p * NN, tmem + a_col + (s * 4 + 2 * p + (term == 1 ? 1 : 0)) * 32 + k * 8,
-                                umma_desc(s_u32(smem) + ((r % 12) + (term == 2 ? 16 : 0)) * 1024 + k * 32), idesc, 1u);
+                                umma_desc(s_u32(smem) + ((r % 4) + (term == 2 ? 8 : 0)) * 1024 + k * 32), idesc, 1u);
             umma_commit(s_u32(&bars[2 + s]));
         }
         const int last = rounds - 1;
