@@ -99,6 +99,11 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n"
                  ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void bar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -110,9 +115,10 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, u
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+                   "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
 }
 
 // general loader for tiles that touch the carried history
@@ -177,7 +183,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_nco + 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars);
     const uint32_t bar0 = s_u32(bars);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index made provably warp-uniform: the issuer warp below runs its loops on all lanes and elects one to issue, so that
+    // the descriptors are computed in uniform registers (a lane == 0 branch makes ptxas wrap every tcgen05.mma in a
+    // R2UR "waterfall" loop: ~15 instructions and ~80 cycles per MMA, which was the kernel's bound)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     // float2 input: a slot is 16 samples and each half of the converters owns one slot of a chunk; short2: 32 samples, shared
     const int slots_per_chunk = a.s16 ? 1 : 2;
 
@@ -251,7 +260,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             }
         }
     } else if (warp == kIssuerWarp) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        if (leader) {
             // the constant band matrix, once per CTA (TMA boxes of box_rows <= 256 rows, a divisor of J)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * kBarG), "r"(2 * g_bytes) : "memory");
             for (int j = 0; j < a.J; j += a.box_rows) {
@@ -260,21 +270,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                              ::"r"(s_u32(s_gl + j * 128)), "l"(&a.map_gl), "r"(0), "r"(j), "r"(bar0 + 8 * kBarG) : "memory");
             }
-            // cute::UMMA::InstrDescriptor: c_format F32 = 1 at [4,6), a / b format TF32 = 2 at [7,10) / [10,13), K-major both,
-            // n_dim = N >> 3 at [17,23), m_dim = 128 >> 4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-            bar_wait(bar0 + 8 * kBarG, 0);
-            uint32_t s = 0, ph = 0, tile = 0;
-            for (long long w = w_lo; w < w_hi; ++w, ++tile) {
-                bar_wait(bar0 + 8 * kBarTmemFree, (tile & 1) ^ 1);            // the epilogue has dumped the previous tile
+        }
+        // cute::UMMA::InstrDescriptor: c_format F32 = 1 at [4,6), a / b format TF32 = 2 at [7,10) / [10,13), K-major both,
+        // n_dim = N >> 3 at [17,23), m_dim = 128 >> 4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+        bar_wait(bar0 + 8 * kBarG, 0);
+        uint32_t s = 0, ph = 0, tile = 0;
+        for (long long w = w_lo; w < w_hi; ++w, ++tile) {
+            bar_wait(bar0 + 8 * kBarTmemFree, (tile & 1) ^ 1);            // the epilogue has dumped the previous tile
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t acc = tmem;
+            for (int c = 0; c < a.chunks; ++c) {
+                bar_wait(bar0 + 8 * (kBarAFull + s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t acc = tmem;
-                for (int c = 0; c < a.chunks; ++c) {
-                    bar_wait(bar0 + 8 * (kBarAFull + s), ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t at = tmem + kACol0 + s * kSetCols;
-                    const uint32_t goff = (uint32_t)(a.chunks - 1 - c) * (kShift * 128);      // chunk c of B = G shifted by whole atoms
-                    const uint32_t gh = s_u32(s_gh) + goff, gl = s_u32(s_gl) + goff;
+                const uint32_t at = tmem + kACol0 + s * kSetCols;
+                const uint32_t goff = (uint32_t)(a.chunks - 1 - c) * (kShift * 128);      // chunk c of B = G shifted by whole atoms
+                const uint32_t gh = s_u32(s_gh) + goff, gl = s_u32(s_gl) + goff;
+                if (leader) {
 #pragma unroll
                     for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -285,8 +297,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                                              umma_desc((term == 2 ? gl : gh) + k * kUmmaK * 4), idesc, (c | term | k) ? 1u : 0u);
                     umma_commit(bar0 + 8 * (kBarAEmpty + s));
                     if (c == a.chunks - 1) umma_commit(bar0 + 8 * kBarTile);
-                    if (++s == kSets) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == kSets) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp < kConvWarps) {
@@ -303,48 +316,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             const bool fast = t_base >= 0;
             for (int c = 0; c < a.chunks; ++c) {
                 bar_wait(bar0 + 8 * (kBarRawFull + slot), sph);                 // raw samples landed
-                bar_wait(bar0 + 8 * (kBarAEmpty + s), ph ^ 1);                  // the MMAs that read this A set are done
-                asm volatile("tcgen05.fence::after_thread_sync;");
+                // read and split BEFORE waiting for the A set: the round trip "set free -> set full" is then only the
+                // eight tcgen05.st of this thread (the conversion itself overlaps the MMAs that still read the set)
                 const uint8_t* row = s_raw + slot * kSlotBytes + r * 128;
+                float ih[16], il[16], qh[16], ql[16];
+                if (fast) {
+                    if (a.s16) {                                                // 16-byte units 4 kh .. 4 kh + 3: 4 samples each
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {                                // 8 samples = one MMA k-step
-                    float ih[8], il[8], qh[8], ql[8];
-                    if (fast) {
-                        if (a.s16) {                                            // 16-byte units 4 kh + 2 ks, + 1: 4 samples each
+                        for (int u = 0; u < 4; ++u) {
+                            const int4 v = *reinterpret_cast<const int4*>(row + (((4 * kh + u) ^ (r & 7)) << 4));
+                            const int wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int4 v = *reinterpret_cast<const int4*>(row + (((4 * kh + 2 * ks + u) ^ (r & 7)) << 4));
-                                const int wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    split_tf32((float)(short)(wv[j] & 0xFFFF), ih[4 * u + j], il[4 * u + j]);
-                                    split_tf32((float)(wv[j] >> 16), qh[4 * u + j], ql[4 * u + j]);
-                                }
-                            }
-                        } else {                                                // 16-byte units 4 ks .. 4 ks + 3: 2 samples each
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float4 v = *reinterpret_cast<const float4*>(row + (((4 * ks + u) ^ (r & 7)) << 4));
-                                split_tf32(v.x, ih[2 * u], il[2 * u]);
-                                split_tf32(v.y, qh[2 * u], ql[2 * u]);
-                                split_tf32(v.z, ih[2 * u + 1], il[2 * u + 1]);
-                                split_tf32(v.w, qh[2 * u + 1], ql[2 * u + 1]);
+                            for (int j = 0; j < 4; ++j) {
+                                split_tf32((float)(short)(wv[j] & 0xFFFF), ih[4 * u + j], il[4 * u + j]);
+                                split_tf32((float)(wv[j] >> 16), qh[4 * u + j], ql[4 * u + j]);
                             }
                         }
-                    } else {
+                    } else {                                                    // 16-byte units 0 .. 7: 2 samples each
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float2 v = tc_load(a, rb * kRows + r, t_base + (long long)c * kKB + kh * 16 + ks * 8 + j);
-                            split_tf32(v.x, ih[j], il[j]);
-                            split_tf32(v.y, qh[j], ql[j]);
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 v = *reinterpret_cast<const float4*>(row + ((u ^ (r & 7)) << 4));
+                            split_tf32(v.x, ih[2 * u], il[2 * u]);
+                            split_tf32(v.y, qh[2 * u], ql[2 * u]);
+                            split_tf32(v.z, ih[2 * u + 1], il[2 * u + 1]);
+                            split_tf32(v.w, qh[2 * u + 1], ql[2 * u + 1]);
                         }
                     }
-                    const uint32_t col = lane_base + s * kSetCols + ks * 8;
-                    tmem_st8(col + 0 * 32, ih);
-                    tmem_st8(col + 1 * 32, il);
-                    tmem_st8(col + 2 * 32, qh);
-                    tmem_st8(col + 3 * 32, ql);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 v = tc_load(a, rb * kRows + r, t_base + (long long)c * kKB + kh * 16 + j);
+                        split_tf32(v.x, ih[j], il[j]);
+                        split_tf32(v.y, qh[j], ql[j]);
+                    }
                 }
+                bar_wait(bar0 + 8 * (kBarAEmpty + s), ph ^ 1);                  // the MMAs that read this A set are done
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t col = lane_base + s * kSetCols;
+                tmem_st16(col + 0 * 32, ih);
+                tmem_st16(col + 1 * 32, il);
+                tmem_st16(col + 2 * 32, qh);
+                tmem_st16(col + 3 * 32, ql);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
