@@ -60,10 +60,11 @@ constexpr int kKB = 32;                    // floats per 128-byte swizzle row = 
 constexpr int kUmmaK = 8;                  // tf32: 32 bytes per instruction along K
 constexpr int kConvWarps = 8;
 constexpr int kIssuerWarp = kConvWarps;
-constexpr int kLoaderWarp0 = kConvWarps + 1;
-constexpr int kLoaderWarps = 3;
+constexpr int kTmaWarp = kConvWarps + 1;
+constexpr int kLoaderWarp0 = kConvWarps + 2;
+constexpr int kLoaderWarps = 2;
 constexpr int kEpiWarp0 = kLoaderWarp0 + kLoaderWarps;
-constexpr int kTcThreads = 32 * (kConvWarps + 1 + kLoaderWarps + 4);
+constexpr int kTcThreads = 32 * (kConvWarps + 2 + kLoaderWarps + 4);
 constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 128 B]
 constexpr int kMaxSlots = 8;
 constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 N + 4] floats (row pitch = 4 words mod 32: conflict-free)
@@ -77,6 +78,7 @@ __constant__ float2 c_tc_nco[kNcoPeriod];  // (cos, -sin)(2 pi k 14000 / 63000),
 
 struct TcArgs {
     CUtensorMap map_gh, map_gl;            // band matrix G[J][32], high / low TF32 parts
+    CUtensorMap map_x;                     // this block as [rows][2 n_in] floats / shorts, box = one slot (128 B x 128 rows, SWIZZLE_128B)
     const void* in;
     const float2* hist;
     float2* out;
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < kBars; ++i) {
             int count = 1;
+            // chunks alternate between the cp.async loaders (one arrival per thread) and the TMA thread (which arrives for as many)
             if (i >= kBarRawFull && i < kBarRawFull + kMaxSlots) count = 32 * kLoaderWarps;
             if (i >= kBarRawEmpty && i < kBarRawEmpty + kMaxSlots) count = kConvWarps / slots_per_chunk;
             if (i >= kBarAFull && i < kBarAFull + kMaxSets) count = kConvWarps;
@@ -217,7 +220,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     const long long per = (a.work + gridDim.x - 1) / gridDim.x;
     const long long w_lo = (long long)blockIdx.x * per, w_hi = w_lo + per < a.work ? w_lo + per : a.work;
 
-    if (warp >= kLoaderWarp0 && warp < kLoaderWarp0 + kLoaderWarps) {
+    // The raw window of a tile goes through the slot ring chunk by chunk; chunks are numbered g = 0, 1, ... across the CTA's
+    // tiles and alternate between two independent paths into the same swizzled layout -- even g: one 2-D TMA box per slot
+    // (its 128-byte rows cap the TMA unit near 14 B/clk per SM), odd g: 16-byte cp.async pieces from two loader warps (capped
+    // at about the same rate by the SM's outstanding-load limit) -- because neither alone keeps up with the tensor core.
+    const int ring_chunks = a.slots / slots_per_chunk;
+    if (warp == kTmaWarp) {
+        if (lane == 0) {
+            long long g = 0;
+            for (long long w = w_lo; w < w_hi; ++w) {
+                const int rb = (int)(w / a.tiles_per_block);
+                const long long n0 = (w % a.tiles_per_block) * N;
+                const long long t_base = (long long)kTcD * n0 + kTcD - a.T;      // first input of the tile's window (block-relative)
+                const bool fast = t_base >= 0;
+                for (int c = 0; c < a.chunks; ++c, ++g) {
+                    if (g & 1) continue;
+                    const int slot = (int)(g % ring_chunks) * slots_per_chunk;
+                    const uint32_t ph = (uint32_t)(g / ring_chunks) & 1;
+                    for (int h = 0; h < slots_per_chunk; ++h) {
+                        const uint32_t full = bar0 + 8 * (kBarRawFull + slot + h);
+                        bar_wait(bar0 + 8 * (kBarRawEmpty + slot + h), ph ^ 1);
+                        if (fast) {
+                            // x coordinate in 32-bit (float) / 16-bit (short) elements, two per sample; rows past the last
+                            // stream and samples past the block end are zero-filled by the TMA unit
+                            const int x0 = (int)(2 * (t_base + (long long)c * kKB + h * 16));
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(kSlotBytes) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                         ::"r"(s_u32(s_raw + (slot + h) * kSlotBytes)), "l"(&a.map_x), "r"(x0), "r"(rb * kRows), "r"(full) : "memory");
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps - 1) : "memory");
+                        } else {                            // the converters load this chunk themselves
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps) : "memory");
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= kLoaderWarp0 && warp < kLoaderWarp0 + kLoaderWarps) {
         // loaders: 16-byte cp.async pieces (L1 bypassed), zero fill past the last stream / the block end, written in the
         // 128-byte-swizzled slot layout: piece (row r, unit u) -> r * 128 + ((u ^ (r % 8)) * 16)
         const int tid = (warp - kLoaderWarp0) * 32 + lane;
@@ -226,14 +264,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         const int u16 = tid % units, r0 = tid / units, r_step = kLoaders / units;
         const int esz = a.s16 ? 4 : 8;                            // bytes per sample
         const int per_piece = 16 / esz;                           // samples per piece
-        int slot = 0;
-        uint32_t ph = 0;
+        long long g = 0;
         for (long long w = w_lo; w < w_hi; ++w) {
             const int rb = (int)(w / a.tiles_per_block);
             const long long n0 = (w % a.tiles_per_block) * N;
-            const long long t_base = (long long)kTcD * n0 + kTcD - a.T;      // first input of the tile's window (block-relative)
+            const long long t_base = (long long)kTcD * n0 + kTcD - a.T;
             const bool fast = t_base >= 0;
-            for (int c = 0; c < a.chunks; ++c) {
+            for (int c = 0; c < a.chunks; ++c, ++g) {
+                if (!(g & 1)) continue;
+                const int slot = (int)(g % ring_chunks) * slots_per_chunk;
+                const uint32_t ph = (uint32_t)(g / ring_chunks) & 1;
                 bar_wait(bar0 + 8 * (kBarRawEmpty + slot), ph ^ 1);
                 if (slots_per_chunk == 2) bar_wait(bar0 + 8 * (kBarRawEmpty + slot + 1), ph ^ 1);
                 if (fast) {
@@ -252,11 +292,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                     if (slots_per_chunk == 2)
                         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * (kBarRawFull + slot + 1)) : "memory");
                 } else {
-                    bar_arrive(bar0 + 8 * (kBarRawFull + slot));               // the converters load this part themselves
+                    bar_arrive(bar0 + 8 * (kBarRawFull + slot));               // the converters load this chunk themselves
                     if (slots_per_chunk == 2) bar_arrive(bar0 + 8 * (kBarRawFull + slot + 1));
                 }
-                slot += slots_per_chunk;
-                if (slot >= a.slots) { slot = 0; ph ^= 1; }
             }
         }
     } else if (warp == kIssuerWarp) {
@@ -570,8 +608,20 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     a.in = la.in; a.hist = la.hist; a.out = la.out;
     a.n_in = la.n_in; a.in_pitch = in_pitch; a.out_pitch = la.out_pitch; a.out_off = la.out_off; a.k_abs = la.k_abs;
     a.nco = la.nco; a.rows = la.rows_in; a.s16 = la.s16; a.T = s->T; a.H = st.H; a.chunks = s->chunks; a.J = s->J; a.slots = 4; a.box_rows = s->box_rows;
-    // 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by construction)
-    if (((uintptr_t)la.in & 15) || ((in_pitch * (la.s16 ? 4 : 8)) & 15)) return cudaErrorNotSupported;
+    // TMA boxes and 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by
+    // construction).  The block as a 2-D tensor of 32-bit (float2 input) or 16-bit (short2 input) elements, two per sample:
+    {
+        const size_t esz = la.s16 ? 2 : 4;
+        cuuint64_t dims[2] = {(cuuint64_t)(2 * la.n_in), (cuuint64_t)la.rows_in};
+        cuuint64_t strides[1] = {(cuuint64_t)in_pitch * 2 * esz};
+        cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)kRows};
+        cuuint32_t es[2] = {1, 1};
+        if (((uintptr_t)la.in & 15) || (strides[0] & 15) ||
+            s->enc(&a.map_x, la.s16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(la.in), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorNotSupported;
+    }
     const long long n_out = la.n_in / s->D;
     a.tiles_per_block = (n_out + s->N - 1) / s->N;
     a.work = (long long)((la.rows_in + kRows - 1) / kRows) * a.tiles_per_block;

@@ -20,6 +20,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+    return p != 0;
+}
+
 constexpr int kOp = 128 * 128;
 
 // mode 0: MMAs only; 1: warps 1..8 also store 64 floats per thread per round (the converters' traffic); order: 0 = (p, term, k), 1 = (p, k, term)
@@ -30,7 +36,7 @@ __global__ void __launch_bounds__(288, 1) rate(int rounds, int mode, int order, 
     uint8_t* s_b = smem + 8 * kOp;          // 2 parts x 256 rows
     __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < (8 * kOp + 2 * 256 * 128) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(&bars[i])));
@@ -46,7 +52,10 @@ __global__ void __launch_bounds__(288, 1) rate(int rounds, int mode, int order, 
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_slot;
     if (warp == 0) {
-        if (lane == 0) {
+        // the whole warp runs the loop and ONE elected lane issues: descriptors stay in uniform registers.  (A lane == 0 branch
+        // instead makes ptxas wrap every tcgen05.mma in an R2UR waterfall loop: measured 74.6 cycles per MMA for any N.)
+        const bool leader = elect_one();
+        {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const long long t0 = clock64();
             for (int r = 0; r < rounds; ++r) {
@@ -54,6 +63,7 @@ __global__ void __launch_bounds__(288, 1) rate(int rounds, int mode, int order, 
                 if (r >= 2) bar_wait(s_u32(&bars[s]), ((r >> 1) - 1) & 1);
                 const uint32_t op = s_u32(s_a + s * 4 * kOp);
                 const uint32_t bh = s_u32(s_b) + (r % 12) * 1024, bl = s_u32(s_b + 256 * 128) + (r % 12) * 1024;
+                if (!leader) continue;
                 if (order == 0) {
 #pragma unroll
                     for (int p = 0; p < 2; ++p)
@@ -76,7 +86,7 @@ __global__ void __launch_bounds__(288, 1) rate(int rounds, int mode, int order, 
             bar_wait(s_u32(&bars[(rounds - 1) & 1]), ((rounds - 1) >> 1) & 1);
             if (rounds >= 2) bar_wait(s_u32(&bars[rounds & 1]), ((rounds - 2) >> 1) & 1);
             const long long t1 = clock64();
-            if (blockIdx.x == 0) *cycles = t1 - t0;
+            if (blockIdx.x == 0 && leader) *cycles = t1 - t0;
         }
     } else if (mode == 1) {
         const int w = warp - 1;

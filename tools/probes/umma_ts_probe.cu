@@ -33,6 +33,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+    return p != 0;
+}
+
 constexpr int M = 128, N = 128, K = 32;
 
 // a: [M][K], b: [N][K] row-major in global memory; d: [M][N]
@@ -92,12 +98,14 @@ __global__ void __launch_bounds__(128, 1) probe(const float* a, const float* b, 
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     // rate: rounds of 2 planes x 3 terms x 4 k-steps, A tiles rotating over the 8 TMEM tiles, 2 rounds in flight
-    if (threadIdx.x == 0 && rounds > 0) {
+    if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0 && rounds > 0) {     // warp-uniform loop, one elected lane issues
+        const bool leader = elect_one();
         asm volatile("tcgen05.fence::after_thread_sync;");
         const long long t0 = clock64();
         for (int r = 0; r < rounds; ++r) {
             const int s = r & 1;
             if (r >= 2) bar_wait(s_u32(&bars[2 + s]), ((r >> 1) - 1) & 1);
+            if (!leader) continue;
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(128, 1) probe(const float* a, const float* b, 
         const int last = rounds - 1;
         bar_wait(s_u32(&bars[2 + (last & 1)]), (last >> 1) & 1);
         const long long t1 = clock64();
-        if (blockIdx.x == 0) *cycles = t1 - t0;
+        if (blockIdx.x == 0 && leader) *cycles = t1 - t0;
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
