@@ -409,8 +409,9 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         CU_TRY(long_carry(e->lhist[0][cur], d_x, n, e->lhist[0][nx], e->S, e->lst[0].H, n, s16, e->stream));
         la.in = e->y1buf; la.hist = e->lhist[1][cur]; la.out = e->y2buf; la.n_in = n / NVX_D1; la.out_pitch = p2;
         la.rows_in = e->channels; la.stage = 1; la.s16 = 0; la.nco = nullptr;
-        CU_TRY(e->ltc[1] ? long_tc_launch(e->ltc[1], la, e->lst[1], p1, e->stream)
-                         : long_launch(la, e->lst[1], p1, e->stream));  // 63 k -> 9 k
+        tc = e->ltc[1] ? long_tc_launch(e->ltc[1], la, e->lst[1], p1, e->stream) : cudaErrorNotSupported;
+        if (tc == cudaErrorNotSupported) tc = long_launch(la, e->lst[1], p1, e->stream);   // 63 k -> 9 k
+        CU_TRY(tc);
         CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->channels, e->lst[1].H, n / NVX_D1, 0, e->stream));
         la.in = e->y2buf; la.hist = e->lhist[2][cur]; la.out = e->y3buf[b]; la.n_in = n / (NVX_D1 * NVX_D2);
         la.out_pitch = ca.y3_pitch; la.out_off = ca.y3_off; la.stage = 2;
@@ -639,10 +640,11 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         for (int k = 0; k < 3; ++k)
             for (int q = 0; q < 2; ++q)
                 CREATE_TRY(cudaMalloc(&e->lhist[k][q], (size_t)(k == 0 ? e->S : e->channels) * e->lst[k].H * sizeof(float2)));
-        // stage 1 on the tensor cores where the band matrix fits (fir_long_tc.cu); NVX_LONG_TC=0 keeps the CUDA-core kernel,
-        // whose output is bit-identical across blockings
-        if (!(getenv("NVX_LONG_TC") && atoi(getenv("NVX_LONG_TC")) == 0))
-            e->ltc[0] = nvx::long_tc_prepare(NVX_D1, e->lst[0].T, cfg->h1 ? cfg->h1 : d1, e->stream);
+        // stages 1 and 2 on the tensor cores where the band matrix fits (fir_long_tc.cu); NVX_LONG_TC is a mask (bit 0: stage
+        // 1, bit 1: stage 2; 0 keeps the CUDA-core kernels, whose output is bit-identical across blockings)
+        const int tc_mask = getenv("NVX_LONG_TC") ? atoi(getenv("NVX_LONG_TC")) : 3;
+        if (tc_mask & 1) e->ltc[0] = nvx::long_tc_prepare(NVX_D1, e->lst[0].T, cfg->h1 ? cfg->h1 : d1, e->stream);
+        if (tc_mask & 2) e->ltc[1] = nvx::long_tc_prepare(NVX_D2, e->lst[1].T, cfg->h2 ? cfg->h2 : d2, e->stream);
         CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->channels * (cfg->max_block / NVX_D1) * sizeof(float2)));
         CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));
     } else {

@@ -69,8 +69,11 @@ constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 12
 constexpr int kMaxSlots = 8;
 constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 N + 4] floats (row pitch = 4 words mod 32: conflict-free)
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kTcD = NVX_D1;
-constexpr int kShift = kKB / kTcD;         // band rows per chunk
+// A K chunk is 32 columns holding the largest whole number of outputs' worth of samples: D = 4: 32 samples = 8 outputs; D = 7:
+// 28 samples = 4 outputs and 4 zero columns.  The band matrix moves 8 / 4 rows per chunk; descriptors can only move in whole
+// 8-row atoms, so D = 7 keeps two copies of the band (even / odd chunks, the odd one pre-shifted by 4 rows).
+__host__ __device__ constexpr int chunk_samples(int D) { return kKB / D * D; }
+__host__ __device__ constexpr int band_copies(int D) { return 8 / (chunk_samples(D) / D); }
 constexpr int kMaxSets = 3;                // A sets in tensor memory
 constexpr uint32_t kSetCols = 128;         // {I_hi, I_lo, Q_hi, Q_lo} x 32 columns
 
@@ -84,7 +87,7 @@ struct TcArgs {
     float2* out;
     long long n_in, in_pitch, out_pitch, out_off, k_abs;
     const NcoParam* nco;
-    int rows, s16, T, H, chunks, J, slots, box_rows;
+    int rows, s16, T, H, chunks, J, slots, box_rows, mix;
     long long tiles_per_block;             // output tiles per row block
     long long work;                        // row blocks * tiles_per_block
 };
@@ -166,8 +169,10 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-template <int N>
+template <int D, int N>
 __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_constant__ TcArgs a) {
+    constexpr int kCS = chunk_samples(D);                   // samples per chunk
+    constexpr int kCopies = band_copies(D);
     extern __shared__ __align__(1024) uint8_t smem[];
     // TMEM map: accumulators (I | Q) in columns [0, 2 N), A sets of 128 columns at the top.  Three A sets, not two plus a
     // second accumulator buffer: the round trip "MMAs of a set done -> converters refill it -> next MMAs issued" takes ~3200
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     constexpr int kSets = (512 - 2 * N) / (int)kSetCols < kMaxSets ? (512 - 2 * N) / (int)kSetCols : kMaxSets;
     constexpr uint32_t kACol0 = 512 - kSets * kSetCols;
     constexpr int kDumpPitch = 2 * N + kDumpPad;             // floats per dump row
-    const int g_bytes = a.J * 128;                          // one part of the band matrix (a multiple of 1024)
+    const int g_bytes = kCopies * a.J * 128;                // one part of the band matrix (a multiple of 1024), all copies
     uint8_t* s_gh = smem;
     uint8_t* s_gl = smem + g_bytes;
     uint8_t* s_raw = smem + 2 * g_bytes;                    // ring of raw-input slots
@@ -231,10 +236,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             for (long long w = w_lo; w < w_hi; ++w) {
                 const int rb = (int)(w / a.tiles_per_block);
                 const long long n0 = (w % a.tiles_per_block) * N;
-                const long long t_base = (long long)kTcD * n0 + kTcD - a.T;      // first input of the tile's window (block-relative)
+                const long long t_base = (long long)D * n0 + D - a.T;      // first input of the tile's window (block-relative)
                 const bool fast = t_base >= 0;
                 for (int c = 0; c < a.chunks; ++c, ++g) {
-                    if (g & 1) continue;
+                    if ((g & 1) || kCS != kKB) continue;    // 28-sample chunks are not whole 128-byte box rows: cp.async only
                     const int slot = (int)(g % ring_chunks) * slots_per_chunk;
                     const uint32_t ph = (uint32_t)(g / ring_chunks) & 1;
                     for (int h = 0; h < slots_per_chunk; ++h) {
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                         if (fast) {
                             // x coordinate in 32-bit (float) / 16-bit (short) elements, two per sample; rows past the last
                             // stream and samples past the block end are zero-filled by the TMA unit
-                            const int x0 = (int)(2 * (t_base + (long long)c * kKB + h * 16));
+                            const int x0 = (int)(2 * (t_base + (long long)c * kCS + h * 16));
                             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(kSlotBytes) : "memory");
                             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                                          ::"r"(s_u32(s_raw + (slot + h) * kSlotBytes)), "l"(&a.map_x), "r"(x0), "r"(rb * kRows), "r"(full) : "memory");
@@ -268,17 +273,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         for (long long w = w_lo; w < w_hi; ++w) {
             const int rb = (int)(w / a.tiles_per_block);
             const long long n0 = (w % a.tiles_per_block) * N;
-            const long long t_base = (long long)kTcD * n0 + kTcD - a.T;
+            const long long t_base = (long long)D * n0 + D - a.T;
             const bool fast = t_base >= 0;
             for (int c = 0; c < a.chunks; ++c, ++g) {
-                if (!(g & 1)) continue;
+                if (!(g & 1) && kCS == kKB) continue;
                 const int slot = (int)(g % ring_chunks) * slots_per_chunk;
                 const uint32_t ph = (uint32_t)(g / ring_chunks) & 1;
                 bar_wait(bar0 + 8 * (kBarRawEmpty + slot), ph ^ 1);
                 if (slots_per_chunk == 2) bar_wait(bar0 + 8 * (kBarRawEmpty + slot + 1), ph ^ 1);
                 if (fast) {
-                    const long long t = t_base + (long long)c * kKB + u16 * per_piece;       // first sample of this thread's pieces
-                    const bool t_ok = t + per_piece <= a.n_in;
+                    const long long t = t_base + (long long)c * kCS + u16 * per_piece;       // first sample of this thread's pieces
+                    const bool t_ok = t + per_piece <= a.n_in && u16 * per_piece < kCS;
                     const uint8_t* src = static_cast<const uint8_t*>(a.in) + ((size_t)(rb * kRows + r0) * a.in_pitch + t) * esz;
                     const size_t src_step = (size_t)r_step * a.in_pitch * esz;
                     const uint32_t dst0 = s_u32(s_raw + (slot + (u16 >> 3)) * kSlotBytes);
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         if (leader) {
             // the constant band matrix, once per CTA (TMA boxes of box_rows <= 256 rows, a divisor of J)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * kBarG), "r"(2 * g_bytes) : "memory");
-            for (int j = 0; j < a.J; j += a.box_rows) {
+            for (int j = 0; j < kCopies * a.J; j += a.box_rows) {
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                              ::"r"(s_u32(s_gh + j * 128)), "l"(&a.map_gh), "r"(0), "r"(j), "r"(bar0 + 8 * kBarG) : "memory");
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -322,7 +327,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                 bar_wait(bar0 + 8 * (kBarAFull + s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t at = tmem + kACol0 + s * kSetCols;
-                const uint32_t goff = (uint32_t)(a.chunks - 1 - c) * (kShift * 128);      // chunk c of B = G shifted by whole atoms
+                // chunk c of B = copy c % kCopies of the band, moved up by whole atoms
+                const uint32_t goff = (uint32_t)((a.chunks - 1) / kCopies - c / kCopies) * 1024 + (uint32_t)(c % kCopies) * (a.J * 128);
                 const uint32_t gh = s_u32(s_gh) + goff, gl = s_u32(s_gl) + goff;
                 if (leader) {
 #pragma unroll
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         for (long long w = w_lo; w < w_hi; ++w) {
             const int rb = (int)(w / a.tiles_per_block);
             const long long n0 = (w % a.tiles_per_block) * N;
-            const long long t_base = (long long)kTcD * n0 + kTcD - a.T;
+            const long long t_base = (long long)D * n0 + D - a.T;
             const bool fast = t_base >= 0;
             for (int c = 0; c < a.chunks; ++c) {
                 bar_wait(bar0 + 8 * (kBarRawFull + slot), sph);                 // raw samples landed
@@ -373,7 +379,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                     } else {                                                    // 16-byte units 0 .. 7: 2 samples each
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const float4 v = *reinterpret_cast<const float4*>(row + ((u ^ (r & 7)) << 4));
+                            float4 v = *reinterpret_cast<const float4*>(row + ((u ^ (r & 7)) << 4));
+                            if (kCS != kKB && kh * 16 + 2 * u >= kCS) v = make_float4(0.f, 0.f, 0.f, 0.f);     // zero columns
                             split_tf32(v.x, ih[2 * u], il[2 * u]);
                             split_tf32(v.y, qh[2 * u], ql[2 * u]);
                             split_tf32(v.z, ih[2 * u + 1], il[2 * u + 1]);
@@ -383,7 +390,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float2 v = tc_load(a, rb * kRows + r, t_base + (long long)c * kKB + kh * 16 + j);
+                        float2 v = make_float2(0.f, 0.f);
+                        if (kh * 16 + j < kCS) v = tc_load(a, rb * kRows + r, t_base + (long long)c * kCS + kh * 16 + j);
                         split_tf32(v.x, ih[j], il[j]);
                         split_tf32(v.y, qh[j], ql[j]);
                     }
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         // clock tick k_abs + k; channel c gets y * (cos - j sin)(2 pi tick f_c / 63000), fir2cpp.C:112-128 -- and store 256
         // contiguous bytes per instruction (one row per lane was measured 1.5x slower for the whole kernel).
         const int q = warp & 3;
-        const long long n_out = a.n_in / kTcD;
+        const long long n_out = a.n_in / D;
         float* my_row = s_dump + (q * 32 + lane) * kDumpPitch;
         const float* rows0 = s_dump + (q * 32) * kDumpPitch;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
@@ -443,6 +451,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                 const int n = h * 32 + lane;
                 if (n0 + n >= n_out) continue;
                 const long long tick = a.k_abs + n0 + n;
+                if (!a.mix) {                               // stage 2: one output row per input row, no rotation
+                    float2* dst1 = a.out + (size_t)row0 * a.out_pitch + a.out_off + n0 + n;
+#pragma unroll 4
+                    for (int r = 0; r < r_max; ++r, dst1 += a.out_pitch)
+                        *dst1 = make_float2(rows0[r * kDumpPitch + n], rows0[r * kDumpPitch + N + n]);
+                    continue;
+                }
                 float2* dst = a.out + (size_t)(2 * row0) * a.out_pitch + a.out_off + n0 + n;
                 if (a.nco) {
                     const long long rden = tick % kNcoDen;
@@ -492,10 +507,12 @@ float tf32_rna(float x) {                  // round to nearest, ties away, 10-bi
     return x;
 }
 
-int tc_chunks(int N, int T) { return (kTcD * (N - 1) + T + kKB - 1) / kKB; }
-int tc_band_rows(int N, int T) { return N + kShift * (tc_chunks(N, T) - 1); }
-size_t tc_smem(int N, int T, int slots) {
-    return (size_t)2 * tc_band_rows(N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * N + kDumpPad) * 4 + 128 + kBars * 8 + 16;
+int tc_chunks(int D, int N, int T) { return (D * (N - 1) + T + chunk_samples(D) - 1) / chunk_samples(D); }
+// rows of one copy of the band matrix: N plus one 8-row atom per further (group of) chunk(s)
+int tc_band_rows(int D, int N, int T) { return N + 8 * ((tc_chunks(D, N, T) - 1) / band_copies(D)); }
+size_t tc_smem(int D, int N, int T, int slots) {
+    return (size_t)2 * band_copies(D) * tc_band_rows(D, N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * N + kDumpPad) * 4 + 128 +
+           kBars * 8 + 16;
 }
 int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 rows, dividing J
     int best = 1;
@@ -503,34 +520,33 @@ int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 r
         if ((J / 8) % d == 0) best = d;
     return 8 * best;
 }
-int tc_slots(int N, int T) {               // raw-input slots that fit beside the band matrix: even, >= 4 (0: the stage does not fit)
+int tc_slots(int D, int N, int T) {        // raw-input slots that fit beside the band matrix: even, >= 4 (0: the stage does not fit)
     for (int slots = kMaxSlots; slots >= 4; slots -= 2)
-        if (tc_smem(N, T, slots) <= (size_t)kSmemLimit) return slots;
+        if (tc_smem(D, N, T, slots) <= (size_t)kSmemLimit) return slots;
     return 0;
 }
 
-template <int N>
+template <int D, int N>
 cudaError_t launch_tc(TcArgs& a, int sms, cudaStream_t stream) {
-    a.slots = tc_slots(N, a.T);
-    const size_t smem = tc_smem(N, a.T, a.slots);
-    cudaError_t e = cudaFuncSetAttribute(fir_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    a.slots = tc_slots(D, N, a.T);
+    const size_t smem = tc_smem(D, N, a.T, a.slots);
+    cudaError_t e = cudaFuncSetAttribute(fir_tc_kernel<D, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long grid = a.work < sms ? a.work : sms;
-    fir_tc_kernel<N><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
+    fir_tc_kernel<D, N><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-// outputs per tile for (D, T); 0 = the stage is not served by the tensor-core kernel (only D = 4 is: a K chunk must be a whole
-// number of outputs)
+// outputs per tile for (D, T); 0 = the stage is not served by the tensor-core kernel
 int long_tc_tile(int D, int T) {
-    if (D != kTcD) return 0;
-    // one tcgen05.mma (M = 128, K = 8) costs ~70 cycles for any N <= 128 (tools/probes/umma_rate.cu, umma_ts_probe.cu), so wide
-    // tiles win as long as the band matrix leaves room for the raw-input ring
+    if (D != NVX_D1 && D != NVX_D2) return 0;
+    // measured with the data operand in tensor memory (tools/probes/umma_ts_probe.cu): 23 / 36 / 64 cycles per tcgen05.mma at
+    // N = 32 / 64 / 128, i.e. 211 / 218 / 288 cycles per output column at 255 taps: N = 64 halves the re-read of N = 32
     int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : 64;
     for (int N : {64, 32})
-        if (N <= want && tc_slots(N, T)) return N;
+        if (N <= want && tc_slots(D, N, T)) return N;
     return 0;
 }
 
@@ -543,9 +559,11 @@ struct LongTcStage {
 
 // builds the band matrix of the stage on the device; returns nullptr if the stage does not fit the tensor-core kernel
 LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t stream) {
-    // zero taps appended at the old end until the tile windows start on a whole 32-byte sector (4 samples): the TMA unit needs
-    // 16-byte aligned box origins, and aligned rows cost 8 sectors instead of 9
-    const int T = (T_taps + 3) & ~3;
+    // zero taps appended at the old end until the tile windows (first sample D n0 + D - T, n0 a multiple of 32) start on a whole
+    // 32-byte sector = 4 samples: TMA box origins and cp.async pieces need 16-byte alignment, and aligned rows cost 8 sectors
+    // instead of 9
+    int T = T_taps;
+    while ((D - T) & 3) ++T;
     const int N = long_tc_tile(D, T);
     if (!N) return nullptr;
     void* fn = nullptr;
@@ -553,20 +571,23 @@ LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t st
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
     LongTcStage* s = new LongTcStage();
     s->D = D; s->T = T; s->N = N;
-    s->chunks = tc_chunks(N, T);
-    s->J = tc_band_rows(N, T);
+    s->chunks = tc_chunks(D, N, T);
+    s->J = tc_band_rows(D, N, T);
     s->box_rows = tc_box_rows(s->J);
-    std::vector<float> gh((size_t)s->J * kKB, 0.f), gl((size_t)s->J * kKB, 0.f);
-    for (int j = 0; j < s->J; ++j)
-        for (int k = 0; k < kKB; ++k) {
-            // row j of G is output n = j - 8 (chunks - 1 - c) of chunk c: tap index D n + T - 1 - (32 c + k)
-            const int i = D * (j - kShift * (s->chunks - 1)) + T - 1 - k;
-            if (i >= 0 && i < T_taps) {
-                const float t = (float)h[i];
-                gh[(size_t)j * kKB + k] = tf32_rna(t);
-                gl[(size_t)j * kKB + k] = t - tf32_rna(t);
+    const int P = band_copies(D), CS = chunk_samples(D), M1 = (s->chunks - 1) / P;
+    std::vector<float> gh((size_t)P * s->J * kKB, 0.f), gl((size_t)P * s->J * kKB, 0.f);
+    for (int p = 0; p < P; ++p)
+        for (int j = 0; j < s->J; ++j)
+            for (int k = 0; k < CS; ++k) {
+                // chunk c = P m + p reads copy p from atom M1 - m on: its row j is output n = j - 8 (M1 - m), whose tap for sample
+                // k of the chunk is D n + T - 1 - (CS c + k) = D (j - 8 M1) + T - 1 - CS p - k   (8 D = CS P)
+                const int i = D * (j - 8 * M1) + T - 1 - CS * p - k;
+                if (i >= 0 && i < T_taps) {
+                    const float t = (float)h[i];
+                    gh[((size_t)p * s->J + j) * kKB + k] = tf32_rna(t);
+                    gl[((size_t)p * s->J + j) * kKB + k] = t - tf32_rna(t);
+                }
             }
-        }
     bool ok = cudaMalloc(&s->d_gh, gh.size() * 4) == cudaSuccess && cudaMalloc(&s->d_gl, gl.size() * 4) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(s->d_gh, gh.data(), gh.size() * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(s->d_gl, gl.data(), gl.size() * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
@@ -577,7 +598,7 @@ LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t st
     ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
     if (ok) {
         EncodeTiledFn enc = s->enc = (EncodeTiledFn)fn;
-        cuuint64_t dims[2] = {(cuuint64_t)kKB, (cuuint64_t)s->J};
+        cuuint64_t dims[2] = {(cuuint64_t)kKB, (cuuint64_t)P * s->J};
         cuuint64_t strides[1] = {(cuuint64_t)kKB * 4};
         cuuint32_t box[2] = {kKB, (cuuint32_t)s->box_rows};
         cuuint32_t es[2] = {1, 1};
@@ -600,24 +621,25 @@ void long_tc_free(LongTcStage* s) {
     delete s;
 }
 
-// same contract as long_launch (fir_long.cu) for stage 0; cudaErrorNotSupported = this block cannot be described to the TMA
+// same contract as long_launch (fir_long.cu) for stages 0 and 1; cudaErrorNotSupported = this block cannot be described to the TMA
 // unit (misaligned pointer or pitch): the caller falls back to long_launch
 cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongStage& st, long long in_pitch, cudaStream_t stream) {
-    TcArgs a;
+    TcArgs a = {};
     a.map_gh = s->map_gh; a.map_gl = s->map_gl;
     a.in = la.in; a.hist = la.hist; a.out = la.out;
     a.n_in = la.n_in; a.in_pitch = in_pitch; a.out_pitch = la.out_pitch; a.out_off = la.out_off; a.k_abs = la.k_abs;
     a.nco = la.nco; a.rows = la.rows_in; a.s16 = la.s16; a.T = s->T; a.H = st.H; a.chunks = s->chunks; a.J = s->J; a.slots = 4; a.box_rows = s->box_rows;
+    a.mix = la.stage == 0;
     // TMA boxes and 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by
     // construction).  The block as a 2-D tensor of 32-bit (float2 input) or 16-bit (short2 input) elements, two per sample:
-    {
+    if (((uintptr_t)la.in & 15) || ((in_pitch * (la.s16 ? 4 : 8)) & 15)) return cudaErrorNotSupported;
+    if (chunk_samples(s->D) == kKB) {
         const size_t esz = la.s16 ? 2 : 4;
         cuuint64_t dims[2] = {(cuuint64_t)(2 * la.n_in), (cuuint64_t)la.rows_in};
         cuuint64_t strides[1] = {(cuuint64_t)in_pitch * 2 * esz};
         cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)kRows};
         cuuint32_t es[2] = {1, 1};
-        if (((uintptr_t)la.in & 15) || (strides[0] & 15) ||
-            s->enc(&a.map_x, la.s16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(la.in), dims, strides,
+        if (s->enc(&a.map_x, la.s16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(la.in), dims, strides,
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorNotSupported;
@@ -629,7 +651,8 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return s->N == 64 ? launch_tc<64>(a, sms, stream) : launch_tc<32>(a, sms, stream);
+    if (s->D == NVX_D1) return s->N == 64 ? launch_tc<NVX_D1, 64>(a, sms, stream) : launch_tc<NVX_D1, 32>(a, sms, stream);
+    return s->N == 64 ? launch_tc<NVX_D2, 64>(a, sms, stream) : launch_tc<NVX_D2, 32>(a, sms, stream);
 }
 
 }  // namespace nvx
