@@ -67,7 +67,11 @@ typedef struct {
     const double *nco_hz;
     /* optional per-stream tags [n_streams][2] handed to add_message instead of freq_tag (e.g. 4209 for 4209.5 kHz) */
     const int *stream_freq_tag;
-    int n1, n2, n3;             /* tap counts of h1 / h2 / h3; 0 = reference length */
+    /* tap counts of h1 / h2 / h3; 0 = reference length.  Up to 61 / 75 / 111 taps the fused kernel serves them (results do not
+     * depend on how the samples are cut into blocks); longer sets, up to 1024 per stage, run one kernel per stage, stages 1
+     * and 2 on the tensor cores (3xTF32, equal to the FP64 oracle to 1e-5; different blockings agree to rounding, not bit
+     * for bit -- set NVX_LONG_TC=0 in the environment for the CUDA-core kernels if block-invariant bits matter) */
+    int n1, n2, n3;
 } nvx_config;
 
 typedef struct {
