@@ -67,7 +67,8 @@ constexpr int kEpiWarp0 = kLoaderWarp0 + kLoaderWarps;
 constexpr int kTcThreads = 32 * (kConvWarps + 2 + kLoaderWarps + 4);
 constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 128 B]
 constexpr int kMaxSlots = 8;
-constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 N + 4] floats (row pitch = 4 words mod 32: conflict-free)
+constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 NP + 4] floats (row pitch = 4 words mod 32: conflict-free)
+__host__ __device__ constexpr int dump_outputs(int N) { return N > 64 ? 64 : N; }      // NP: outputs dumped per pass
 constexpr int kSmemLimit = 227 * 1024;
 // A K chunk is 32 columns holding the largest whole number of outputs' worth of samples: D = 4: 32 samples = 8 outputs; D = 7:
 // 28 samples = 4 outputs and 4 zero columns.  The band matrix moves 8 / 4 rows per chunk; descriptors can only move in whole
@@ -180,7 +181,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     // accumulators are only held for the few hundred cycles the epilogue needs to dump them to shared memory.
     constexpr int kSets = (512 - 2 * N) / (int)kSetCols < kMaxSets ? (512 - 2 * N) / (int)kSetCols : kMaxSets;
     constexpr uint32_t kACol0 = 512 - kSets * kSetCols;
-    constexpr int kDumpPitch = 2 * N + kDumpPad;             // floats per dump row
+    constexpr int NP = dump_outputs(N);                      // the epilogue dumps and stores the tile in N / NP passes
+    constexpr int kDumpPitch = 2 * NP + kDumpPad;            // floats per dump row: NP I columns, NP Q columns, padding
     const int g_bytes = kCopies * a.J * 128;                // one part of the band matrix (a multiple of 1024), all copies
     uint8_t* s_gh = smem;
     uint8_t* s_gl = smem + g_bytes;
@@ -432,30 +434,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
             const long long n0 = (w % a.tiles_per_block) * N;
             bar_wait(bar0 + 8 * kBarTile, tile & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
+            const int row0 = rb * kRows + q * 32;
+            const int r_max = a.rows - row0 < 32 ? a.rows - row0 : 32;
 #pragma unroll 1
-            for (int h = 0; h < 2 * N / 32; ++h) {
+            for (int pass = 0; pass < N / NP; ++pass) {
+            if (pass) __syncwarp();                         // the previous pass has been stored
+#pragma unroll 1
+            for (int h = 0; h < 2 * NP / 32; ++h) {
                 uint32_t v[32];
-                tmem_ld32(taddr + h * 32, v);
+                // dump column h * 32: I columns of this pass first, then its Q columns
+                tmem_ld32(taddr + (h < NP / 32 ? pass * NP + h * 32 : N + pass * NP + (h - NP / 32) * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(my_row + h * 32 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;");
+            if (pass == N / NP - 1) asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
-            if (lane == 0) bar_arrive(bar0 + 8 * kBarTmemFree);          // the accumulators may be overwritten
-            const int row0 = rb * kRows + q * 32;
-            const int r_max = a.rows - row0 < 32 ? a.rows - row0 : 32;
+            if (pass == N / NP - 1 && lane == 0) bar_arrive(bar0 + 8 * kBarTmemFree);      // the accumulators may be overwritten
 #pragma unroll 1
-            for (int h = 0; h < N / 32; ++h) {
-                const int n = h * 32 + lane;
+            for (int h = 0; h < NP / 32; ++h) {
+                const int m = h * 32 + lane;                // column of the dump
+                const int n = pass * NP + m;                // output of the tile
                 if (n0 + n >= n_out) continue;
                 const long long tick = a.k_abs + n0 + n;
                 if (!a.mix) {                               // stage 2: one output row per input row, no rotation
                     float2* dst1 = a.out + (size_t)row0 * a.out_pitch + a.out_off + n0 + n;
 #pragma unroll 4
                     for (int r = 0; r < r_max; ++r, dst1 += a.out_pitch)
-                        *dst1 = make_float2(rows0[r * kDumpPitch + n], rows0[r * kDumpPitch + N + n]);
+                        *dst1 = make_float2(rows0[r * kDumpPitch + m], rows0[r * kDumpPitch + NP + m]);
                     continue;
                 }
                 float2* dst = a.out + (size_t)(2 * row0) * a.out_pitch + a.out_off + n0 + n;
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
 #pragma unroll 2
                     for (int r = 0; r < r_max; ++r, dst += 2 * a.out_pitch) {
                         const NcoParam np = a.nco[row0 + r];
-                        const float2 y = make_float2(rows0[r * kDumpPitch + n], rows0[r * kDumpPitch + N + n]);
+                        const float2 y = make_float2(rows0[r * kDumpPitch + m], rows0[r * kDumpPitch + NP + m]);
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
                             const int phs = (int)((kden * np.num[c]) % kNcoDen);
@@ -481,11 +488,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                     const float2 rot = s_nco[r9 < 0 ? r9 + kNcoPeriod : r9];       // (cos, -sin); "490" uses the conjugate (fir2cpp.C:121-124)
 #pragma unroll 4
                     for (int r = 0; r < r_max; ++r, dst += 2 * a.out_pitch) {
-                        const float2 y = make_float2(rows0[r * kDumpPitch + n], rows0[r * kDumpPitch + N + n]);
+                        const float2 y = make_float2(rows0[r * kDumpPitch + m], rows0[r * kDumpPitch + NP + m]);
                         dst[0] = make_float2(fmaf(-y.y, rot.y, y.x * rot.x), fmaf(y.x, rot.y, y.y * rot.x));
                         dst[a.out_pitch] = make_float2(fmaf(y.y, rot.y, y.x * rot.x), fmaf(-y.x, rot.y, y.y * rot.x));
                     }
                 }
+            }
             }
             __syncwarp();                                   // the dump rows are overwritten by the next tile
         }
@@ -511,7 +519,7 @@ int tc_chunks(int D, int N, int T) { return (D * (N - 1) + T + chunk_samples(D) 
 // rows of one copy of the band matrix: N plus one 8-row atom per further (group of) chunk(s)
 int tc_band_rows(int D, int N, int T) { return N + 8 * ((tc_chunks(D, N, T) - 1) / band_copies(D)); }
 size_t tc_smem(int D, int N, int T, int slots) {
-    return (size_t)2 * band_copies(D) * tc_band_rows(D, N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * N + kDumpPad) * 4 + 128 +
+    return (size_t)2 * band_copies(D) * tc_band_rows(D, N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * dump_outputs(N) + kDumpPad) * 4 + 128 +
            kBars * 8 + 16;
 }
 int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 rows, dividing J
@@ -543,10 +551,12 @@ cudaError_t launch_tc(TcArgs& a, int sms, cudaStream_t stream) {
 int long_tc_tile(int D, int T) {
     if (D != NVX_D1 && D != NVX_D2) return 0;
     // measured with the data operand in tensor memory (tools/probes/umma_ts_probe.cu): 23 / 36 / 64 cycles per tcgen05.mma at
-    // N = 32 / 64 / 128, i.e. 211 / 218 / 288 cycles per output column at 255 taps: N = 64 halves the re-read of N = 32
-    int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : 64;
-    for (int N : {64, 32})
-        if (N <= want && tc_slots(D, N, T)) return N;
+    // N = 32 / 64 / 128, i.e. 211 / 218 / 288 cycles per output column at 255 taps; N = 64 halves the re-read of N = 32.  N = 128
+    // (stage 1 only: 1.5x instead of 2x re-read, but two A sets and a two-pass epilogue) wins from ~400 taps on: 511 taps 131
+    // against 122 Gsamples/s, 255 taps 183 against 190
+    int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : (D == NVX_D1 && T >= 384 ? 128 : 64);
+    for (int N : {128, 64, 32})
+        if (N <= want && (N <= 64 || D == NVX_D1) && tc_slots(D, N, T)) return N;
     return 0;
 }
 
@@ -651,7 +661,9 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (s->D == NVX_D1) return s->N == 64 ? launch_tc<NVX_D1, 64>(a, sms, stream) : launch_tc<NVX_D1, 32>(a, sms, stream);
+    if (s->D == NVX_D1)
+        return s->N == 128 ? launch_tc<NVX_D1, 128>(a, sms, stream)
+                           : s->N == 64 ? launch_tc<NVX_D1, 64>(a, sms, stream) : launch_tc<NVX_D1, 32>(a, sms, stream);
     return s->N == 64 ? launch_tc<NVX_D2, 64>(a, sms, stream) : launch_tc<NVX_D2, 32>(a, sms, stream);
 }
 
