@@ -1,43 +1,45 @@
-// fir_long_tc.cu -- the first long-tap decimating FIR stage (252 k -> 63 k, D = 4) on the 5th-generation tensor cores
-// (tcgen05 + TMEM + TMA).
+// fir_long_tc.cu -- the first two long-tap decimating FIR stages (252 k -> 63 k, D = 4, with the NCO mix; 63 k -> 9 k, D = 7)
+// on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
 //
-// Same arithmetic definition as fir_long.cu / the reference stage (fir1cpp.C:80-136):
+// Same arithmetic definition as fir_long.cu / the reference stages (fir1cpp.C:80-136, fir2cpp.C:131-215):
 //     y[k] = sum_{i < T} h[i] x[D (k + 1) - 1 - i].
-// With hundreds of taps that is a dense contraction, and for a tile of N consecutive outputs of 128 rows (streams) it
-// is the GEMM
-//     Y_p[128 x N] = X_p[128 x K] * B[N x K]^T,   p in {I, Q},  K = D (N - 1) + T rounded up to 32,
+// With hundreds of taps that is a dense contraction, and for a tile of N consecutive outputs of 128 rows (streams, or
+// channel rows for stage 2) it is the GEMM
+//     Y_p[128 x N] = X_p[128 x K] * B[N x K]^T,   p in {I, Q},  K = D (N - 1) + T rounded up to whole chunks,
 // where X_p is the window of inputs the tile depends on and B[n][k] = h[D n + T - 1 - k] is the Toeplitz matrix of the
-// taps.  B is the same for every tile, and because one 32-sample K chunk is exactly 32 / D = 8 outputs, chunk c of B is
-// chunk 0 shifted down by 8 c rows: the whole operand is ONE band matrix G[j][k] = h[D (j - 8 (chunks - 1)) + T - 1 - k]
-// of N + 8 (chunks - 1) rows, kept in shared memory (TMA, SWIZZLE_128B) and addressed per chunk by moving the matrix
+// taps.  B is the same for every tile.  A K chunk is 32 columns holding a whole number of outputs' worth of samples (D = 4:
+// 32 samples = 8 outputs; D = 7: 28 samples = 4 outputs + 4 zero columns), so chunk c of B is chunk 0 shifted down by 8 c
+// (4 c) rows: the whole operand is ONE band matrix G of N + 8 (chunks - 1) rows (D = 7: two copies, the one for odd chunks
+// pre-shifted by 4 rows), kept in shared memory (TMA, SWIZZLE_128B) and addressed per chunk by moving the matrix
 // descriptor's start address in whole 8-row swizzle atoms (1024 B).
 // Precision: the north star's 1e-5 bar rules out plain TF32 (10-bit mantissa), so every product is the 3xTF32 split
 // x_hi h_hi + x_lo h_hi + x_hi h_lo accumulated in FP32 in TMEM (measured 1.5e-6 relative to the FP64 oracle).
 //
 // Measured on B200 (tools/probes/umma_rate.cu, umma_ts_probe.cu): one tcgen05.mma.kind::tf32 with M = 128, K = 8 costs
-// ~70 cycles for ANY N <= 128, and with both operands in shared memory the operand reads (8 KB per instruction at N = 128)
-// plus the converters' stores saturate the 128 B/clk shared-memory pipe.  Hence: wide tiles (N = 128 / 64), and the DATA
-// operand lives in tensor memory -- the converters write it with tcgen05.st -- so shared memory only serves the band matrix
-// reads and a deep ring of raw input.
+// 52 / 59 / 73 cycles at N = 32 / 64 / 128 with both operands in shared memory (4 KB of A per instruction through the
+// 128 B/clk pipe the converters' stores also need), but 23 / 36 / 64 with A in tensor memory.  Hence the DATA operand lives
+// in tensor memory -- the converters write it with tcgen05.st -- and shared memory only serves the band matrix reads, the
+// ring of raw input and the epilogue's dump.
 //
 // One CTA = 16 warps, persistent over a contiguous range of (row block, output tile) work items:
-//   * warps 9..11, loaders: stream the raw input window of each tile through a ring of [128 rows x 128 B] slots with 16-byte
-//     cp.async copies completing on the slot's mbarrier (128-byte XOR swizzle so that a thread can read ITS row
-//     conflict-free; rows past the last stream and samples past the block end are zero-filled).  A TMA box per slot was
-//     measured first: 128-byte box rows cap the TMA unit near 4 TB/s chip-wide (profiles/r1_staging_sweep.md D), below what
-//     this kernel re-reads from L2, and one 1-D bulk copy per row costs ~63 cycles of the TMA unit each, whatever its size
-//     (2.8x slower end to end).  Tiles that touch the carried history skip the copies and the converters call the general
-//     loader instead; the ring protocol is the same;
-//   * warps 0..7, converters: thread = row (TMEM lane) x half of the 32-sample chunk; reads its 16 samples from the slot,
-//     de-interleaves I and Q, splits them into TF32 high and low parts and writes the four A tiles (I_hi, I_lo, Q_hi,
-//     Q_lo; 32 columns each, two sets) into tensor memory with tcgen05.st;
-//   * warp 8, issuer: one thread issues the 2 planes x 3 terms x 4 k-steps tcgen05.mma.kind::tf32 (A in TMEM, B = band
-//     matrix in shared memory) per chunk and commits them to the A set's empty barrier; the last chunk of a tile also commits
-//     to the tile barrier;
-//   * warps 12..15, epilogue: dump the tile's 2 N accumulator columns to shared memory (tcgen05.ld, lane = row) and release
-//     the accumulators at once, then, lane = output, apply the NCO rotation of both channels (fir2cpp.C:112-128) and store
-//     one 63 kHz row per channel, 256 contiguous bytes per instruction.
-// TMEM map (512 columns): [0, 2 N) accumulators, [128, 512) three A sets of 4 x 32 columns.
+//   * warp 9 (one thread, TMA) and warps 10..11 (cp.async loaders): stream the raw input window of each tile through a
+//     ring of [128 rows x 128 B] slots, alternating chunks between one 2-D TMA box per slot (SWIZZLE_128B; D = 4 only) and
+//     16-byte cp.async copies written in the same XOR-swizzled layout, both completing on the slot's mbarrier; the swizzle
+//     lets a thread read ITS row conflict-free, and rows past the last stream / samples past the block end are zero-filled.
+//     (One 1-D bulk copy per row was measured at ~63 cycles of the TMA unit each, whatever its size: 2.8x slower end to
+//     end.)  Tiles that touch the carried history skip the copies and the converters call the general loader instead; the
+//     ring protocol is the same;
+//   * warps 0..7, converters: thread = row (TMEM lane) x half of the chunk; reads its 16 samples from the slot,
+//     de-interleaves I and Q, splits them into TF32 high and low parts and writes the four A tiles (I_hi, I_lo, Q_hi, Q_lo;
+//     32 columns each) of one of the A sets into tensor memory with tcgen05.st;
+//   * warp 8, issuer: the whole warp runs the loop, one elect.sync-elected lane issues the 2 planes x 3 terms x 4 k-steps
+//     tcgen05.mma.kind::tf32 (A in TMEM, B = band matrix in shared memory) per chunk and commits them to the A set's empty
+//     barrier; the last chunk of a tile also commits to the tile barrier.  (Issued from an "if (lane == 0)" branch, ptxas
+//     wraps every MMA in an R2UR waterfall loop -- ~80 cycles per MMA, which bounded the first versions of this kernel.);
+//   * warps 12..15, epilogue: dump the tile's accumulator columns to shared memory (tcgen05.ld, lane = row; 64 outputs per
+//     pass) and release the accumulators, then, lane = output, apply the NCO rotation of both channels (stage 1,
+//     fir2cpp.C:112-128) and store 256 contiguous bytes per instruction.
+// TMEM map (512 columns): [0, 2 N) accumulators (I | Q), A sets of 4 x 32 columns at the top: three at N <= 64, two at N = 128.
 // The accumulation order inside the tensor core is fixed per tile position, so results are deterministic for a given
 // blocking but not bit-identical across blockings (tile boundaries move); the tests hold this path to the 1e-5 bar.
 #include <cuda.h>
