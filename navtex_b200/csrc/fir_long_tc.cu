@@ -558,7 +558,7 @@ int long_tc_tile(int D, int T) {
     // against 122 Gsamples/s, 255 taps 183 against 190
     int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : (D == NVX_D1 && T >= 384 ? 128 : 64);
     for (int N : {128, 64, 32})
-        // stage 2 only with N = 64: once its two band copies leave room for N = 32 tiles only (~600 taps on), the CUDA-core
+        // stage 2 only with N = 64: once its two band copies leave room for N = 32 tiles only (512 taps on), the CUDA-core
         // kernel is faster (767 taps: 69.8 against 67.4 Gsamples/s)
         if (N <= want && (D == NVX_D1 || N == 64) && tc_slots(D, N, T)) return N;
     return 0;
