@@ -435,7 +435,9 @@ def main():
     device = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION) off it
+        # stdout carries exactly one JSON line: NCCL prints its version banner (and anything else NCCL_DEBUG asks for) to
+        # stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
