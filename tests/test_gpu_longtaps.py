@@ -1,5 +1,7 @@
 """BASELINE.json configs[4] on the GPU: long-tap FIR stress (255-tap Kaiser designs for all three stages, steeper
-than fir1cpp.C:8 / fir2cpp.C:22 / fir3cpp.h:16) through the long-tap path (one register-tiled kernel per stage).
+than fir1cpp.C:8 / fir2cpp.C:22 / fir3cpp.h:16) through the long-tap path: one kernel per stage, stages 1 and 2 on the tensor
+cores by default (fir_long_tc.cu: tcgen05 3xTF32 Toeplitz GEMM), stage 3 and the NVX_LONG_TC=0 variants register-tiled on
+CUDA cores (fir_long.cu).
 
 The unmodified reference cannot run other tap sets, so parity is against the C restatement of the three stages
 (oracle/navtex_oracle.c, h1/h2/h3 parameters), which is pinned to the compiled reference at the default taps."""
