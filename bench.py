@@ -380,7 +380,7 @@ def run_config5(args, torch, dist, device, rank, world, local, barrier):
         chunks = -(-(D * (n_tile - 1) + t_pad) // cs)
         tiles = -(-rows // 128) * -(-(n_in // D) // n_tile)
         return tiles * chunks * 24 * 2.0 * 128 * n_tile * 8 / 1e12
-    ex = executed_tflop(4, S, BLOCK, 128 if 384 <= T <= 548 else 64) + (executed_tflop(7, 2 * S, BLOCK // 4, 64) if T <= 511 else 0.0)
+    ex = executed_tflop(4, S, BLOCK, 128 if 384 <= T <= 548 else 64) + (executed_tflop(7, 2 * S, BLOCK // 4, 64) if T <= 959 else 0.0)
     print(json.dumps({
         "metric": "iq_msamples_per_s", "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

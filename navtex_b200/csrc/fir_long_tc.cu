@@ -70,7 +70,9 @@ constexpr int kTcThreads = 32 * (kConvWarps + 2 + kLoaderWarps + 4);
 constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 128 B]
 constexpr int kMaxSlots = 8;
 constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 NP + 4] floats (row pitch = 4 words mod 32: conflict-free)
-__host__ __device__ constexpr int dump_outputs(int N) { return N > 64 ? 64 : N; }      // NP: outputs dumped per pass
+// NP: outputs dumped per epilogue pass.  Stage 2 (D = 7) dumps 32 at a time: its two band copies leave little shared memory, and
+// two more raw-input slots are worth more than a one-pass epilogue
+__host__ __device__ constexpr int dump_outputs(int D, int N) { return D == NVX_D2 ? 32 : (N > 64 ? 64 : N); }
 constexpr int kSmemLimit = 227 * 1024;
 // A K chunk is 32 columns holding the largest whole number of outputs' worth of samples: D = 4: 32 samples = 8 outputs; D = 7:
 // 28 samples = 4 outputs and 4 zero columns.  The band matrix moves 8 / 4 rows per chunk; descriptors can only move in whole
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     // accumulators are only held for the few hundred cycles the epilogue needs to dump them to shared memory.
     constexpr int kSets = (512 - 2 * N) / (int)kSetCols < kMaxSets ? (512 - 2 * N) / (int)kSetCols : kMaxSets;
     constexpr uint32_t kACol0 = 512 - kSets * kSetCols;
-    constexpr int NP = dump_outputs(N);                      // the epilogue dumps and stores the tile in N / NP passes
+    constexpr int NP = dump_outputs(D, N);                      // the epilogue dumps and stores the tile in N / NP passes
     constexpr int kDumpPitch = 2 * NP + kDumpPad;            // floats per dump row: NP I columns, NP Q columns, padding
     const int g_bytes = kCopies * a.J * 128;                // one part of the band matrix (a multiple of 1024), all copies
     uint8_t* s_gh = smem;
@@ -521,7 +523,7 @@ int tc_chunks(int D, int N, int T) { return (D * (N - 1) + T + chunk_samples(D) 
 // rows of one copy of the band matrix: N plus one 8-row atom per further (group of) chunk(s)
 int tc_band_rows(int D, int N, int T) { return N + 8 * ((tc_chunks(D, N, T) - 1) / band_copies(D)); }
 size_t tc_smem(int D, int N, int T, int slots) {
-    return (size_t)2 * band_copies(D) * tc_band_rows(D, N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * dump_outputs(N) + kDumpPad) * 4 + 128 +
+    return (size_t)2 * band_copies(D) * tc_band_rows(D, N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * dump_outputs(D, N) + kDumpPad) * 4 + 128 +
            kBars * 8 + 16;
 }
 int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 rows, dividing J
@@ -558,8 +560,7 @@ int long_tc_tile(int D, int T) {
     // against 122 Gsamples/s, 255 taps 183 against 190
     int want = getenv("NVX_TC_N") ? atoi(getenv("NVX_TC_N")) : (D == NVX_D1 && T >= 384 ? 128 : 64);
     for (int N : {128, 64, 32})
-        // stage 2 only with N = 64: once its two band copies leave room for N = 32 tiles only (512 taps on), the CUDA-core
-        // kernel is faster (767 taps: 69.8 against 67.4 Gsamples/s)
+        // stage 2 only with N = 64 (fits up to 959 taps): with N = 32 tiles the CUDA-core kernel is faster
         if (N <= want && (D == NVX_D1 || N == 64) && tc_slots(D, N, T)) return N;
     return 0;
 }
