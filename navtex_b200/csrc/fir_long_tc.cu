@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                         split_tf32(v.y, qh[j], ql[j]);
                     }
                 }
+                __syncwarp();                                                   // every lane holds its samples in registers:
+                if (lane == 0) bar_arrive(bar0 + 8 * (kBarRawEmpty + slot));    // the slot can be refilled already
                 bar_wait(bar0 + 8 * (kBarAEmpty + s), ph ^ 1);                  // the MMAs that read this A set are done
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t col = lane_base + s * kSetCols;
@@ -412,10 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) {
-                    bar_arrive(bar0 + 8 * (kBarAFull + s));
-                    bar_arrive(bar0 + 8 * (kBarRawEmpty + slot));
-                }
+                if (lane == 0) bar_arrive(bar0 + 8 * (kBarAFull + s));
                 if (++s == kSets) { s = 0; ph ^= 1; }
                 slot += slots_per_chunk;
                 if (slot >= a.slots) { slot -= a.slots; sph ^= 1; }
