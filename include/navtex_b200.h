@@ -142,6 +142,14 @@ void *nvx_engine_stream(nvx_engine *e);
  * channel's event bytes; calls cb once per completed message and returns their number */
 int nvx_host_assemble(const unsigned char *events, size_t n, int stream, int freq, nvx_message_cb cb, void *user);
 
+/* host-only test hook (no GPU needed): the operand the tensor-core long-tap kernel (stage with the given decimation, 4 or 7)
+ * builds from n_taps taps h.  geometry[5] = { taps after zero padding, outputs per tile N, K chunks per tile, band rows J per
+ * copy, copies }; g_hi / g_lo (may be NULL to query the size) receive the TF32 high / low parts as [copies][J][32] floats.
+ * Chunk c of a tile multiplies 32 window columns (D = 4: 32 samples; D = 7: 28 samples + 4 zero columns) with rows
+ * [8 ((chunks - 1) / copies - c / copies), + N) of copy c % copies.  Returns the float count per part, or NVX_ERR_ARG when
+ * the stage is not served by that kernel. */
+int nvx_debug_long_tc_band(int decimation, const double *h, int n_taps, int *geometry, float *g_hi, float *g_lo, size_t capacity);
+
 /* ---- SDRplay-format front end (host): replaces the ring buffer + 50 ms consumer loop of capt_sched.c:105-148, :484-528 --- */
 typedef struct nvx_capture nvx_capture;
 /* one ring of ring_samples int16 I,Q pairs per stream (>= 2 max_block); max_block <= the engine's */

@@ -834,4 +834,17 @@ int nvx_host_assemble(const unsigned char* events, size_t n, int stream, int fre
     return (int)out.size();
 }
 
+int nvx_debug_long_tc_band(int decimation, const double* h, int n_taps, int* geometry, float* g_hi, float* g_lo, size_t capacity) {
+    nvx::TcBand b;
+    if (!h || n_taps < 1 || !geometry || !nvx::long_tc_band(decimation, n_taps, h, &b))
+        return fail(NVX_ERR_ARG, "no tensor-core band matrix for decimation %d, %d taps", decimation, n_taps);
+    geometry[0] = b.T; geometry[1] = b.N; geometry[2] = b.chunks; geometry[3] = b.J; geometry[4] = b.copies;
+    if (g_hi && g_lo) {
+        if (capacity < b.gh.size()) return fail(NVX_ERR_ARG, "the band matrix needs %zu floats per part", b.gh.size());
+        memcpy(g_hi, b.gh.data(), b.gh.size() * sizeof(float));
+        memcpy(g_lo, b.gl.data(), b.gl.size() * sizeof(float));
+    }
+    return (int)b.gh.size();
+}
+
 }  // extern "C"

@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "fir_cascade.cuh"
 
 namespace nvx {
@@ -58,6 +60,11 @@ cudaError_t long_carry(const float2* old_hist, const void* block, long long pitc
 
 // ---- tensor-core variant of stages 1 and 2 (fir_long_tc.cu): tcgen05 3xTF32 Toeplitz GEMM, same contract as long_launch ----
 struct LongTcStage;
+struct TcBand {
+    int T, N, chunks, J, copies;      // padded taps, outputs per tile, K chunks per tile, band rows per copy, copies
+    std::vector<float> gh, gl;        // [copies][J][32] high / low TF32 parts
+};
+bool long_tc_band(int D, int T_taps, const double* h, TcBand* out);
 // builds the Toeplitz operand of one stage (D = 4 or 7, T taps) on the device; nullptr when the stage does not fit the kernel
 LongTcStage* long_tc_prepare(int D, int T, const double* h, cudaStream_t stream);
 void long_tc_free(LongTcStage* s);

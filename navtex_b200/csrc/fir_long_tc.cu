@@ -571,37 +571,52 @@ struct LongTcStage {
     EncodeTiledFn enc = nullptr;
 };
 
-// builds the band matrix of the stage on the device; returns nullptr if the stage does not fit the tensor-core kernel
-LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t stream) {
+// host side of the band matrix (no GPU needed; also behind nvx_debug_long_tc_band for the CPU tests): padded tap count, tile
+// width, chunk count, rows per copy, copies, and the hi / lo TF32 parts [copies][J][32]
+bool long_tc_band(int D, int T_taps, const double* h, TcBand* b) {
     // zero taps appended at the old end until the tile windows (first sample D n0 + D - T, n0 a multiple of 32) start on a whole
     // 32-byte sector = 4 samples: TMA box origins and cp.async pieces need 16-byte alignment, and aligned rows cost 8 sectors
     // instead of 9
     int T = T_taps;
     while ((D - T) & 3) ++T;
     const int N = long_tc_tile(D, T);
-    if (!N) return nullptr;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
-    LongTcStage* s = new LongTcStage();
-    s->D = D; s->T = T; s->N = N;
-    s->chunks = tc_chunks(D, N, T);
-    s->J = tc_band_rows(D, N, T);
-    s->box_rows = tc_box_rows(s->J);
-    const int P = band_copies(D), CS = chunk_samples(D), M1 = (s->chunks - 1) / P;
-    std::vector<float> gh((size_t)P * s->J * kKB, 0.f), gl((size_t)P * s->J * kKB, 0.f);
+    if (!N) return false;
+    b->T = T; b->N = N;
+    b->chunks = tc_chunks(D, N, T);
+    b->J = tc_band_rows(D, N, T);
+    b->copies = band_copies(D);
+    const int P = b->copies, CS = chunk_samples(D), M1 = (b->chunks - 1) / P;
+    b->gh.assign((size_t)P * b->J * kKB, 0.f);
+    b->gl.assign((size_t)P * b->J * kKB, 0.f);
     for (int p = 0; p < P; ++p)
-        for (int j = 0; j < s->J; ++j)
+        for (int j = 0; j < b->J; ++j)
             for (int k = 0; k < CS; ++k) {
                 // chunk c = P m + p reads copy p from atom M1 - m on: its row j is output n = j - 8 (M1 - m), whose tap for sample
                 // k of the chunk is D n + T - 1 - (CS c + k) = D (j - 8 M1) + T - 1 - CS p - k   (8 D = CS P)
                 const int i = D * (j - 8 * M1) + T - 1 - CS * p - k;
                 if (i >= 0 && i < T_taps) {
                     const float t = (float)h[i];
-                    gh[((size_t)p * s->J + j) * kKB + k] = tf32_rna(t);
-                    gl[((size_t)p * s->J + j) * kKB + k] = t - tf32_rna(t);
+                    b->gh[((size_t)p * b->J + j) * kKB + k] = tf32_rna(t);
+                    b->gl[((size_t)p * b->J + j) * kKB + k] = t - tf32_rna(t);
                 }
             }
+    return true;
+}
+
+// builds the band matrix of the stage on the device; returns nullptr if the stage does not fit the tensor-core kernel
+LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t stream) {
+    TcBand band;
+    if (!long_tc_band(D, T_taps, h, &band)) return nullptr;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
+    LongTcStage* s = new LongTcStage();
+    s->D = D; s->T = band.T; s->N = band.N;
+    s->chunks = band.chunks;
+    s->J = band.J;
+    s->box_rows = tc_box_rows(s->J);
+    const int P = band.copies;
+    const std::vector<float>&gh = band.gh, &gl = band.gl;
     bool ok = cudaMalloc(&s->d_gh, gh.size() * 4) == cudaSuccess && cudaMalloc(&s->d_gl, gl.size() * 4) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(s->d_gh, gh.data(), gh.size() * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(s->d_gl, gl.data(), gl.size() * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;

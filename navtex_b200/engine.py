@@ -51,7 +51,7 @@ EXPORTS = (
     "nvx_engine_push_host_f32", "nvx_engine_push_host_s16", "nvx_engine_push_device_f32", "nvx_engine_push_device_s16",
     "nvx_engine_sync", "nvx_engine_wait_ingest", "nvx_engine_poll_messages", "nvx_engine_try_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
     "nvx_engine_read_bits", "nvx_engine_read_events", "nvx_engine_enable_timing", "nvx_engine_get_stats",
-    "nvx_engine_stream", "nvx_synth_fill_device", "nvx_host_assemble",
+    "nvx_engine_stream", "nvx_synth_fill_device", "nvx_host_assemble", "nvx_debug_long_tc_band",
     "nvx_capture_create", "nvx_capture_destroy", "nvx_capture_write", "nvx_capture_pump", "nvx_capture_start", "nvx_capture_stop",
     "nvx_capture_dropped", "nvx_store_create", "nvx_store_destroy", "nvx_store_add", "nvx_store_add_at", "nvx_store_sink",
     "nvx_store_count", "nvx_store_get", "nvx_store_purge", "nvx_store_dump_csv",
@@ -126,6 +126,25 @@ def host_assemble(events: bytes, stream: int = 0, freq: int = 518):
 
     _check(min(0, load_library().nvx_host_assemble(events, len(events), stream, freq, MESSAGE_CB(cb), None)))
     return out
+
+
+def long_tc_band(decimation: int, h):
+    """The band-matrix operand of the tensor-core long-tap kernel for one stage (host only; tests): returns
+    (geometry dict, g_hi, g_lo) with g_* shaped [copies][J][32], see nvx_debug_long_tc_band in navtex_b200.h."""
+    L = load_library()
+    L.nvx_debug_long_tc_band.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float), C.c_size_t]
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    geo = (C.c_int * 5)()
+    hp = h.ctypes.data_as(C.POINTER(C.c_double))
+    n = L.nvx_debug_long_tc_band(decimation, hp, h.size, geo, None, None, 0)
+    _check(min(0, n))
+    hi, lo = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    _check(min(0, L.nvx_debug_long_tc_band(decimation, hp, h.size, geo, hi.ctypes.data_as(C.POINTER(C.c_float)),
+                                           lo.ctypes.data_as(C.POINTER(C.c_float)), n)))
+    g = dict(zip(("taps_padded", "n_tile", "chunks", "band_rows", "copies"), list(geo)))
+    shape = (g["copies"], g["band_rows"], 32)
+    return g, hi.reshape(shape), lo.reshape(shape)
 
 
 def _check(rc, allow_overflow=False):
