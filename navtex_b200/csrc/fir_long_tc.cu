@@ -180,9 +180,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     constexpr int kCopies = band_copies(D);
     extern __shared__ __align__(1024) uint8_t smem[];
     // TMEM map: accumulators (I | Q) in columns [0, 2 N), A sets of 128 columns at the top.  Three A sets, not two plus a
-    // second accumulator buffer: the round trip "MMAs of a set done -> converters refill it -> next MMAs issued" takes ~3200
-    // cycles against ~1450 cycles of MMAs per chunk, so two sets leave the tensor core idle a third of the time, while the
-    // accumulators are only held for the few hundred cycles the epilogue needs to dump them to shared memory.
+    // second accumulator buffer: the round trip "MMAs of a set done -> converters refill it -> next MMAs issued" is a multiple
+    // of the ~870 cycles the MMAs of one chunk take (N = 64), so two sets leave the tensor core idle much of the time, while
+    // the accumulators are only held for the few hundred cycles the epilogue needs to dump them to shared memory.
     constexpr int kSets = (512 - 2 * N) / (int)kSetCols < kMaxSets ? (512 - 2 * N) / (int)kSetCols : kMaxSets;
     constexpr uint32_t kACol0 = 512 - kSets * kSetCols;
     constexpr int NP = dump_outputs(D, N);                      // the epilogue dumps and stores the tile in N / NP passes
