@@ -1,0 +1,4 @@
+/* decoder.h -- same-named shim of the reference header receiver/decoder.h:26-88 (class decoder).
+ * Put include/compat on the include path INSTEAD of the reference's receiver/ directory and the reference's own host
+ * sources (nav_sched.C, capt_sched.c) compile unmodified against the GPU engine; link with -lnavtex_compat. */
+#include "../navtex_compat.h"

@@ -56,8 +56,8 @@ typedef struct {
      * (zero-padded to the class; the medium class is where it turns from HBM-bound to FP32-bound); longer ones (up to
      * 1024 per stage, e.g. the 255-tap stress designs) take the long-tap path: one register-tiled FIR kernel per stage,
      * intermediates in HBM.
-     * Tap sets live in the device's constant bank, which all engines of a process on that device share: engines that
-     * are alive at the same time on one device must use the same tap sets (the last create wins) */
+     * Tap sets are per engine (they travel in the kernel parameter block of every launch): engines with different
+     * filters can be alive on one device at the same time */
     const double *h1, *h2, *h3;
     int keep_bits;              /* record 'B'/'Y' decisions and discriminator sums for nvx_engine_read_bits */
     int first_stream_id;        /* global id of stream 0 (multi-GPU sharding; only used to label messages) */
@@ -112,7 +112,12 @@ int nvx_engine_sync(nvx_engine *e);
 int nvx_engine_poll_messages(nvx_engine *e, const nvx_message **msgs, size_t *count);
 /* same without waiting: whatever the blocks already finished have completed (the pipeline keeps running) */
 int nvx_engine_try_poll_messages(nvx_engine *e, const nvx_message **msgs, size_t *count);
-/* alternatively deliver them through an add_message-shaped callback during sync/poll */
+/* alternatively deliver them through an add_message-shaped callback.  The callback runs on the engine's worker thread as
+ * soon as the block that completed a message (NNNN line or abort, nav_b_sm.C:47-50, :82-88) has drained -- no sync or poll
+ * needed, so a capture poller + nvx_store_sink see rows while the capture runs.  Calls are serialised (never two at a
+ * time per engine); nvx_engine_sync returns after every callback of the blocks pushed so far has returned.  The
+ * callback must not call back into the same engine.  Messages queued before the callback was installed are delivered
+ * from this call; cb = NULL goes back to queueing for poll. */
 int nvx_engine_set_message_callback(nvx_engine *e, nvx_message_cb cb, void *user);
 
 /* taps of the LAST pushed block (imply sync).  y3: [S][2][n/280] float pairs (I,Q) at 900 Hz */
@@ -131,6 +136,10 @@ typedef struct {
     long long aux_launches;     /* tail carry, s16 -> f32 conversion */
     long long samples;          /* IQ samples (all streams) pushed */
     double demod_stage_ms[6];   /* split of demod_ms: angle/correlation, per-offset sums + arg max, history carry | symbol clock, bit decisions, SITOR-B state machine */
+    long long long_tc_fallbacks;/* long-tap stage launches that were meant for the tensor-core kernel but ran on the CUDA-core one
+                                 * (tap set outside its tile geometry, or a block the TMA unit cannot address); nvx_last_error() says why */
+    long long messages;         /* messages completed (delivered to the callback or queued for poll) */
+    double cascade_ms_min, cascade_ms_max;   /* fastest / slowest single launch of the fused-FIR kernel (or the long-path stage trio) */
 } nvx_stats;
 /* on: 0 = off, 1 = time the fused-FIR kernel only (two event records per block), 2 = also every demod stage */
 int nvx_engine_enable_timing(nvx_engine *e, int on);

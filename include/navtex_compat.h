@@ -2,7 +2,8 @@
  *
  * A host written against the reference headers (capt_sched.c:17-18, :511, :554, :612; nav_sched.C)
  * keeps calling exactly these names and links against libnavtex_compat.so instead of
- * fir1cpp.o / fir2cpp.o / fir3cpp.o / decoder.o / nav_b_sm.o / nav_sched.o:
+ * fir1cpp.o / fir2cpp.o / fir3cpp.o / decoder.o / nav_b_sm.o (and, if it likes, nav_sched.o: the reference's own
+ * nav_sched.C also compiles UNMODIFIED against the same-named shim headers in include/compat/ and links on top):
  *
  *   extern "C" void init_fir_filter1();                    receiver/fir1cpp.h:2
  *   extern "C" void sample_in_1(double I, double Q);       receiver/fir1cpp.h:3
@@ -60,7 +61,9 @@ class fir_filter3 {
     void sample_in(double sample_I, double sample_Q);
     decoder *output_dec;
 };
-void init_fir_filter2(fir_filter3 *ff3_518, fir_filter3 *ff3_490);
-void sample_in_2(double sample_I, double sample_Q);
+void init_fir_filter2(fir_filter3 *ff3_518, fir_filter3 *ff3_490);   /* fir2cpp.h:3 */
+void sample_in_2(double sample_I, double sample_Q);                    /* fir2cpp.h:4: aborts (no per-stage push) */
+void fir_in_2(double sample_I, double sample_Q);                       /* fir2cpp.h:5: aborts */
+void fir_in_2_490(double sample_I, double sample_Q);                   /* fir2cpp.h:6: aborts */
 #endif
 #endif

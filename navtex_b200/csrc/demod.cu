@@ -150,7 +150,9 @@ __device__ __forceinline__ void fsm_bit(FsmState& s, Emit& e, bool is_y) {
 __device__ __forceinline__ size_t pitch_y(int p_max) { return (size_t)kHistY + p_max; }
 __device__ __forceinline__ size_t pitch_c(int p_max) { return (size_t)kHistC + p_max + kPadC; }
 __host__ __device__ __forceinline__ size_t pitch_p(int p_max) { return ((size_t)p_max / kSpb + 2 + 15) & ~(size_t)15; }   // picks (bytes)
-__host__ __device__ __forceinline__ size_t pitch_b(int p_max) { return ((size_t)p_max / kSpb + 8 + 15) & ~(size_t)15; }   // bits (elements)
+// bits per block: a bit normally takes 9 samples, but while the tracked offset slews by -1 per evaluation the next trigger comes
+// 8 samples after the previous one (decoder.C:217-249), so a block of P samples can hold up to P / 8 + 1 bits
+__host__ __device__ __forceinline__ size_t pitch_b(int p_max) { return ((size_t)p_max / (kSpb - 1) + 2 + 15) & ~(size_t)15; }   // bits (elements)
 
 // decoder.C:48-52
 __device__ __forceinline__ double angle_of(float2 cur, float2 prev) {
@@ -576,7 +578,7 @@ cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_s
     mark(4, s_seq);
     symbol_clock_kernel<<<seq_ctas, kSeqWarps * 32, kSeqSmem, s_seq>>>(a);
     mark(5, s_seq);
-    bit_decide_kernel<<<dim3((unsigned)((a.n_new / kSpb + 2 + 127) / 128), a.channels), 128, 0, s_seq>>>(a);
+    bit_decide_kernel<<<dim3((unsigned)((a.n_new / (kSpb - 1) + 2 + 127) / 128), a.channels), 128, 0, s_seq>>>(a);
     mark(6, s_seq);
     fsm_kernel<<<seq_ctas, kSeqWarps * 32, kSeqSmem, s_seq>>>(a);
     mark(7, s_seq);

@@ -29,9 +29,8 @@ namespace nvx {
 int cascade_box_elems(bool s16);
 int cascade_tap_class(int n1, int n2, int n3);
 int cascade_warm_super(int tap_class);
-cudaError_t cascade_upload_constants(int tap_class, const double* h1, int n1, const double* h2, int n2, const double* h3, int n3,
-                                     cudaStream_t stream);
-cudaError_t cascade_launch(const CascadeArgs& a, int tap_class, bool custom_taps, bool s16, cudaStream_t stream);
+void cascade_fill_taps(int tap_class, const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, CascadeTaps* out);
+cudaError_t cascade_launch(const CascadeArgs& a, const CascadeTaps& taps, int tap_class, bool custom_taps, bool s16, cudaStream_t stream);
 int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class);
 }  // namespace nvx
 
@@ -135,6 +134,7 @@ struct nvx_engine {
     long long sb_abs = 0;
     int last_P = 0;
     bool custom_taps = false;
+    nvx::CascadeTaps taps;                // this engine's filter constants: passed in the parameter block of every cascade launch
     nvx::NcoParam* d_nco = nullptr;       // per-stream NCO parameters (general-NCO kernel variant), else null
     // long-tap path (tap counts other than 37 / 47 / 71): per-stage kernels, intermediates and histories in HBM
     bool long_taps = false;
@@ -143,6 +143,8 @@ struct nvx_engine {
     float2 *y1buf = nullptr, *y2buf = nullptr;
     int lcur = 0;
     nvx::LongTcStage* ltc[2] = {nullptr, nullptr};   // tensor-core variants of stages 1 and 2 (null: CUDA-core kernel)
+    bool ltc_wanted[2] = {false, false};  // the tensor-core kernel was asked for (NVX_LONG_TC mask) for that stage
+    nvx::LongStageTaps ltaps[3];          // this engine's long-path taps: passed in the parameter block of every stage launch
     std::vector<int> stream_tag;          // optional [S][2] message tags
     bool serial = false;                  // NVX_PIPELINE=serial: the next cascade waits for this block's whole demod
     bool ff_on_main = true;               // feed-forward demod kernels follow the cascade on the main stream
@@ -156,6 +158,7 @@ struct nvx_engine {
     std::mutex mu;
     std::condition_variable cv;
     long long queued = 0, drained = 0;      // blocks handed to / finished by the worker
+    long long delivered = 0;                // messages completed so far (callback or queue)
     bool stop = false;
     int worker_rc = 0;
     // timing
@@ -257,7 +260,11 @@ void collect_spans(nvx_engine* e) {
     for (const auto& sp : e->spans) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e->ev_pool[sp.a], e->ev_pool[sp.b]);
-        if (sp.kind == 0) e->stats.cascade_ms += ms;
+        if (sp.kind == 0) {
+            e->stats.cascade_ms += ms;
+            if (e->stats.cascade_ms_min == 0.0 || ms < e->stats.cascade_ms_min) e->stats.cascade_ms_min = ms;
+            if (ms > e->stats.cascade_ms_max) e->stats.cascade_ms_max = ms;
+        }
         else if (sp.kind == 1) e->stats.demod_ms += ms;
         else e->stats.demod_stage_ms[sp.kind - 2] += ms;
     }
@@ -278,8 +285,22 @@ int drain_events(nvx_engine* e, int b) {
                               (size_t)n, &out);
     }
     if (!out.empty()) {
-        std::lock_guard<std::mutex> lk(e->mu);
-        for (auto& m : out) e->ready.push_back(std::move(m));
+        // With a callback installed the messages are delivered right here, on the worker thread, as soon as the block that
+        // completed them has drained -- the reference calls add_message the moment NNNN or an abort is seen
+        // (nav_b_sm.C:47-50, :82-88).  Without one they queue for nvx_engine_poll_messages.
+        nvx_message_cb cb;
+        void* user;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            cb = e->cb; user = e->cb_user;
+            if (!cb) for (auto& m : out) e->ready.push_back(std::move(m));
+            e->delivered += (long long)out.size();
+        }
+        if (cb)
+            for (auto& m : out) {
+                std::string bb = m.bbbb, t = m.text;
+                cb(user, m.stream, &bb[0], &t[0], m.freq);
+            }
     }
     return rc;
 }
@@ -313,16 +334,20 @@ void wait_drained(nvx_engine* e, long long upto) {
     e->cv.wait(lk, [&] { return e->drained >= upto; });
 }
 
+// messages that were queued before a callback was installed
 void deliver_callbacks(nvx_engine* e) {
-    if (!e->cb) return;
     std::vector<nvx::AssembledMessage> take;
+    nvx_message_cb cb;
+    void* user;
     {
         std::lock_guard<std::mutex> lk(e->mu);
+        cb = e->cb; user = e->cb_user;
+        if (!cb) return;
         take.swap(e->ready);
     }
     for (auto& m : take) {
         std::string bb = m.bbbb, t = m.text;
-        e->cb(e->cb_user, m.stream, &bb[0], &t[0], m.freq);
+        cb(user, m.stream, &bb[0], &t[0], m.freq);
     }
 }
 
@@ -343,6 +368,12 @@ int sync_engine(nvx_engine* e) {
     if (rc == NVX_ERR_OVERFLOW) return fail(rc, "an event buffer overflowed");
     if (rc) return fail(rc, "event download failed");
     return 0;
+}
+
+// a long-tap stage that was meant for the tensor cores ran on the CUDA-core kernel: counted, and explained in nvx_last_error()
+void note_tc_fallback(nvx_engine* e, int stage, const char* why) {
+    e->stats.long_tc_fallbacks++;
+    fail(0, "note: long-tap stage %d ran on the CUDA-core kernel: %s", stage, why);
 }
 
 int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
@@ -404,23 +435,31 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         la.in = d_x; la.hist = e->lhist[0][cur]; la.out = e->y1buf; la.n_in = n; la.out_pitch = p1; la.out_off = 0;
         la.rows_in = e->S; la.stage = 0; la.s16 = s16; la.k_abs = e->sb_abs * (kSuper / NVX_D1); la.nco = e->d_nco;
         cudaError_t tc = e->ltc[0] ? long_tc_launch(e->ltc[0], la, e->lst[0], n, e->stream) : cudaErrorNotSupported;
-        if (tc == cudaErrorNotSupported) tc = long_launch(la, e->lst[0], n, e->stream);   // 252 k -> 63 k, mixed: one row per channel
+        if (tc == cudaErrorNotSupported) {         // 252 k -> 63 k, mixed: one row per channel
+            if (e->ltc_wanted[0]) note_tc_fallback(e, 1, e->ltc[0] ? "this block cannot be described to the TMA unit (pointer or pitch not 16-byte aligned)"
+                                                                    : "the tap set does not fit the tensor-core tile");
+            tc = long_launch(la, e->lst[0], e->ltaps[0], n, e->stream);
+        }
         CU_TRY(tc);
         CU_TRY(long_carry(e->lhist[0][cur], d_x, n, e->lhist[0][nx], e->S, e->lst[0].H, n, s16, e->stream));
         la.in = e->y1buf; la.hist = e->lhist[1][cur]; la.out = e->y2buf; la.n_in = n / NVX_D1; la.out_pitch = p2;
         la.rows_in = e->channels; la.stage = 1; la.s16 = 0; la.nco = nullptr;
         tc = e->ltc[1] ? long_tc_launch(e->ltc[1], la, e->lst[1], p1, e->stream) : cudaErrorNotSupported;
-        if (tc == cudaErrorNotSupported) tc = long_launch(la, e->lst[1], p1, e->stream);   // 63 k -> 9 k
+        if (tc == cudaErrorNotSupported) {         // 63 k -> 9 k
+            if (e->ltc_wanted[1]) note_tc_fallback(e, 2, e->ltc[1] ? "this block cannot be described to the TMA unit (pointer or pitch not 16-byte aligned)"
+                                                                    : "the tap set does not fit the tensor-core tile");
+            tc = long_launch(la, e->lst[1], e->ltaps[1], p1, e->stream);
+        }
         CU_TRY(tc);
         CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->channels, e->lst[1].H, n / NVX_D1, 0, e->stream));
         la.in = e->y2buf; la.hist = e->lhist[2][cur]; la.out = e->y3buf[b]; la.n_in = n / (NVX_D1 * NVX_D2);
         la.out_pitch = ca.y3_pitch; la.out_off = ca.y3_off; la.stage = 2;
-        CU_TRY(long_launch(la, e->lst[2], p2, e->stream));                // 9 k -> 900
+        CU_TRY(long_launch(la, e->lst[2], e->ltaps[2], p2, e->stream));                // 9 k -> 900
         CU_TRY(long_carry(e->lhist[2][cur], e->y2buf, p2, e->lhist[2][nx], e->channels, e->lst[2].H, la.n_in, 0, e->stream));
         e->lcur = nx;
         e->stats.aux_launches += 5;
     } else {
-        CU_TRY(cascade_launch(ca, e->tap_class, e->custom_taps, s16, e->stream));
+        CU_TRY(cascade_launch(ca, e->taps, e->tap_class, e->custom_taps, s16, e->stream));
     }
     if (e->timing) CU_TRY(cudaEventRecord(t1, e->stream));
 
@@ -575,7 +614,7 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     }
     // per block and channel: at most one character plus one abort per 14 bits ... generous bound
     e->ev_cap = 2 * (e->P_max / 63 + 2) + 8;
-    e->bit_cap = cfg->keep_bits ? e->P_max / 9 + 2 : 0;
+    e->bit_cap = cfg->keep_bits ? e->P_max / 8 + 2 : 0;      // the symbol clock may run one sample per bit fast while it slews
 #define CREATE_TRY(expr)                                                                                      \
     do {                                                                                                      \
         cudaError_t e__ = (expr);                                                                             \
@@ -635,20 +674,29 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     }
     if (e->long_taps) {
         static const double d1[NVX_T1] = {NVX_H1_VALUES}, d2[NVX_T2] = {NVX_H2_VALUES}, d3[NVX_T3] = {NVX_H3_VALUES};
-        CREATE_TRY(nvx::long_upload_taps(cfg->h1 ? cfg->h1 : d1, e->lst[0].T, cfg->h2 ? cfg->h2 : d2, e->lst[1].T,
-                                         cfg->h3 ? cfg->h3 : d3, e->lst[2].T, e->stream));
+        const double* hh[3] = {cfg->h1 ? cfg->h1 : d1, cfg->h2 ? cfg->h2 : d2, cfg->h3 ? cfg->h3 : d3};
+        for (int k = 0; k < 3; ++k)
+            if (!nvx::long_fill_taps(e->lst[k], hh[k], &e->ltaps[k])) { free_engine(e); return fail(NVX_ERR_ARG, "stage %d: %d taps do not fit the long-tap kernel", k + 1, e->lst[k].T); }
         for (int k = 0; k < 3; ++k)
             for (int q = 0; q < 2; ++q)
                 CREATE_TRY(cudaMalloc(&e->lhist[k][q], (size_t)(k == 0 ? e->S : e->channels) * e->lst[k].H * sizeof(float2)));
         // stages 1 and 2 on the tensor cores where the band matrix fits (fir_long_tc.cu); NVX_LONG_TC is a mask (bit 0: stage
         // 1, bit 1: stage 2; 0 keeps the CUDA-core kernels, whose output is bit-identical across blockings)
         const int tc_mask = getenv("NVX_LONG_TC") ? atoi(getenv("NVX_LONG_TC")) : 3;
-        if (tc_mask & 1) e->ltc[0] = nvx::long_tc_prepare(NVX_D1, e->lst[0].T, cfg->h1 ? cfg->h1 : d1, e->stream);
-        if (tc_mask & 2) e->ltc[1] = nvx::long_tc_prepare(NVX_D2, e->lst[1].T, cfg->h2 ? cfg->h2 : d2, e->stream);
+        e->ltc_wanted[0] = (tc_mask & 1) != 0;
+        e->ltc_wanted[1] = (tc_mask & 2) != 0;
+        if (tc_mask & 1) e->ltc[0] = nvx::long_tc_prepare(NVX_D1, e->lst[0].T, hh[0], e->stream);
+        if (tc_mask & 2) e->ltc[1] = nvx::long_tc_prepare(NVX_D2, e->lst[1].T, hh[1], e->stream);
+        // a stage the tensor-core kernel does not serve (e.g. stage 2 beyond 959 taps) runs on the CUDA-core kernel: same
+        // results to rounding, about half the speed.  Not an error, but never silent: nvx_last_error() says so after create
+        // and nvx_stats.long_tc_fallbacks counts every such stage launch.
+        for (int k = 0; k < 2; ++k)
+            if (e->ltc_wanted[k] && !e->ltc[k])
+                fail(0, "note: long-tap stage %d (%d taps) is not served by the tensor-core kernel and runs on the CUDA-core kernel", k + 1, e->lst[k].T);
         CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->channels * (cfg->max_block / NVX_D1) * sizeof(float2)));
         CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));
     } else {
-        CREATE_TRY(nvx::cascade_upload_constants(e->tap_class, cfg->h1, n[0], cfg->h2, n[1], cfg->h3, n[2], e->stream));
+        nvx::cascade_fill_taps(e->tap_class, cfg->h1, n[0], cfg->h2, n[1], cfg->h3, n[2], &e->taps);
     }
     if (!nco.empty()) {
         CREATE_TRY(cudaMalloc(&e->d_nco, nco.size() * sizeof(nvx::NcoParam)));
@@ -671,7 +719,8 @@ void nvx_engine_destroy(nvx_engine* e) { free_engine(e); }
 int nvx_engine_reset(nvx_engine* e) {
     if (!e) return fail(NVX_ERR_ARG, "null engine");
     CU_TRY(cudaSetDevice(e->cfg.device));
-    sync_engine(e);
+    const int rc_sync = sync_engine(e);
+    if (rc_sync == NVX_ERR_CUDA) return rc_sync;   // a dead context cannot be reset; an event-buffer overflow of the old run can
     {
         std::lock_guard<std::mutex> lk(e->mu);
         e->ready.clear();
@@ -759,7 +808,11 @@ int nvx_engine_try_poll_messages(nvx_engine* e, const nvx_message** msgs, size_t
 
 int nvx_engine_set_message_callback(nvx_engine* e, nvx_message_cb cb, void* user) {
     if (!e) return fail(NVX_ERR_ARG, "null engine");
-    e->cb = cb; e->cb_user = user;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->cb = cb; e->cb_user = user;
+    }
+    deliver_callbacks(e);                  // anything queued before the callback existed goes out first, in order
     return 0;
 }
 
@@ -815,6 +868,10 @@ int nvx_engine_get_stats(nvx_engine* e, nvx_stats* out, int reset) {
     if (!e || !out) return fail(NVX_ERR_ARG, "null argument");
     int rc = sync_engine(e);
     *out = e->stats;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        out->messages = e->delivered;
+    }
     if (reset) e->stats = nvx_stats{};
     return rc;
 }

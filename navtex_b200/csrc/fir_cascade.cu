@@ -8,7 +8,8 @@
 namespace nvx {
 
 template <bool kImm, bool kGenNco, bool kS16, int kClass>
-__global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeArgs a) {
+__global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeParams<kClass> prm) {
+    const CascadeArgs& a = prm.a;
     using F = InFmt<kS16, kClass>;
     using G = Geo<kClass>;
     constexpr int kWarmSuper = G::kWarm, kHalo = G::kWarm * kSuper, kLive1 = G::kLive1, kLive2 = G::kLive2, kLive3 = G::kLive3;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) 
                     if (nco_idx[c] >= kNcoDen) nco_idx[c] -= kNcoDen;
                 }
             }
-            cascade_step<kImm, kGenNco, kS16, kClass>(st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3, nl);
+            cascade_step<kImm, kGenNco, kS16, kClass>(prm.taps, prm.nco, st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3, nl);
             phase += 7;
             if (phase >= kNcoPeriod) phase -= kNcoPeriod;
         }
@@ -155,35 +156,23 @@ int cascade_tap_class(int n1, int n2, int n3) {
 }
 int cascade_warm_super(int tap_class) { return tap_class == 1 ? Geo<1>::kWarm : Geo<0>::kWarm; }
 
-cudaError_t cascade_upload_constants(int tap_class, const double* h1, int n1, const double* h2, int n2, const double* h3, int n3,
-                                     cudaStream_t stream) {
+// the filter constants of one engine (host side; they travel in the kernel parameter block of every launch)
+void cascade_fill_taps(int tap_class, const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, CascadeTaps* out) {
     static const double d1[NVX_T1] = {NVX_H1_VALUES};
     static const double d2[NVX_T2] = {NVX_H2_VALUES};
     static const double d3[NVX_T3] = {NVX_H3_VALUES};
     if (!h1) { h1 = d1; n1 = NVX_T1; }
     if (!h2) { h2 = d2; n2 = NVX_T2; }
     if (!h3) { h3 = d3; n3 = NVX_T3; }
-    cudaError_t e;
-    if (tap_class == 1) {
-        TapSet<1> t = {};
-        fill_taps<1>(h1, n1, h2, n2, h3, n3, &t);
-        e = cudaMemcpyToSymbolAsync(c_taps1, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
-    } else {
-        TapSet<0> t = {};
-        fill_taps<0>(h1, n1, h2, n2, h3, n3, &t);
-        e = cudaMemcpyToSymbolAsync(c_taps0, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
-    }
-    if (e != cudaSuccess) return e;
-    NcoTable n = {};
+    *out = CascadeTaps{};
+    if (tap_class == 1) fill_taps<1>(h1, n1, h2, n2, h3, n3, &out->t1);
+    else fill_taps<0>(h1, n1, h2, n2, h3, n3, &out->t0);
     for (int i = 0; i < kNcoPeriod + NVX_D2; ++i) {
         const int k = i % kNcoPeriod;
         // same expression as fir2cpp.C:105-106, rounded once to float
-        n.w[i].x = (float)cos((2 * M_PI * k * 14000) / 63000);
-        n.w[i].y = (float)-sin((2 * M_PI * k * 14000) / 63000);
+        out->nco.w[i].x = (float)cos((2 * M_PI * k * 14000) / 63000);
+        out->nco.w[i].y = (float)-sin((2 * M_PI * k * 14000) / 63000);
     }
-    e = cudaMemcpyToSymbolAsync(c_nco, &n, sizeof n, 0, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(stream);
 }
 
 // warps that are resident at once across the device, leaving `reserved_sms` SMs to the sequential demod kernels:
@@ -206,7 +195,7 @@ int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class) 
 }
 
 template <bool kS16, int kClass>
-static cudaError_t launch_fmt(const CascadeArgs& a, bool custom_taps, cudaStream_t stream) {
+static cudaError_t launch_fmt(const CascadeArgs& a, const CascadeTaps& taps, bool custom_taps, cudaStream_t stream) {
     const size_t smem = InFmt<kS16, kClass>::kSmemBytes;
     const bool gen = a.nco != nullptr;
     // immediates only for the reference taps themselves; every other set (class 0 or 1) reads the constant bank
@@ -220,13 +209,17 @@ static cudaError_t launch_fmt(const CascadeArgs& a, bool custom_taps, cudaStream
     constexpr int kWarpsPerCta = InFmt<kS16, kClass>::kWarps;
     const long long warps = (long long)((a.streams + 31) / 32) * a.segs;
     const unsigned grid = (unsigned)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
-    kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(a);
+    CascadeParams<kClass> prm;
+    prm.a = a;
+    if constexpr (kClass == 1) prm.taps = taps.t1; else prm.taps = taps.t0;
+    prm.nco = taps.nco;
+    kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(prm);
     return cudaGetLastError();
 }
 
-cudaError_t cascade_launch(const CascadeArgs& a, int tap_class, bool custom_taps, bool s16, cudaStream_t stream) {
-    if (tap_class == 1) return s16 ? launch_fmt<true, 1>(a, true, stream) : launch_fmt<false, 1>(a, true, stream);
-    return s16 ? launch_fmt<true, 0>(a, custom_taps, stream) : launch_fmt<false, 0>(a, custom_taps, stream);
+cudaError_t cascade_launch(const CascadeArgs& a, const CascadeTaps& taps, int tap_class, bool custom_taps, bool s16, cudaStream_t stream) {
+    if (tap_class == 1) return s16 ? launch_fmt<true, 1>(a, taps, true, stream) : launch_fmt<false, 1>(a, taps, true, stream);
+    return s16 ? launch_fmt<true, 0>(a, taps, custom_taps, stream) : launch_fmt<false, 0>(a, taps, custom_taps, stream);
 }
 
 }  // namespace nvx

@@ -162,13 +162,24 @@ struct CascadeArgs {
     long long y3_off;
 };
 
+// Everything a launch needs travels in the kernel parameter block (constant bank 0, __grid_constant__): the tap set and the NCO
+// table are PER ENGINE, so engines with different filters can be alive on one device at the same time.  Taps are read as
+// constant-bank operands of the FFMA2s exactly as they would be from a __constant__ symbol.
+template <int kClass>
+struct CascadeParams {
+    CascadeArgs a;
+    TapSet<kClass> taps;
+    NcoTable nco;
+};
+static_assert(sizeof(CascadeParams<kTapClasses - 1>) <= 4096, "kernel parameter block");
+// host-side copy of an engine's filter constants (both classes' layouts; only the engine's own class is filled)
+struct CascadeTaps {
+    TapSet<0> t0;
+    TapSet<1> t1;
+    NcoTable nco;
+};
+
 #ifdef NVX_CASCADE_DEVICE_CODE
-__constant__ TapSet<0> c_taps0;
-__constant__ TapSet<1> c_taps1;
-__constant__ NcoTable c_nco;
-template <int kClass> __device__ __forceinline__ const TapSet<kClass>& class_taps();
-template <> __device__ __forceinline__ const TapSet<0>& class_taps<0>() { return c_taps0; }
-template <> __device__ __forceinline__ const TapSet<1>& class_taps<1>() { return c_taps1; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -195,8 +206,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-template <bool kImm, int kClass> __device__ __forceinline__ float tap1(int i) { return kImm ? (float)kH1[i] : class_taps<kClass>().h1[i]; }
-template <bool kImm, int kClass> __device__ __forceinline__ float tap2(int i) { return kImm ? (float)kH2[i] : class_taps<kClass>().h2[i]; }
+template <bool kImm, int kClass> __device__ __forceinline__ float tap1(const TapSet<kClass>& ts, int i) { return kImm ? (float)kH1[i] : ts.h1[i]; }
+template <bool kImm, int kClass> __device__ __forceinline__ float tap2(const TapSet<kClass>& ts, int i) { return kImm ? (float)kH2[i] : ts.h2[i]; }
 
 __device__ __forceinline__ float2 fma2(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
 
@@ -226,8 +237,8 @@ __device__ __forceinline__ float2 iq_of(int packed) {
 }
 
 template <bool kImm, bool kGenNco, bool kS16, int kClass>
-__device__ __forceinline__ void cascade_step(CascadeState<kClass>& st, const float4* __restrict__ row, int nco_phase,
-                                             const int r10, float2 (&y3)[2], NcoLane& nl) {
+__device__ __forceinline__ void cascade_step(const TapSet<kClass>& ts, const NcoTable& nco, CascadeState<kClass>& st,
+                                             const float4* __restrict__ row, int nco_phase, const int r10, float2 (&y3)[2], NcoLane& nl) {
     using G = Geo<kClass>;
     constexpr int kLive1 = G::kLive1, kLive2 = G::kLive2, kLive3 = G::kLive3;
     static_assert(!kImm || kClass == 0, "immediate taps are the reference set");
@@ -260,7 +271,7 @@ __device__ __forceinline__ void cascade_step(CascadeState<kClass>& st, const flo
 #pragma unroll
         for (int r = 0; r < NVX_D1; ++r) {
 #pragma unroll
-            for (int j = 0; 4 * j + 3 - r < G::T1; ++j) w[q + j] = fma2(xs[r], tap1<kImm, kClass>(4 * j + 3 - r), w[q + j]);
+            for (int j = 0; 4 * j + 3 - r < G::T1; ++j) w[q + j] = fma2(xs[r], tap1<kImm, kClass>(ts, 4 * j + 3 - r), w[q + j]);
         }
         const float2 y1 = w[q];
         // NCO mix (fir2cpp.C:115-124): ch0 = y1 * (re + j im), ch1 = y1 * (re - j im), (re, im) = (cos, -sin)
@@ -274,7 +285,7 @@ __device__ __forceinline__ void cascade_step(CascadeState<kClass>& st, const flo
                     nl.w[c] = make_float2(fmaf(-rot.y, nl.step[c].y, rot.x * nl.step[c].x), fmaf(rot.x, nl.step[c].y, rot.y * nl.step[c].x));
             }
         } else {
-            const float2 rot = c_nco.w[nco_phase + q];
+            const float2 rot = nco.w[nco_phase + q];
             const float ar = y1.x * rot.x, br = y1.y * rot.x;
             m[0] = make_float2(fmaf(-y1.y, rot.y, ar), fmaf(y1.x, rot.y, br));
             m[1] = make_float2(fmaf(y1.y, rot.y, ar), fmaf(-y1.x, rot.y, br));
@@ -282,7 +293,7 @@ __device__ __forceinline__ void cascade_step(CascadeState<kClass>& st, const flo
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
-            for (int j = 0; 7 * j + 6 - q < G::T2; ++j) b[c][j] = fma2(m[c], tap2<kImm, kClass>(7 * j + 6 - q), b[c][j]);
+            for (int j = 0; 7 * j + 6 - q < G::T2; ++j) b[c][j] = fma2(m[c], tap2<kImm, kClass>(ts, 7 * j + 6 - q), b[c][j]);
         }
     }
 #pragma unroll
@@ -296,7 +307,7 @@ __device__ __forceinline__ void cascade_step(CascadeState<kClass>& st, const flo
         // stage 3: sample 10p + r10 feeds outputs p + j with tap 10 j + 9 - r10 (table row r10; the last j only
         // carries a non-zero tap for the largest r10)
 #pragma unroll
-        for (int j = 0; j < kLive3; ++j) st.a3[c][j] = fma2(y2, class_taps<kClass>().h3t[r10][j], st.a3[c][j]);
+        for (int j = 0; j < kLive3; ++j) st.a3[c][j] = fma2(y2, ts.h3t[r10][j], st.a3[c][j]);
     }
     if (r10 == NVX_D3 - 1) {
 #pragma unroll

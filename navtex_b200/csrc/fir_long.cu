@@ -7,9 +7,9 @@ namespace nvx {
 
 namespace {
 
-constexpr int kTapSlots = 1152;                     // per stage: D * J <= 1024 + D * kLongR
-__constant__ float c_long_taps[3][kTapSlots];       // [stage][p * J + j] = h[D j + D - 1 - p] (0 beyond T)
-__constant__ float2 c_long_nco[kNcoPeriod];         // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
+// The taps of the launched stage and the reference NCO table travel in the kernel parameter block (constant bank 0,
+// __grid_constant__): per engine, so engines with different tap sets can be alive on one device, and still warp-uniform
+// constant-bank operands for the FFMA2 loops.
 
 __device__ __forceinline__ float2 ffma2s(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
 
@@ -34,7 +34,8 @@ __device__ __forceinline__ int slot(int f) { return f + f / (kLongR * D); }
 // grid (tiles, input rows).  STAGE 0 (the first stage) writes TWO output rows per input row: its 63 kHz outputs rotated by
 // each channel's NCO (fir2cpp.C:112-128), so that the second stage is a plain FIR over channel rows.
 template <int D, int STAGE>
-__global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a, const int J, const long long in_pitch) {
+__global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a, const int J, const long long in_pitch,
+                                                                const __grid_constant__ LongStageTaps tp) {
     extern __shared__ __align__(16) float2 s_x[];
     const int H = D * J;
     const int F = D * (kLongTile + J - 1);                    // inputs staged per tile
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a
     float2 acc[kLongR];
 #pragma unroll
     for (int u = 0; u < kLongR; ++u) acc[u] = make_float2(0.f, 0.f);
-    const float* taps = c_long_taps[STAGE];
+    const float* taps = tp.h;
     constexpr int kLane = kLongR * D + 1;
 #pragma unroll 1
     for (int p = 0; p < D; ++p) {
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a
                     rot[c] = make_float2(cs, -sn);
                 }
             } else {
-                rot[0] = c_long_nco[k9];
+                rot[0] = tp.nco[k9];
                 rot[1] = make_float2(rot[0].x, -rot[0].y);     // "490": conjugate rotation (fir2cpp.C:121-124)
             }
             if (k0 + (long long)kLongR * t + u < n_out) {
@@ -169,7 +170,7 @@ __global__ void long_carry_kernel(const float2* __restrict__ old_hist, const Sam
 }
 
 template <int D, int STAGE>
-cudaError_t launch_one(const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream) {
+cudaError_t launch_one(const LongArgs& a, const LongStage& st, const LongStageTaps& tp, long long in_pitch, cudaStream_t stream) {
     const int F = D * (kLongTile + st.J - 1);
     const size_t smem = (size_t)(F + F / (kLongR * D) + 2) * sizeof(float2);
     {   // per device: not cached
@@ -178,7 +179,7 @@ cudaError_t launch_one(const LongArgs& a, const LongStage& st, long long in_pitc
     }
     const long long n_out = a.n_in / D;
     fir_long_kernel<D, STAGE><<<dim3((unsigned)((n_out + kLongTile - 1) / kLongTile), (unsigned)a.rows_in), kLongThreads, smem, stream>>>(
-        a, st.J, in_pitch);
+        a, st.J, in_pitch, tp);
     return cudaGetLastError();
 }
 
@@ -194,35 +195,25 @@ LongStage long_stage(int D, int T) {
     return s;
 }
 
-cudaError_t long_upload_taps(const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, cudaStream_t stream) {
-    static float host[3][kTapSlots];
-    const double* h[3] = {h1, h2, h3};
-    const int n[3] = {n1, n2, n3}, D[3] = {NVX_D1, NVX_D2, NVX_D3};
-    for (int s = 0; s < 3; ++s) {
-        const LongStage st = long_stage(D[s], n[s]);
-        if (n[s] < 1 || n[s] > kLongMaxTaps || st.D * st.J > kTapSlots) return cudaErrorInvalidValue;
-        for (int k = 0; k < kTapSlots; ++k) host[s][k] = 0.f;
-        for (int p = 0; p < st.D; ++p)
-            for (int j = 0; j < st.J; ++j) {
-                const int i = st.D * j + st.D - 1 - p;
-                host[s][p * st.J + j] = i < n[s] ? (float)h[s][i] : 0.f;
-            }
-    }
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_long_taps, host, sizeof host, 0, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
-    float2 nco[kNcoPeriod];
+// host side of one stage's tap block: [p * J + j] = h[D j + D - 1 - p] (0 beyond the set), plus the reference NCO table
+bool long_fill_taps(const LongStage& st, const double* h, LongStageTaps* out) {
+    if (st.T < 1 || st.T > kLongMaxTaps || st.D * st.J > kLongTapSlots) return false;
+    for (int k = 0; k < kLongTapSlots; ++k) out->h[k] = 0.f;
+    for (int p = 0; p < st.D; ++p)
+        for (int j = 0; j < st.J; ++j) {
+            const int i = st.D * j + st.D - 1 - p;
+            out->h[p * st.J + j] = i < st.T ? (float)h[i] : 0.f;
+        }
     for (int k = 0; k < kNcoPeriod; ++k)       // same expression as fir2cpp.C:105-106, rounded once to float
-        nco[k] = make_float2((float)cos((2 * M_PI * k * 14000) / 63000), (float)-sin((2 * M_PI * k * 14000) / 63000));
-    e = cudaMemcpyToSymbolAsync(c_long_nco, nco, sizeof nco, 0, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(stream);
+        out->nco[k] = make_float2((float)cos((2 * M_PI * k * 14000) / 63000), (float)-sin((2 * M_PI * k * 14000) / 63000));
+    return true;
 }
 
-cudaError_t long_launch(const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream) {
+cudaError_t long_launch(const LongArgs& a, const LongStage& st, const LongStageTaps& tp, long long in_pitch, cudaStream_t stream) {
     switch (a.stage) {
-        case 0: return launch_one<NVX_D1, 0>(a, st, in_pitch, stream);
-        case 1: return launch_one<NVX_D2, 1>(a, st, in_pitch, stream);
-        default: return launch_one<NVX_D3, 2>(a, st, in_pitch, stream);
+        case 0: return launch_one<NVX_D1, 0>(a, st, tp, in_pitch, stream);
+        case 1: return launch_one<NVX_D2, 1>(a, st, tp, in_pitch, stream);
+        default: return launch_one<NVX_D3, 2>(a, st, tp, in_pitch, stream);
     }
 }
 

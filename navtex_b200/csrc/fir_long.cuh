@@ -51,9 +51,16 @@ struct LongArgs {
     const NcoParam* nco;      // stage 1: per-stream general NCO or null (reference table)
 };
 
+// taps of one stage regrouped per decimation phase + the reference NCO table: passed by value in the kernel parameter block
+constexpr int kLongTapSlots = 1152;             // D * J <= 1024 + D * kLongR
+struct LongStageTaps {
+    float h[kLongTapSlots];
+    float2 nco[kNcoPeriod];
+};
+
 LongStage long_stage(int D, int T);
-cudaError_t long_upload_taps(const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, cudaStream_t stream);
-cudaError_t long_launch(const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream);
+bool long_fill_taps(const LongStage& st, const double* h, LongStageTaps* out);
+cudaError_t long_launch(const LongArgs& a, const LongStage& st, const LongStageTaps& tp, long long in_pitch, cudaStream_t stream);
 // new_hist = last H samples of (old_hist ++ block[.][0..n)) per row; block rows are `pitch` samples apart, short2 if s16
 cudaError_t long_carry(const float2* old_hist, const void* block, long long pitch, float2* new_hist, int rows, int H, long long n,
                        int s16, cudaStream_t stream);

@@ -82,8 +82,6 @@ __host__ __device__ constexpr int band_copies(int D) { return 8 / (chunk_samples
 constexpr int kMaxSets = 3;                // A sets in tensor memory
 constexpr uint32_t kSetCols = 128;         // {I_hi, I_lo, Q_hi, Q_lo} x 32 columns
 
-__constant__ float2 c_tc_nco[kNcoPeriod];  // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
-
 struct TcArgs {
     CUtensorMap map_gh, map_gl;            // band matrix G[J][32], high / low TF32 parts
     CUtensorMap map_x;                     // this block as [rows][2 n_in] floats / shorts, box = one slot (128 B x 128 rows, SWIZZLE_128B)
@@ -95,6 +93,7 @@ struct TcArgs {
     int rows, s16, T, H, chunks, J, slots, box_rows, mix;
     long long tiles_per_block;             // output tiles per row block
     long long work;                        // row blocks * tiles_per_block
+    float2 nco_tab[kNcoPeriod];            // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < kNcoPeriod) s_nco[threadIdx.x] = c_tc_nco[threadIdx.x];
+    if (threadIdx.x < kNcoPeriod) s_nco[threadIdx.x] = a.nco_tab[threadIdx.x];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -620,10 +619,6 @@ LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t st
     bool ok = cudaMalloc(&s->d_gh, gh.size() * 4) == cudaSuccess && cudaMalloc(&s->d_gl, gl.size() * 4) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(s->d_gh, gh.data(), gh.size() * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(s->d_gl, gl.data(), gl.size() * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
-    float2 nco[kNcoPeriod];
-    for (int k = 0; k < kNcoPeriod; ++k)       // same expression as fir2cpp.C:105-106, rounded once to float
-        nco[k] = make_float2((float)cos((2 * M_PI * k * 14000) / 63000), (float)-sin((2 * M_PI * k * 14000) / 63000));
-    ok = ok && cudaMemcpyToSymbolAsync(c_tc_nco, nco, sizeof nco, 0, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
     if (ok) {
         EncodeTiledFn enc = s->enc = (EncodeTiledFn)fn;
@@ -659,6 +654,8 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     a.n_in = la.n_in; a.in_pitch = in_pitch; a.out_pitch = la.out_pitch; a.out_off = la.out_off; a.k_abs = la.k_abs;
     a.nco = la.nco; a.rows = la.rows_in; a.s16 = la.s16; a.T = s->T; a.H = st.H; a.chunks = s->chunks; a.J = s->J; a.slots = 4; a.box_rows = s->box_rows;
     a.mix = la.stage == 0;
+    for (int k = 0; k < kNcoPeriod; ++k)       // same expression as fir2cpp.C:105-106, rounded once to float
+        a.nco_tab[k] = make_float2((float)cos((2 * M_PI * k * 14000) / 63000), (float)-sin((2 * M_PI * k * 14000) / 63000));
     // TMA boxes and 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by
     // construction).  The block as a 2-D tensor of 32-bit (float2 input) or 16-bit (short2 input) elements, two per sample:
     if (((uintptr_t)la.in & 15) || ((in_pitch * (la.s16 ? 4 : 8)) & 15)) return cudaErrorNotSupported;

@@ -104,7 +104,15 @@ fir_filter3::fir_filter3(decoder* dec) : output_dec(dec) {}
 void fir_filter3::sample_in(double, double) { no_stage_push("fir_filter3::sample_in"); }
 // fir2cpp.C:90-110: remember which state machines sit behind the 518 / 490 branches (their tags label messages)
 void init_fir_filter2(fir_filter3* ff3_518, fir_filter3* ff3_490) {
-    if (ff3_518 && ff3_518->output_dec && ff3_518->output_dec->output_bsm) g_tag[0] = (int)ff3_518->output_dec->output_bsm->freq;
-    if (ff3_490 && ff3_490->output_dec && ff3_490->output_dec->output_bsm) g_tag[1] = (int)ff3_490->output_dec->output_bsm->freq;
+    int tag[2] = {g_tag[0], g_tag[1]};
+    if (ff3_518 && ff3_518->output_dec && ff3_518->output_dec->output_bsm) tag[0] = (int)ff3_518->output_dec->output_bsm->freq;
+    if (ff3_490 && ff3_490->output_dec && ff3_490->output_dec->output_bsm) tag[1] = (int)ff3_490->output_dec->output_bsm->freq;
+    if (tag[0] == g_tag[0] && tag[1] == g_tag[1]) return;
+    g_tag[0] = tag[0]; g_tag[1] = tag[1];
+    // capt_sched.c calls init_fir_filter1 (:554) before init_fir2_wrapper (:612): an engine created with other tags is
+    // replaced (nothing has been pushed yet at that point of the reference's start-up)
+    if (g_engine) { nvx_engine_destroy(g_engine); g_engine = nullptr; g_buf.clear(); ensure_engine(); }
 }
 void sample_in_2(double, double) { no_stage_push("sample_in_2"); }
+void fir_in_2(double, double) { no_stage_push("fir_in_2"); }
+void fir_in_2_490(double, double) { no_stage_push("fir_in_2_490"); }

@@ -37,7 +37,8 @@ class Message(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("cascade_ms", C.c_double), ("demod_ms", C.c_double), ("cascade_launches", C.c_longlong),
                 ("demod_launches", C.c_longlong), ("aux_launches", C.c_longlong), ("samples", C.c_longlong),
-                ("demod_stage_ms", C.c_double * 6)]
+                ("demod_stage_ms", C.c_double * 6), ("long_tc_fallbacks", C.c_longlong), ("messages", C.c_longlong),
+                ("cascade_ms_min", C.c_double), ("cascade_ms_max", C.c_double)]
 
 
 class SynthDesc(C.Structure):
@@ -234,7 +235,7 @@ class Engine:
         return out.view(np.complex64)[..., 0]
 
     def read_bits(self, stream: int, ch: int):
-        cap = self.last_n // BLOCK_ALIGN // 9 + 4
+        cap = self.last_n // BLOCK_ALIGN // 8 + 4
         bits = np.empty(cap, dtype=np.uint8)
         sums = np.empty((cap, 4), dtype=np.float32)
         got = C.c_size_t()

@@ -70,7 +70,8 @@ extern "C" int add_message(char *bbbb, char *message, int freq) {
     return 0;
 }
 
-// ---- interposers --------------------------------------------------------
+// ---- interposers (left out of the timing binary ref_chain_timing: -DNVX_NO_TAPS, linked without --wrap) -------------
+#ifndef NVX_NO_TAPS
 extern "C" {
 void __real__Z11sample_in_2dd(double, double);
 void __wrap__Z11sample_in_2dd(double i, double q) {
@@ -107,6 +108,7 @@ void __wrap__ZN18byte_state_machine11receive_bitEc(void *self, char b) {
     __real__ZN18byte_state_machine11receive_bitEc(self, b);
 }
 }
+#endif
 
 namespace {
 template <class T>

@@ -134,6 +134,108 @@ def test_c_and_relinked_hosts(tmp_path):
     assert out.stdout == want
 
 
+def test_reference_nav_sched_and_wav_c_host_on_the_gpu(tmp_path):
+    """BASELINE.json configs[0] through the reference's own files: receiver/wav.c reads the WAV (wav_open / wav_read,
+    wav.c:469, :494-528), the reference's unmodified nav_sched.C wires the object graph (compiled against include/compat/),
+    sample_in_1 feeds libnavtex_compat.so -- and the host's add_message receives the golden call of the unmodified CPU chain.
+    The binary is built where /root/reference is mounted (oracle/Makefile: compat_wav_host) and travels prebuilt."""
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "compat_wav_host")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/compat_wav_host was not built (reference tree absent at build time)")
+    g = np.load(os.path.join(GOLDEN, "clean518.npz"))
+    want = "".join("%d|%s|%d\n%s\n" % (int(f), str(b), len(str(t)), str(t)) for f, b, t in zip(g["msg_freq"], g["msg_bbbb"], g["msg_text"]))
+    wav = str(tmp_path / "navtex518.wav")
+    synth.write_wav(wav, cases.build("clean518"))
+    out = subprocess.run([exe, wav], capture_output=True, text=True, check=True)
+    assert out.stdout == want and want.startswith("518|PA12|")
+
+
+def test_two_engines_with_different_taps_on_one_device():
+    """Tap sets are per engine (kernel parameter block), not per process: three engines alive on one device -- reference taps,
+    a replacement class-0 set, and a long-tap set -- interleave their pushes and each equals its own oracle."""
+    from scipy import signal
+
+    iq = cases.build("clean518")
+    n = iq.size // 2 // 280 * 280
+    x = np.ascontiguousarray(iq[: 2 * n].reshape(1, n, 2))
+    short = (signal.firwin(33, 21000, window=("kaiser", 6.0), fs=252000), signal.firwin(45, 2200, window=("kaiser", 6.5), fs=63000),
+             signal.firwin(69, 260, window=("kaiser", 5.0), fs=9000))
+    long_ = tuple(signal.firwin(129, fc, window=("kaiser", 8.0), fs=fs) for fc, fs in ((20000, 252000), (2000, 63000), (250, 9000)))
+    sets = [None, short, long_]
+    engs = [engine.Engine(1, n // 2, keep_bits=True, taps=t) for t in sets]          # all three alive before the first push
+    oracles = [ol.run_oracle(iq[: 2 * n]) if t is None else ol.run_oracle(iq[: 2 * n], h1=t[0], h2=t[1], h3=t[2]) for t in sets]
+    y3 = [[], [], []]
+    for half in range(2):                                                             # interleaved: A, B, C, A, B, C
+        for k, e in enumerate(engs):
+            e.push_host(np.ascontiguousarray(x[:, half * (n // 2):(half + 1) * (n // 2)]))
+            y3[k].append(e.read_y3()[0].copy())
+    for k, (e, o) in enumerate(zip(engs, oracles)):
+        got = np.concatenate(y3[k], axis=1)
+        scale = max(np.abs(o.y3["518"]).max(), np.abs(o.y3["490"]).max())
+        for c, tag in enumerate(ol.CHANNELS):
+            assert np.abs(got[c].astype(np.complex128) - o.y3[tag]).max() <= REL_TOL * scale, (k, tag)
+        assert [m[1:] for m in e.poll_messages()] == o.messages, k
+    # the three filter sets really differ at the 900 Hz output
+    assert np.abs(np.concatenate(y3[0], axis=1) - np.concatenate(y3[1], axis=1)).max() > 1e-3 * scale
+    st = engs[2].stats()
+    assert st.long_tc_fallbacks == 0
+    for e in engs:
+        e.close()
+
+
+def test_long_tc_fallback_is_counted_and_explained(monkeypatch):
+    """Stage 2 beyond 959 taps is not served by the tensor-core kernel: it runs on the CUDA-core one, and says so."""
+    from scipy import signal
+
+    taps = (signal.firwin(255, 20000, window=("kaiser", 8.0), fs=252000), signal.firwin(1001, 2000, window=("kaiser", 8.0), fs=63000),
+            signal.firwin(71, 250, window=("kaiser", 7.0), fs=9000))
+    n = 280 * 90
+    eng = engine.Engine(2, n, taps=taps)
+    assert "stage 2" in eng.L.nvx_last_error().decode() and "CUDA-core" in eng.L.nvx_last_error().decode()
+    eng.push_host(np.zeros((2, n, 2), dtype=np.float32))
+    eng.push_host(np.zeros((2, n, 2), dtype=np.float32))
+    st = eng.stats()
+    assert st.long_tc_fallbacks == 2
+    eng.close()
+
+
+def test_callbacks_arrive_while_the_capture_runs():
+    """INTEGRATION.md's pattern: radio callbacks write the rings, the capture poller pumps, nvx_store_sink is the message
+    callback -- rows must appear in the store while the capture is still running (the reference calls add_message the moment
+    NNNN is seen, nav_b_sm.C:82-88), not only at nvx_capture_stop / sync."""
+    import time
+
+    iq = cases.build("clean518").reshape(-1, 2)
+    blk = 280 * 90                                  # 0.1 s blocks
+    eng = engine.Engine(1, blk)
+    store = engine.Store()
+    store.attach(eng)
+    cap = engine.Capture(eng, blk, 8 * blk)
+    cap.start(poll_ms=5)
+    pos, seen_at = 0, None
+    while pos < len(iq):                           # the "radio": 1008-sample callbacks, as fast as the ring takes them
+        n = min(1008, len(iq) - pos)
+        if cap.write(0, iq[pos:pos + n, 0], iq[pos:pos + n, 1]) == 0:
+            pos += n
+        else:
+            time.sleep(0.002)
+        if seen_at is None and len(store.rows()) > 0:
+            seen_at = pos
+    deadline = time.time() + 5.0                   # tail of the capture after the bulletin: the poller is still running
+    while seen_at is None and time.time() < deadline:
+        time.sleep(0.01)
+        if len(store.rows()) > 0:
+            seen_at = pos
+    rows_before_stop = store.rows()
+    cap.stop()
+    assert rows_before_stop and rows_before_stop[0][2] == "PA12", "no message reached the store before nvx_capture_stop"
+    assert store.rows() == rows_before_stop
+    assert eng.stats().messages == 1
+    cap.close(); store.close(); eng.close()
+
+
 def test_two_engines_on_two_devices_in_one_process():
     """One process, one engine per GPU: function attributes and constant-bank tables are per device."""
     import torch
