@@ -144,6 +144,16 @@ typedef struct {
 /* on: 0 = off, 1 = time the fused-FIR kernel only (two event records per block), 2 = also every demod stage */
 int nvx_engine_enable_timing(nvx_engine *e, int on);
 int nvx_engine_get_stats(nvx_engine *e, nvx_stats *out, int reset);
+/* the per-launch times behind cascade_ms (milliseconds, in launch order, since the last get_stats(reset)); *count = how many
+ * there are, at most cap are copied */
+int nvx_engine_get_cascade_spans(nvx_engine *e, float *ms, size_t cap, size_t *count);
+/* device-side fence, no host wait: whatever is queued on nvx_engine_stream() after this call runs after EVERY kernel and
+ * copy of the blocks pushed so far (the demod / state-machine kernels and the event download run on a second stream) */
+int nvx_engine_fence(nvx_engine *e);
+/* page-locked host memory for the push_host_* calls (cudaHostAlloc, portable; write_combined != 0: write-combined pages, faster
+ * for the device to read on some hosts, slow for the CPU to read back) */
+int nvx_pinned_alloc(size_t bytes, int write_combined, void **out);
+int nvx_pinned_free(void *p);
 /* the CUDA stream everything is queued on (cudaStream_t as void*), for callers that produce input on the device */
 void *nvx_engine_stream(nvx_engine *e);
 

@@ -36,7 +36,10 @@ struct nvx_capture {
         long long dropped = 0;
     };
     std::vector<Ring> rings;
-    std::vector<int16_t> block;            // [S][n] staging, stream-major
+    // [S][n] staging, stream-major: two page-locked buffers (nvx_pinned_alloc), so that the engine's H2D copy of pump k is
+    // asynchronous and overlaps the ring drain of pump k + 1
+    int16_t* block[2] = {nullptr, nullptr};
+    unsigned pumps = 0;
     std::thread poller;
     std::atomic<bool> stop{false};
     std::mutex pump_mu;
@@ -53,9 +56,12 @@ long long pump_locked(nvx_capture* c) {
     }
     n -= n % NVX_BLOCK_ALIGN;
     if (n <= 0) return 0;
+    int16_t* const blk = c->block[c->pumps++ & 1];
+    // the copy that last read this buffer was queued two pumps ago; make sure it is over before the buffer is refilled
+    if (const int rc = nvx_engine_wait_ingest(c->eng)) return rc;
     for (int s = 0; s < c->S; ++s) {
         auto& r = c->rings[(size_t)s];
-        int16_t* dst = c->block.data() + (size_t)s * 2 * (size_t)n;
+        int16_t* dst = blk + (size_t)s * 2 * (size_t)n;
         // the producer only ever writes beyond head, so [tail, tail + n) is stable without the lock
         long long at = r.tail % c->ring;
         long long first = n < c->ring - at ? n : c->ring - at;
@@ -64,7 +70,7 @@ long long pump_locked(nvx_capture* c) {
         std::lock_guard<std::mutex> lk(r.mu);
         r.tail += n;
     }
-    const int rc = nvx_engine_push_host_s16(c->eng, c->block.data(), n);
+    const int rc = nvx_engine_push_host_s16(c->eng, blk, n);
     if (rc != 0) return rc;
     return n;
 }
@@ -81,7 +87,15 @@ int nvx_capture_create(nvx_engine* e, int n_streams, long long max_block, long l
     c->max_block = max_block;
     c->rings = std::vector<nvx_capture::Ring>((size_t)n_streams);
     for (auto& r : c->rings) r.buf.assign(2 * (size_t)ring_samples, 0);
-    c->block.assign((size_t)n_streams * 2 * (size_t)max_block, 0);
+    for (int k = 0; k < 2; ++k) {
+        void* p = nullptr;
+        if (const int rc = nvx_pinned_alloc((size_t)n_streams * 2 * (size_t)max_block * sizeof(int16_t), 0, &p)) {
+            nvx_pinned_free(c->block[0]);
+            delete c;
+            return rc;
+        }
+        c->block[k] = static_cast<int16_t*>(p);
+    }
     *out = c;
     return 0;
 }
@@ -143,6 +157,7 @@ int nvx_capture_stop(nvx_capture* c) {
     std::lock_guard<std::mutex> lk(c->pump_mu);
     long long n;
     while ((n = pump_locked(c)) > 0) {}
+    nvx_engine_wait_ingest(c->eng);
     const int rc = c->pump_rc ? c->pump_rc : (n < 0 ? (int)n : 0);
     c->pump_rc = 0;
     return rc;
@@ -160,6 +175,8 @@ void nvx_capture_destroy(nvx_capture* c) {
         c->stop = true;
         c->poller.join();
     }
+    nvx_pinned_free(c->block[0]);      // cudaFreeHost waits for a copy still reading the buffer
+    nvx_pinned_free(c->block[1]);
     delete c;
 }
 

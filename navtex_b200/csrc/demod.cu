@@ -164,10 +164,22 @@ __device__ __forceinline__ double angle_of(float2 cur, float2 prev) {
 
 // grid (tiles, channels), block kThreads: |mask correlation| for samples [tile0, tile0 + kTile); every thread owns three
 // samples (strided by kThreads) so that one resident warp per SM sub-partition still has independent work in flight
+// The CTA of tile 0 also hands the histories over: the last kHistY samples / kHistC correlation values of the previous block
+// (which live at the end of ITS buffers) become the front of this block's buffers.  Nobody else touches those fronts in this
+// kernel (only tile 0 looks back past sample 0), and every later kernel of the block is ordered behind it.
 __global__ void __launch_bounds__(kThreads) angle_corr_kernel(const DemodArgs a) {
     __shared__ double s_ang[kTile + 8];
     const int ch = blockIdx.y, tile0 = blockIdx.x * kTile, t = threadIdx.x;
-    const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max) + kHistY;     // y[m], m >= -kHistY
+    float2* ybuf = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max);
+    const float2* y = ybuf + kHistY;                                          // y[m], m >= -kHistY
+    if (blockIdx.x == 0) {
+        const float2* yp = a.y3_prev + (size_t)ch * pitch_y(a.b.p_max) + a.n_prev;
+        if (t < kHistY) ybuf[t] = yp[t];
+        double* c = a.b.corr + (size_t)ch * pitch_c(a.b.p_max);
+        const double* cp = a.corr_prev + (size_t)ch * pitch_c(a.b.p_max) + a.n_prev;
+        for (int k = t; k < kHistC; k += kThreads) c[k] = cp[k];
+        __syncthreads();
+    }
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
         const int m = tile0 + t + u * kThreads;
@@ -466,21 +478,6 @@ __global__ void __launch_bounds__(kSeqWarps * 32) fsm_kernel(const DemodArgs a) 
     a.ev_count[ch] = em.n;
 }
 
-// slide every history: the last H entries of [hist | new] become the next block's hist.  One CTA per channel.
-__global__ void __launch_bounds__(256) carry_kernel(const DemodArgs a) {
-    __shared__ double s_c[kHistC];
-    __shared__ float2 s_y[kHistY];
-    const int ch = blockIdx.x, t = threadIdx.x;
-    double* corr = a.b.corr + (size_t)ch * pitch_c(a.b.p_max);
-    const float2* y = a.b.y3 + (size_t)ch * pitch_y(a.b.p_max);
-    float2* yn = a.y3_next + (size_t)ch * pitch_y(a.b.p_max);
-    for (int k = t; k < kHistC; k += blockDim.x) s_c[k] = corr[k + a.n_new];
-    if (t < kHistY) s_y[t] = y[t + a.n_new];
-    __syncthreads();
-    for (int k = t; k < kHistC; k += blockDim.x) corr[k] = s_c[k];
-    if (t < kHistY) yn[t] = s_y[t];
-}
-
 __global__ void init_state_kernel(ClockState* clock, FsmState* fsm, int channels) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= channels) return;
@@ -496,7 +493,7 @@ __global__ void init_state_kernel(ClockState* clock, FsmState* fsm, int channels
 
 }  // namespace
 
-int demod_launches_per_block() { return 6; }
+int demod_launches_per_block() { return 5; }
 size_t demod_pick_pitch(int p_max) { return pitch_p(p_max); }
 size_t demod_bit_pitch(int p_max) { return pitch_b(p_max); }
 int demod_reserved_sms(int channels) {
@@ -561,8 +558,7 @@ cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_s
         }
     }
     mark(2, s_ff);
-    carry_kernel<<<a.channels, 256, 0, s_ff>>>(a);
-    mark(3, s_ff);
+    mark(3, s_ff);      // (the history carry used to be a kernel of its own here; angle_corr_kernel does it now)
     // sequential part: few warps, latency-bound, runs beside the next block's cascade on the SMs it leaves free
     if (s_seq != s_ff) {
         cudaError_t e = cudaEventRecord(ff_done, s_ff);

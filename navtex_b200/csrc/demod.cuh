@@ -38,7 +38,7 @@ struct FsmState {
 
 struct DemodBuffers {
     float2* y3;               // [channels][kHistY + p_max]   (the cascade kernel writes at +kHistY); one per block in flight
-    double* corr;             // [channels][kHistC + p_max + kPadC]   |mask correlation| per sample
+    double* corr;             // [channels][kHistC + p_max + kPadC]   |mask correlation| per sample (two buffers, alternating per block)
     uint8_t* picks;           // [channels][pick pitch]  arg max offset of every evaluation sample of the block; one per block in flight
     int* bitpos;              // [channels][bit pitch]   first sample of the 5-sample window of every bit of the block
     uint8_t* bitval;          // [channels][bit pitch]   1 = 'Y', 0 = 'B'
@@ -50,7 +50,9 @@ struct DemodBuffers {
 
 struct DemodArgs {
     DemodBuffers b;           // b.y3 / b.picks = the buffers of this block
-    float2* y3_next;          // buffer of the NEXT block: receives the kHistY-sample history (may equal b.y3)
+    const float2* y3_prev;    // y3 buffer of the PREVIOUS block: its last kHistY samples are this block's history
+    const double* corr_prev;  // corr buffer of the previous block, likewise (last kHistC values)
+    int n_prev;               // 900 Hz samples per channel of the previous block (0 right after a reset: zero history)
     int n_new;                // new 900 Hz samples per channel in this block
     int channels;             // streams * 2
     long long seen;           // 900 Hz samples consumed before this block (same for every channel)
@@ -68,7 +70,7 @@ size_t demod_pick_pitch(int p_max);  // row pitch of DemodBuffers::picks in byte
 size_t demod_bit_pitch(int p_max);   // row pitch of DemodBuffers::bitpos / bitval in elements
 // SMs the sequential kernels want for themselves (the cascade grid is sized to leave them free)
 int demod_reserved_sms(int channels);
-// Queues the feed-forward kernels (angle/correlation, per-offset sums + arg max, history carry) on s_ff and the
+// Queues the feed-forward kernels (angle/correlation incl. the history hand-over, per-offset sums + arg max) on s_ff and the
 // sequential symbol clock, the per-bit window decisions and the SITOR-B state machine on s_seq (ordered after them
 // through ff_done when the two streams differ).  marks: optional 8 events recorded around the kernels (timing mode).
 cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_seq, cudaEvent_t ff_done, cudaEvent_t* marks = nullptr);

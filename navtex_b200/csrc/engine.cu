@@ -121,6 +121,7 @@ struct nvx_engine {
     int tail_cur = 0;
     int fmt = -1;                         // -1 = nothing pushed since create/reset, 0 = float2, 1 = short2
     nvx::DemodBuffers db = {};
+    double* corrbuf[2] = {nullptr, nullptr};   // |mask correlation| rows, alternating per block (each block reads its history from the other)
     uint8_t* d_events[kBuf] = {}; int* d_ev_count[kBuf] = {}; int ev_cap = 0;
     char* d_bits = nullptr; float* d_disc = nullptr; int* d_bit_count = nullptr; int bit_cap = 0;
     uint8_t* h_events[kBuf] = {}; int* h_ev_count[kBuf] = {};
@@ -167,6 +168,7 @@ struct nvx_engine {
     struct Span { int a, b, kind; };
     std::vector<Span> spans;
     size_t ev_used = 0;
+    std::vector<float> cascade_spans_ms;  // every timed cascade launch since the last nvx_engine_get_stats(reset)
     nvx_stats stats = {};
 };
 
@@ -187,7 +189,7 @@ int free_engine(nvx_engine* e) {
     }
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     for (int f = 0; f < 2; ++f) { cudaFree(e->tail[f][0]); cudaFree(e->tail[f][1]); }
-    cudaFree(e->db.corr); cudaFree(e->db.clock); cudaFree(e->db.fsm);
+    cudaFree(e->corrbuf[0]); cudaFree(e->corrbuf[1]); cudaFree(e->db.clock); cudaFree(e->db.fsm);
     cudaFree(e->db.bitpos); cudaFree(e->db.bitval); cudaFree(e->db.nbits);
     cudaFree(e->d_bits); cudaFree(e->d_disc); cudaFree(e->d_bit_count);
     if (e->stream_copy) cudaStreamSynchronize(e->stream_copy);
@@ -228,6 +230,7 @@ int reset_state(nvx_engine* e) {
     for (int k = 0; k < kBuf; ++k) {
         e->db.y3 = e->y3buf[k];
         e->db.picks = e->pickbuf[k];
+        e->db.corr = e->corrbuf[k & 1];
         CU_TRY(nvx::demod_init_state(e->db, e->channels, e->stream));
     }
     CU_TRY(cudaStreamSynchronize(e->stream));
@@ -262,6 +265,7 @@ void collect_spans(nvx_engine* e) {
         cudaEventElapsedTime(&ms, e->ev_pool[sp.a], e->ev_pool[sp.b]);
         if (sp.kind == 0) {
             e->stats.cascade_ms += ms;
+            if (e->cascade_spans_ms.size() < (1u << 20)) e->cascade_spans_ms.push_back(ms);
             if (e->stats.cascade_ms_min == 0.0 || ms < e->stats.cascade_ms_min) e->stats.cascade_ms_min = ms;
             if (ms > e->stats.cascade_ms_max) e->stats.cascade_ms_max = ms;
         }
@@ -484,7 +488,10 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     da.b = e->db;
     da.b.y3 = e->y3buf[b];
     da.b.picks = e->pickbuf[b];
-    da.y3_next = e->y3buf[(b + 1) % kBuf];
+    da.b.corr = e->corrbuf[e->blocks & 1];
+    da.y3_prev = e->y3buf[(b + kBuf - 1) % kBuf];
+    da.corr_prev = e->corrbuf[(e->blocks & 1) ^ 1];
+    da.n_prev = e->last_P;
     da.n_new = n_super; da.channels = e->channels; da.seen = e->sb_abs;
     da.events = e->d_events[b]; da.ev_count = e->d_ev_count[b]; da.ev_cap = e->ev_cap;
     da.bits = e->d_bits; da.disc = e->d_disc; da.bit_count = e->d_bit_count; da.bit_cap = e->bit_cap;
@@ -493,8 +500,6 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     // only the sequential symbol-clock / state-machine kernel (64 warps) overlaps the next block's cascade.
     cudaStream_t s_ff = e->ff_on_main ? e->stream : e->stream_demod;
     if (!e->ff_on_main) CU_TRY(cudaStreamWaitEvent(e->stream_demod, e->casc_done[b], 0));
-    // the history carry of this block writes into the y3 buffer block i-2 used: its symbol clock must be done (it is, normally)
-    else if (e->blocks >= kBuf - 1) CU_TRY(cudaStreamWaitEvent(e->stream, e->demod_done[(b + 1) % kBuf], 0));
     CU_TRY(demod_launch(da, s_ff, e->stream_demod, e->ff_done[b], e->timing > 1 ? marks : nullptr));
     CU_TRY(cudaMemcpyAsync(e->h_ev_count[b], e->d_ev_count[b], sizeof(int) * e->channels, cudaMemcpyDeviceToHost, e->stream_demod));
     CU_TRY(cudaMemcpyAsync(e->h_events[b], e->d_events[b], (size_t)e->channels * e->ev_cap, cudaMemcpyDeviceToHost, e->stream_demod));
@@ -650,7 +655,7 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
             CREATE_TRY(cudaMalloc(&e->tail[f][k], (size_t)e->S * e->halo * (f ? sizeof(short2) : sizeof(float2))));
     e->db.p_max = e->P_max;
     for (int k = 0; k < kBuf; ++k) CREATE_TRY(cudaMalloc(&e->y3buf[k], (size_t)e->channels * (nvx::kHistY + e->P_max) * sizeof(float2)));
-    CREATE_TRY(cudaMalloc(&e->db.corr, (size_t)e->channels * (nvx::kHistC + e->P_max + nvx::kPadC) * sizeof(double)));
+    for (int k = 0; k < 2; ++k) CREATE_TRY(cudaMalloc(&e->corrbuf[k], (size_t)e->channels * (nvx::kHistC + e->P_max + nvx::kPadC) * sizeof(double)));
     for (int k = 0; k < kBuf; ++k) CREATE_TRY(cudaMalloc(&e->pickbuf[k], (size_t)e->channels * nvx::demod_pick_pitch(e->P_max)));
     CREATE_TRY(cudaMalloc(&e->db.bitpos, (size_t)e->channels * nvx::demod_bit_pitch(e->P_max) * sizeof(int)));
     CREATE_TRY(cudaMalloc(&e->db.bitval, (size_t)e->channels * nvx::demod_bit_pitch(e->P_max)));
@@ -872,8 +877,39 @@ int nvx_engine_get_stats(nvx_engine* e, nvx_stats* out, int reset) {
         std::lock_guard<std::mutex> lk(e->mu);
         out->messages = e->delivered;
     }
-    if (reset) e->stats = nvx_stats{};
+    if (reset) { e->stats = nvx_stats{}; e->cascade_spans_ms.clear(); }
     return rc;
+}
+
+int nvx_engine_get_cascade_spans(nvx_engine* e, float* ms, size_t cap, size_t* count) {
+    if (!e || !count || (!ms && cap)) return fail(NVX_ERR_ARG, "null argument");
+    int rc = sync_engine(e);
+    *count = e->cascade_spans_ms.size();
+    const size_t n = *count < cap ? *count : cap;
+    if (n) memcpy(ms, e->cascade_spans_ms.data(), n * sizeof(float));
+    return rc;
+}
+
+int nvx_engine_fence(nvx_engine* e) {
+    if (!e) return fail(NVX_ERR_ARG, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    if (e->blocks > 0) CU_TRY(cudaStreamWaitEvent(e->stream, e->demod_done[e->last_buf], 0));
+    return 0;
+}
+
+int nvx_pinned_alloc(size_t bytes, int write_combined, void** out) {
+    if (!out || !bytes) return fail(NVX_ERR_ARG, "bad argument");
+    void* p = nullptr;
+    const cudaError_t err = cudaHostAlloc(&p, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+    if (err != cudaSuccess) return fail(err == cudaErrorMemoryAllocation ? NVX_ERR_NOMEM : NVX_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
+    *out = p;
+    return 0;
+}
+
+int nvx_pinned_free(void* p) {
+    if (!p) return 0;
+    CU_TRY(cudaFreeHost(p));
+    return 0;
 }
 
 void* nvx_engine_stream(nvx_engine* e) { return e ? (void*)e->stream : nullptr; }

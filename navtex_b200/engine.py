@@ -52,7 +52,7 @@ EXPORTS = (
     "nvx_engine_push_host_f32", "nvx_engine_push_host_s16", "nvx_engine_push_device_f32", "nvx_engine_push_device_s16",
     "nvx_engine_sync", "nvx_engine_wait_ingest", "nvx_engine_poll_messages", "nvx_engine_try_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
     "nvx_engine_read_bits", "nvx_engine_read_events", "nvx_engine_enable_timing", "nvx_engine_get_stats",
-    "nvx_engine_stream", "nvx_synth_fill_device", "nvx_host_assemble", "nvx_debug_long_tc_band",
+    "nvx_engine_stream", "nvx_engine_get_cascade_spans", "nvx_engine_fence", "nvx_pinned_alloc", "nvx_pinned_free", "nvx_synth_fill_device", "nvx_host_assemble", "nvx_debug_long_tc_band",
     "nvx_capture_create", "nvx_capture_destroy", "nvx_capture_write", "nvx_capture_pump", "nvx_capture_start", "nvx_capture_stop",
     "nvx_capture_dropped", "nvx_store_create", "nvx_store_destroy", "nvx_store_add", "nvx_store_add_at", "nvx_store_sink",
     "nvx_store_count", "nvx_store_get", "nvx_store_purge", "nvx_store_dump_csv",
@@ -89,6 +89,10 @@ def load_library():
     L.nvx_engine_enable_timing.argtypes = [C.c_void_p, C.c_int]
     L.nvx_engine_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
     L.nvx_engine_stream.argtypes = [C.c_void_p]
+    L.nvx_engine_get_cascade_spans.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.nvx_engine_fence.argtypes = [C.c_void_p]
+    L.nvx_pinned_alloc.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    L.nvx_pinned_free.argtypes = [C.c_void_p]
     L.nvx_engine_stream.restype = C.c_void_p
     L.nvx_synth_fill_device.argtypes = [C.c_int, C.POINTER(SynthDesc), C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]
     L.nvx_host_assemble.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, MESSAGE_CB, C.c_void_p]
@@ -259,9 +263,46 @@ class Engine:
         _check(self.L.nvx_engine_get_stats(self._h, C.byref(st), int(reset)), allow_overflow=True)
         return st
 
+    def cascade_spans(self) -> np.ndarray:
+        """Per-launch times (ms) of the fused-FIR kernel since the last stats(reset=True)."""
+        cnt = C.c_size_t()
+        _check(self.L.nvx_engine_get_cascade_spans(self._h, None, 0, C.byref(cnt)), allow_overflow=True)
+        out = np.zeros(cnt.value, dtype=np.float32)
+        if cnt.value:
+            _check(self.L.nvx_engine_get_cascade_spans(self._h, out.ctypes.data_as(C.c_void_p), out.size, C.byref(cnt)), allow_overflow=True)
+        return out
+
+    def fence(self):
+        """Order the engine's main stream behind everything queued so far on its demod stream (device side, no host wait)."""
+        _check(self.L.nvx_engine_fence(self._h))
+
     @property
     def stream(self) -> int:
         return self.L.nvx_engine_stream(self._h) or 0
+
+
+class PinnedBuffer:
+    """Page-locked host memory from nvx_pinned_alloc as a numpy array (int16 by default)."""
+
+    def __init__(self, shape, dtype=np.int16, write_combined=False):
+        self.L = load_library()
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = C.c_void_p()
+        _check(self.L.nvx_pinned_alloc(self.nbytes, int(write_combined), C.byref(self._p)))
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self._p.value)).view(self.dtype).reshape(self.shape)
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self.array = None
+            self.L.nvx_pinned_free(self._p)
+            self._p = C.c_void_p()
+
+    __del__ = close
 
 
 class Store:

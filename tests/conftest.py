@@ -18,3 +18,17 @@ def oracle():
 
     oracle_lib.lib()
     return oracle_lib
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """GPU runs: the parity figures of every stream that was compared (tests/parity.py), for profiles/."""
+    try:
+        import json
+        import parity
+        if parity.REPORT:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_report.json"), "w") as f:
+                json.dump(parity.REPORT, f, indent=1)
+    except Exception:
+        pass

@@ -7,6 +7,7 @@ import pytest
 
 import cases
 import oracle_lib as ol
+import parity
 from navtex_b200 import engine, synth
 
 pytestmark = pytest.mark.gpu
@@ -15,14 +16,18 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 REL_TOL = 1e-5
 
 
-def _check_all(eng, k, o, exact_channels=("518", "490")):
+def _check_all(eng, k, o, exact_channels=("518", "490"), where=""):
+    """tests/parity.py's bar for the channels that carry something to decide on; events exact there, decisions of the others
+    counted and reported."""
     y3 = eng.read_y3()
-    scale = max(np.abs(o.y3["518"]).max(), np.abs(o.y3["490"]).max(), 1e-30)
+    bits, disc = {}, {}
+    for c in range(2):
+        bits[c], disc[c] = eng.read_bits(k, c)
+    cmp = parity.compare_stream(y3[k], bits, disc, o, set(exact_channels))
+    parity.assert_stream(cmp, set(exact_channels), where=where)
+    parity.record(where or "edge case", cmp, exact_channels)
     for c, tag in enumerate(ol.CHANNELS):
-        assert np.abs(y3[k, c].astype(np.complex128) - o.y3[tag]).max() <= REL_TOL * scale, tag
         if tag in exact_channels:
-            bits, _ = eng.read_bits(k, c)
-            assert bits == o.bits[tag], tag
             assert eng.read_events(k, c) == o.events[tag], tag
 
 
@@ -40,7 +45,7 @@ def test_config1_wav_file(tmp_path):
     g = np.load(os.path.join(GOLDEN, "clean518.npz"))
     gold = [(0, int(f), str(b), str(t)) for f, b, t in zip(g["msg_freq"], g["msg_bbbb"], g["msg_text"])]
     assert msgs == gold and len(gold) == 1
-    _check_all(eng, 0, ol.run_oracle(frames[: 2 * n]), exact_channels=("518",))
+    _check_all(eng, 0, ol.run_oracle(frames[: 2 * n]), exact_channels=("518",), where="config-1 WAV")
     eng.close()
 
 
@@ -56,7 +61,7 @@ def test_digital_silence_and_full_scale():
     eng.push_host(np.ascontiguousarray(x))
     assert eng.poll_messages() == []
     o0 = ol.run_oracle(zeros.reshape(-1))
-    _check_all(eng, 0, o0)
+    _check_all(eng, 0, o0, where="digital silence")
     assert len(o0.bits["518"]) > 300 and set(o0.bits["518"]) == {ord("Y")}          # ties decide 'Y' (decoder.C:125)
     o1 = ol.run_oracle(square.reshape(-1))
     y3 = eng.read_y3()
@@ -79,7 +84,7 @@ def test_one_stream_one_minute_single_block():
     msgs = eng.poll_messages()
     o = ol.run_oracle(iq)
     assert [m[1:] for m in msgs] == o.messages == [(518, bbbb, text)]
-    _check_all(eng, 0, o, exact_channels=("518",))
+    _check_all(eng, 0, o, exact_channels=("518",), where="one stream, 60 s, single block")
     eng.close()
 
 
