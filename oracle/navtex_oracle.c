@@ -127,6 +127,9 @@ struct nvo_decoder {
     double osum[SPB]; int osum_at, osum_full;
     int sync_tick;          /* bs_seq_nbr */
     int last_pick;          /* prev_offset */
+    /* not in the reference: how close the last arg max was, (best - runner-up) / best, for the parity reports of the tests
+     * (a GPU / CPU difference in the last bits of the sums can only flip a pick at a near-tie) */
+    double pick_margin; int pick_fresh;
     /* mark/space discriminator */
     int state, tick, offs, next_offs, burned, used;
     float br, bi, yr, yi;
@@ -178,6 +181,13 @@ static void decoder_timing(nvo_decoder *d, double angle) {
             int pick = 0;
             for (int i = 0; i < SPB; ++i)
                 if (d->osum[i] > best) { best = d->osum[i]; pick = i; }
+            {
+                double second = -1.0;
+                for (int i = 0; i < SPB; ++i)
+                    if (i != pick && d->osum[i] > second) second = d->osum[i];
+                d->pick_margin = best > 0.0 ? (best - second) / best : 0.0;
+                d->pick_fresh = 1;
+            }
             if (d->last_pick != -1 && pick != d->last_pick) {
                 /* slew by exactly one step toward the new maximum, the short way round (decoder.C:217-246) */
                 int up;
@@ -313,7 +323,7 @@ struct nvo_chain {
     nvo_decoder dec[2];
     nvo_bsm bsm[2];
     long n3[2];
-    bytes_t y1, y2[2], y3[2], bits[2], bitpos[2], disc[2];
+    bytes_t y1, y2[2], y3[2], bits[2], bitpos[2], disc[2], pickm[2];
     msg_t *msgs; size_t n_msgs, cap_msgs;
 };
 
@@ -513,7 +523,7 @@ void nvo_free(nvo_chain *c) {
         fir_free(&c->f2[ch]); fir_free(&c->f3[ch]); nco_free(&c->nco[ch]);
         regfree(&c->bsm[ch].re_som); regfree(&c->bsm[ch].re_eom);
         free(c->bsm[ch].events.p);
-        free(c->y2[ch].p); free(c->y3[ch].p); free(c->bits[ch].p); free(c->bitpos[ch].p); free(c->disc[ch].p);
+        free(c->y2[ch].p); free(c->y3[ch].p); free(c->bits[ch].p); free(c->bitpos[ch].p); free(c->disc[ch].p); free(c->pickm[ch].p);
     }
     free(c->y1.p);
     for (size_t k = 0; k < c->n_msgs; ++k) free(c->msgs[k].text);
@@ -540,6 +550,10 @@ static void chain_sample(nvo_chain *c, double xi, double xq) {
         c->n3[ch]++;
         float sums[4];
         char bit = nvo_decoder_sample(&c->dec[ch], ci, cq, sums);
+        if (c->dec[ch].pick_fresh) {
+            c->dec[ch].pick_fresh = 0;
+            if (c->prm.record_taps) { double rec[2] = {(double)c->n3[ch], c->dec[ch].pick_margin}; bytes_add(&c->pickm[ch], rec, sizeof rec); }
+        }
         if (bit) {
             int32_t pos = (int32_t)c->n3[ch];
             bytes_add_c(&c->bits[ch], bit);
@@ -566,6 +580,7 @@ size_t nvo_y3(const nvo_chain *c, int ch, const double **iq) { *iq = (const doub
 size_t nvo_bits(const nvo_chain *c, int ch, const char **b) { *b = c->bits[ch].p; return c->bits[ch].n; }
 size_t nvo_bitpos(const nvo_chain *c, int ch, const int32_t **p) { *p = (const int32_t *)c->bitpos[ch].p; return c->bitpos[ch].n / 4; }
 size_t nvo_disc(const nvo_chain *c, int ch, const float **s) { *s = (const float *)c->disc[ch].p; return c->disc[ch].n / 16; }
+size_t nvo_pick_margins(const nvo_chain *c, int ch, const double **m) { *m = (const double *)c->pickm[ch].p; return c->pickm[ch].n / 16; }
 size_t nvo_events(const nvo_chain *c, int ch, const char **e) { *e = c->bsm[ch].events.p; return c->bsm[ch].events.n; }
 size_t nvo_n_messages(const nvo_chain *c) { return c->n_msgs; }
 int nvo_message(const nvo_chain *c, size_t k, int *freq, const char **bbbb, const char **text) {

@@ -56,6 +56,8 @@ size_t nvo_y2(const nvo_chain *c, int ch, const double **iq);
 size_t nvo_y3(const nvo_chain *c, int ch, const double **iq);
 size_t nvo_bits(const nvo_chain *c, int ch, const char **bits);          /* 'B' / 'Y' */
 size_t nvo_bitpos(const nvo_chain *c, int ch, const int32_t **pos);      /* 900 Hz sample count at decision */
+/* per bit-sync evaluation (decoder.C:204-215): pairs (900 Hz sample count, (best - runner-up) / best of the nine sums) */
+size_t nvo_pick_margins(const nvo_chain *c, int ch, const double **pairs);
 size_t nvo_disc(const nvo_chain *c, int ch, const float **sums);         /* 4 floats per bit: BR BI YR YI */
 /* every character appended to a line, '\n' for a completed line, 0x18 for an abort (in order) */
 size_t nvo_events(const nvo_chain *c, int ch, const char **ev);

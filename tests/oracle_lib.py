@@ -55,6 +55,8 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_size_t
             f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(t))]
+        L.nvo_pick_margins.restype = C.c_size_t
+        L.nvo_pick_margins.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_double))]
         L.nvo_n_messages.restype = C.c_size_t
         L.nvo_n_messages.argtypes = [C.c_void_p]
         L.nvo_message.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
@@ -72,6 +74,7 @@ class Result:
     def __init__(self):
         self.y1 = None
         self.y2, self.y3, self.bits, self.bitpos, self.disc, self.events = {}, {}, {}, {}, {}, {}
+        self.pick_margins = {}   # oracle only: (n, 2) [900 Hz sample count, (best - runner-up) / best] per bit-sync evaluation
         self.messages = []       # (freq, bbbb, text)
         self.timing = None
 
@@ -127,6 +130,9 @@ def run_oracle(iq, h1=None, h2=None, h3=None, nco_hz=(14000.0, -14000.0), nco_pe
         pf = C.POINTER(C.c_float)()
         nb = L.nvo_disc(ch, c, C.byref(pf))
         r.disc[tag] = np.ctypeslib.as_array(pf, shape=(nb, 4)).copy() if nb else np.zeros((0, 4), np.float32)
+        pm = C.POINTER(C.c_double)()
+        nm = L.nvo_pick_margins(ch, c, C.byref(pm))
+        r.pick_margins[tag] = np.ctypeslib.as_array(pm, shape=(nm, 2)).copy() if nm else np.zeros((0, 2))
         pc = C.POINTER(C.c_char)()
         ne = L.nvo_events(ch, c, C.byref(pc))
         r.events[tag] = C.string_at(pc, ne) if ne else b""

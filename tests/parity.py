@@ -57,6 +57,21 @@ def compare_stream(y3_gpu, bits_gpu, disc_gpu, ref, occupied):
             bad = np.nonzero(ga != ra)[0]
             out["bit_mismatches"][tag] = int(bad.size)
             out["mismatch_margins"][tag] = [decision_margin(ref.disc[tag][k]) for k in bad[:64]]
+            # a RUN of differing decisions with healthy mark/space margins is a timing slip: one of the nine-way arg max
+            # picks fell the other way at a near-tie and the slew-limited offset took a different path for a while.  With the
+            # restated oracle's per-evaluation margins, report the tightest arg max in the 64 evaluations before the run.
+            pm, bp = getattr(ref, "pick_margins", {}).get(tag), getattr(ref, "bitpos", {}).get(tag)
+            if bad.size and pm is not None and len(pm) and bp is not None and len(bp) == len(rb):
+                runs, start = [], int(bad[0])
+                for a, b in zip(bad[:-1], bad[1:]):
+                    if b - a > 16:
+                        runs.append(start); start = int(b)
+                runs.append(start)
+                tight = []
+                for k in runs:
+                    at = np.searchsorted(pm[:, 0], bp[k])
+                    tight.append(float(pm[max(0, at - 64):at + 1, 1].min()))
+                out.setdefault("timing_slip_pick_margins", {})[tag] = tight
         else:
             out["bit_mismatches"][tag] = None
             out["mismatch_margins"][tag] = []
@@ -111,4 +126,5 @@ def record(where, cmp, occupied):
                    "y3_rel_own_rms": cmp["y3_rel_own_rms"], "disc_rel": cmp["disc_rel"],
                    "empty_channels": {t: {"y3_rel_own_rms": cmp["empty_rel_own_rms"].get(t), "bit_len_diff": cmp["bit_len_diff"][t],
                                           "bit_mismatches": cmp["bit_mismatches"][t],
-                                          "mismatch_margins": cmp["mismatch_margins"][t]} for t in empty}})
+                                          "mismatch_margins": cmp["mismatch_margins"][t],
+                                          "timing_slip_pick_margins": cmp.get("timing_slip_pick_margins", {}).get(t)} for t in empty}})
