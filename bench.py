@@ -609,6 +609,17 @@ def leg_config5(c, x, expect, taps_n, steps, warmup):
     else:
         peak, peak_src = 1125.0, "fallback: nominal dense TF32 = 2250 / 2 TFLOP/s (B200_PROFILING.md)"
     ach = S * BLOCK * flop / (fir_ms * 1e-3) / 1e12
+
+    def executed_tflop(D, h, rows, n_in):
+        # what the tensor cores execute for one stage (fir_long_tc.cu geometry, from the library's own band builder): per 128-row
+        # tile of n_tile outputs, `chunks` K chunks of 2 planes x 3 TF32 terms x 4 k-steps of M128 x n_tile x K8
+        try:
+            g, _, _ = engine.long_tc_band(D, h)
+        except engine.NvxError:
+            return 0.0           # the stage runs on CUDA cores
+        tiles = -(-rows // 128) * -(-(n_in // D) // g["n_tile"])
+        return tiles * g["chunks"] * 24 * 2.0 * 128 * g["n_tile"] * 8 / 1e12
+    ex = executed_tflop(4, taps[0], S, BLOCK) + executed_tflop(7, taps[1], 2 * S, BLOCK // 4)
     return {
         "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
         "workload": "configs[4]: long-tap FIR stress, %d-tap Kaiser designs in all three stages, 1024 synthetic IQ streams per GPU resident in HBM "
@@ -620,7 +631,8 @@ def leg_config5(c, x, expect, taps_n, steps, warmup):
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src,
                      "kernel": "nvx::fir_tc_kernel<4,.> + <7,.> + fir_long_kernel<10,2>", "kernel_ms": fir_ms, **span_stats(spans),
                      "note": "achieved = ALGORITHMIC FP32 flops (%.0f per input sample) / time of the three stage kernels; the tensor cores "
-                             "execute 3x that for the TF32 split plus the structural zeros of the Toeplitz band" % flop},
+                             "execute 3x that for the TF32 split plus the structural zeros of the Toeplitz band" % flop,
+                     "executed_tensor_tflops": ex / (fir_ms * 1e-3), "executed_frac": ex / (fir_ms * 1e-3) / peak},
         "gpu_launches": int(st.cascade_launches + st.demod_launches + st.aux_launches), "clocks": clocks,
         "check": {"bulletins_in_capture_all_ranks": exp_all, "decoded_exact_all_ranks": ok_all, "messages_total_all_ranks": n_all},
     }

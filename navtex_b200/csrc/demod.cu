@@ -560,10 +560,10 @@ cudaError_t demod_launch(const DemodArgs& a, cudaStream_t s_ff, cudaStream_t s_s
     mark(2, s_ff);
     mark(3, s_ff);      // (the history carry used to be a kernel of its own here; angle_corr_kernel does it now)
     // sequential part: few warps, latency-bound, runs beside the next block's cascade on the SMs it leaves free
-    if (s_seq != s_ff) {
+    {   // ff_done also tells the engine when this block's look-back into the previous block's y3 buffer is over
         cudaError_t e = cudaEventRecord(ff_done, s_ff);
         if (e != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(s_seq, ff_done, 0)) != cudaSuccess) return e;
+        if (s_seq != s_ff && (e = cudaStreamWaitEvent(s_seq, ff_done, 0)) != cudaSuccess) return e;
     }
     {   // per device, and a few hundred nanoseconds: not cached
         cudaError_t e = cudaFuncSetAttribute(symbol_clock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem);

@@ -69,6 +69,7 @@ cudaError_t long_carry(const float2* old_hist, const void* block, long long pitc
 struct LongTcStage;
 struct TcBand {
     int T, N, chunks, J, copies;      // padded taps, outputs per tile, K chunks per tile, band rows per copy, copies
+    bool streaming = false;           // served by the streaming kernel (every input chunk feeds the two tiles that contain it)
     std::vector<float> gh, gl;        // [copies][J][32] high / low TF32 parts
 };
 bool long_tc_band(int D, int T_taps, const double* h, TcBand* out);

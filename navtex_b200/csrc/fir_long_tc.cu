@@ -46,6 +46,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -91,6 +92,9 @@ struct TcArgs {
     long long n_in, in_pitch, out_pitch, out_off, k_abs;
     const NcoParam* nco;
     int rows, s16, T, H, chunks, J, slots, box_rows, mix;
+    int cpt, lead;                         // streaming kernel: chunks per tile advance (D N / chunk samples), chunks a window leads its tile by
+    long long* trace;                      // development aid (NVX_TC_TRACE): clock64 stamps of CTA 0's first chunks, else null
+    int dbg;                               // development aid (NVX_TC_DBG bit mask): leave parts of the pipeline out to find the limiter (results are garbage)
     long long tiles_per_block;             // output tiles per row block
     long long work;                        // row blocks * tiles_per_block
     float2 nco_tab[kNcoPeriod];            // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
@@ -132,7 +136,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 
 // general loader for tiles that touch the carried history
 __device__ __noinline__ float2 tc_load(const TcArgs& a, int row, long long g) {
-    if (row >= a.rows || g >= a.n_in) return make_float2(0.f, 0.f);
+    if (row >= a.rows || g >= a.n_in || g < -(long long)a.H) return make_float2(0.f, 0.f);   // (older than the history: only zero-padded taps reach there)
     if (g < 0) return a.hist[(size_t)row * a.H + (a.H + g)];
     if (a.s16) {
         const short2 v = static_cast<const short2*>(a.in)[(size_t)row * a.in_pitch + g];
@@ -162,9 +166,9 @@ enum {
     kBarRawEmpty = kBarRawFull + kMaxSlots,
     kBarAFull = kBarRawEmpty + kMaxSlots,
     kBarAEmpty = kBarAFull + kMaxSets,
-    kBarTile = kBarAEmpty + kMaxSets,
-    kBarTmemFree = kBarTile + 1,
-    kBars = kBarTmemFree + 1
+    kBarTile = kBarAEmpty + kMaxSets,      // (streaming kernel: one per accumulator slot)
+    kBarTmemFree = kBarTile + 2,
+    kBars = kBarTmemFree + 2
 };
 
 // round to TF32 (10-bit mantissa, nearest, ties away) with integer ops; the remainder is exact in FP32
@@ -237,16 +241,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     const int ring_chunks = a.slots / slots_per_chunk;
     if (warp == kTmaWarp) {
         if (lane == 0) {
-            long long g = 0;
+            int ring_at = 0;                                // ring position of chunk g, kept incrementally (no 64-bit divisions per chunk)
+            uint32_t ring_ph = 0, odd = 0;
             for (long long w = w_lo; w < w_hi; ++w) {
                 const int rb = (int)(w / a.tiles_per_block);
                 const long long n0 = (w % a.tiles_per_block) * N;
                 const long long t_base = (long long)D * n0 + D - a.T;      // first input of the tile's window (block-relative)
                 const bool fast = t_base >= 0;
-                for (int c = 0; c < a.chunks; ++c, ++g) {
-                    if ((g & 1) || kCS != kKB) continue;    // 28-sample chunks are not whole 128-byte box rows: cp.async only
-                    const int slot = (int)(g % ring_chunks) * slots_per_chunk;
-                    const uint32_t ph = (uint32_t)(g / ring_chunks) & 1;
+                for (int c = 0; c < a.chunks; ++c) {
+                    const int slot = ring_at * slots_per_chunk;
+                    const uint32_t ph = ring_ph;
+                    const bool mine = !odd && kCS == kKB;   // 28-sample chunks are not whole 128-byte box rows: cp.async only
+                    odd ^= 1;
+                    if (++ring_at == ring_chunks) { ring_at = 0; ring_ph ^= 1; }
+                    if (!mine) continue;
                     for (int h = 0; h < slots_per_chunk; ++h) {
                         const uint32_t full = bar0 + 8 * (kBarRawFull + slot + h);
                         bar_wait(bar0 + 8 * (kBarRawEmpty + slot + h), ph ^ 1);
@@ -274,16 +282,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
         const int u16 = tid % units, r0 = tid / units, r_step = kLoaders / units;
         const int esz = a.s16 ? 4 : 8;                            // bytes per sample
         const int per_piece = 16 / esz;                           // samples per piece
-        long long g = 0;
+        int ring_at = 0;
+        uint32_t ring_ph = 0, odd = 0;
         for (long long w = w_lo; w < w_hi; ++w) {
             const int rb = (int)(w / a.tiles_per_block);
             const long long n0 = (w % a.tiles_per_block) * N;
             const long long t_base = (long long)D * n0 + D - a.T;
             const bool fast = t_base >= 0;
-            for (int c = 0; c < a.chunks; ++c, ++g) {
-                if (!(g & 1) && kCS == kKB) continue;
-                const int slot = (int)(g % ring_chunks) * slots_per_chunk;
-                const uint32_t ph = (uint32_t)(g / ring_chunks) & 1;
+            for (int c = 0; c < a.chunks; ++c) {
+                const int slot = ring_at * slots_per_chunk;
+                const uint32_t ph = ring_ph;
+                const bool mine = odd || kCS != kKB;
+                odd ^= 1;
+                if (++ring_at == ring_chunks) { ring_at = 0; ring_ph ^= 1; }
+                if (!mine) continue;
                 bar_wait(bar0 + 8 * (kBarRawEmpty + slot), ph ^ 1);
                 if (slots_per_chunk == 2) bar_wait(bar0 + 8 * (kBarRawEmpty + slot + 1), ph ^ 1);
                 if (fast) {
@@ -505,6 +517,396 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Streaming variant (the default wherever a window spans at most two tiles: up to 260 taps at D = 4, 455 at D = 7).
+//
+// fir_tc_kernel above treats every tile on its own: it loads and converts the tile's whole window, D (N - 1) + T samples for
+// D N new ones -- at 255 taps every input sample travels L2 -> shared memory -> registers -> tensor memory TWICE, and that
+// traffic, not the tensor core, bounded the kernel (ncu: tensor pipe 51 % busy, converters waiting for raw input).  Here the
+// input is cut into GLOBAL chunks G (chunk_samples(D) samples each, the same grid for every tile: the tap count is padded to
+// T = D + lead * chunk so that tile t's window is exactly the chunks [cpt t - lead, cpt t + cpt), cpt = D N / chunk) and a CTA
+// walks its contiguous range of tiles chunk by chunk: every chunk is loaded once, converted once, written to tensor memory
+// once -- and multiplied into BOTH tiles whose windows contain it, the one that is finishing (band rows of its late chunks)
+// and the one that is starting (band rows of its early chunks).  Two tiles are therefore live at a time:
+//   TMEM: accumulator slot 0 in columns [0, 128), slot 1 in [128, 256) (I | Q, N = 64), two A sets of 128 columns above.
+// The epilogue dumps a finished tile to shared memory while the MMAs of the next chunk's older tile run, and the slot is handed
+// back before the tile after next needs it.  Per chunk the tensor core now has 48 MMAs to chew on instead of 24 while the
+// converters refill the other A set, so two A sets are enough.  Everything else -- band matrix, descriptors, 3xTF32 split, slot
+// ring, TMA / cp.async alternation, epilogue phases -- is as in fir_tc_kernel.
+constexpr int kSN = 64;                    // outputs per tile of the streaming kernel
+constexpr int kTraceChunks = 96, kTraceCols = 8;
+#define NVX_TRACE(col, idx)                                                                                   \
+    do {                                                                                                      \
+        if (a.trace && blockIdx.x == 0 && (idx) < kTraceChunks && lane == 0) a.trace[(idx) * kTraceCols + (col)] = clock64(); \
+    } while (0)
+
+template <int D>
+__global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_constant__ TcArgs a) {
+    constexpr int N = kSN;
+    constexpr int kCS = chunk_samples(D);
+    constexpr int kCopies = band_copies(D);
+    constexpr int kSets = 2;
+    constexpr uint32_t kACol0 = 512 - kSets * kSetCols;      // 256: above the two accumulator slots
+    constexpr uint32_t kSlotCols = 2 * N;
+    constexpr int NP = dump_outputs(D, N);
+    constexpr int kDumpPitch = 2 * NP + kDumpPad;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int g_bytes = kCopies * a.J * 128;
+    uint8_t* s_gh = smem;
+    uint8_t* s_gl = smem + g_bytes;
+    uint8_t* s_raw = smem + 2 * g_bytes;
+    float* s_dump = reinterpret_cast<float*>(s_raw + a.slots * kSlotBytes);
+    float2* s_nco = reinterpret_cast<float2*>(s_dump + kRows * kDumpPitch);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_nco + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars);
+    const uint32_t bar0 = s_u32(bars);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int slots_per_chunk = a.s16 ? 1 : 2;
+    const int cpt = a.cpt, lead = a.lead;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kBars; ++i) {
+            int count = 1;
+            if (i >= kBarRawFull && i < kBarRawFull + kMaxSlots) count = 32 * kLoaderWarps;
+            if (i >= kBarRawEmpty && i < kBarRawEmpty + kMaxSlots) count = kConvWarps / slots_per_chunk;
+            if (i >= kBarAFull && i < kBarAFull + kMaxSets) count = kConvWarps;
+            if (i >= kBarTmemFree) count = 4;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(count));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < kNcoPeriod) s_nco[threadIdx.x] = a.nco_tab[threadIdx.x];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot;
+
+    // a contiguous range of (row block, tile) items per CTA, walked as segments [ta, tb) of consecutive tiles of one row block;
+    // only the first `lead` chunks of a segment are loaded without feeding a second tile (the neighbour CTA loads them too)
+    const long long per = (a.work + gridDim.x - 1) / gridDim.x;
+    const long long w_lo = (long long)blockIdx.x * per, w_hi = w_lo + per < a.work ? w_lo + per : a.work;
+    const long long tpb = a.tiles_per_block;
+    const int ring_chunks = a.slots / slots_per_chunk;
+
+#define NVX_FOR_SEGMENTS(...)                                                                        \
+    for (long long w_ = w_lo; w_ < w_hi;) {                                                          \
+        const int rb = (int)(w_ / tpb);                                                              \
+        const long long ta = w_ % tpb;                                                               \
+        const long long tb = ta + (w_hi - w_) < tpb ? ta + (w_hi - w_) : tpb;                        \
+        __VA_ARGS__                                                                                  \
+        w_ += tb - ta;                                                                               \
+    }
+
+    if (warp == kTmaWarp) {
+        if (lane == 0) {
+            // ring position of chunk g, kept incrementally (no 64-bit divisions on any role's critical path)
+            int ring_at = 0;
+            uint32_t ring_ph = 0, odd = 0;
+            NVX_FOR_SEGMENTS({
+                for (long long G = cpt * ta - lead; G < cpt * tb; ++G) {
+                    const int slot = ring_at * slots_per_chunk;
+                    const uint32_t ph = ring_ph;
+                    const bool mine = !odd;                 // odd chunks: the cp.async loaders
+                    odd ^= 1;
+                    if (++ring_at == ring_chunks) { ring_at = 0; ring_ph ^= 1; }
+                    if (!mine) continue;
+                    const bool fast = G >= 0 && !(a.dbg & 1);   // chunks before the block come from the carried history
+                    for (int h = 0; h < slots_per_chunk; ++h) {
+                        const uint32_t full = bar0 + 8 * (kBarRawFull + slot + h);
+                        bar_wait(bar0 + 8 * (kBarRawEmpty + slot + h), ph ^ 1);
+                        if (fast) {
+                            // x coordinate in 32-bit (float) / 16-bit (short) elements, two per sample.  D = 7: the second box of a
+                            // 28-sample chunk over-fetches 4 samples of the next chunk (the converters zero those columns); rows past
+                            // the last stream and samples past the block end are zero-filled by the TMA unit
+                            const int x0 = (int)(2 * (G * kCS + h * 16));
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(kSlotBytes) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                         ::"r"(s_u32(s_raw + (slot + h) * kSlotBytes)), "l"(&a.map_x), "r"(x0), "r"(rb * kRows), "r"(full) : "memory");
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps - 1) : "memory");
+                        } else {
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps) : "memory");
+                        }
+                    }
+                }
+            })
+        }
+    } else if (warp >= kLoaderWarp0 && warp < kLoaderWarp0 + kLoaderWarps) {
+        const int tid = (warp - kLoaderWarp0) * 32 + lane;
+        constexpr int kLoaders = 32 * kLoaderWarps;
+        const int units = 8 * slots_per_chunk;
+        const int u16 = tid % units, r0 = tid / units, r_step = kLoaders / units;
+        const int esz = a.s16 ? 4 : 8;
+        const int per_piece = 16 / esz;
+        int ring_at = 0;
+        uint32_t ring_ph = 0, odd = 0;
+        NVX_FOR_SEGMENTS({
+            for (long long G = cpt * ta - lead; G < cpt * tb; ++G) {
+                const int slot = ring_at * slots_per_chunk;
+                const uint32_t ph = ring_ph;
+                const bool mine = odd != 0;
+                odd ^= 1;
+                if (++ring_at == ring_chunks) { ring_at = 0; ring_ph ^= 1; }
+                if (!mine) continue;
+                bar_wait(bar0 + 8 * (kBarRawEmpty + slot), ph ^ 1);
+                if (slots_per_chunk == 2) bar_wait(bar0 + 8 * (kBarRawEmpty + slot + 1), ph ^ 1);
+                if (G >= 0 && !(a.dbg & 1)) {
+                    const long long t = G * kCS + u16 * per_piece;
+                    const bool t_ok = t + per_piece <= a.n_in && u16 * per_piece < kCS;
+                    const uint8_t* src = static_cast<const uint8_t*>(a.in) + ((size_t)(rb * kRows + r0) * a.in_pitch + t) * esz;
+                    const size_t src_step = (size_t)r_step * a.in_pitch * esz;
+                    const uint32_t dst0 = s_u32(s_raw + (slot + (u16 >> 3)) * kSlotBytes);
+#pragma unroll 4
+                    for (int r = r0; r < kRows; r += r_step, src += src_step) {
+                        const uint32_t dst = dst0 + r * 128 + (((u16 & 7) ^ (r & 7)) << 4);
+                        const int bytes = (t_ok && rb * kRows + r < a.rows) ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(bytes ? src : static_cast<const uint8_t*>(a.in)), "r"(bytes) : "memory");
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * (kBarRawFull + slot)) : "memory");
+                    if (slots_per_chunk == 2)
+                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * (kBarRawFull + slot + 1)) : "memory");
+                } else {
+                    bar_arrive(bar0 + 8 * (kBarRawFull + slot));
+                    if (slots_per_chunk == 2) bar_arrive(bar0 + 8 * (kBarRawFull + slot + 1));
+                }
+            }
+        })
+    } else if (warp == kIssuerWarp) {
+        const bool leader = elect_one();
+        if (leader) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * kBarG), "r"(2 * g_bytes) : "memory");
+            for (int j = 0; j < kCopies * a.J; j += a.box_rows) {
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(s_u32(s_gh + j * 128)), "l"(&a.map_gh), "r"(0), "r"(j), "r"(bar0 + 8 * kBarG) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(s_u32(s_gl + j * 128)), "l"(&a.map_gl), "r"(0), "r"(j), "r"(bar0 + 8 * kBarG) : "memory");
+            }
+        }
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+        bar_wait(bar0 + 8 * kBarG, 0);
+        uint32_t s = 0, ph = 0;
+        int gi = 0;
+        int q0 = 0;                                         // tiles of the segments already done (32-bit: a CTA walks < 2^31 tiles)
+        uint64_t dh0[kKB / kUmmaK], dl0[kKB / kUmmaK];      // band descriptors at offset 0, one per k-step
+#pragma unroll
+        for (int k = 0; k < kKB / kUmmaK; ++k) {
+            dh0[k] = umma_desc(s_u32(s_gh) + k * kUmmaK * 4);
+            dl0[k] = umma_desc(s_u32(s_gl) + k * kUmmaK * 4);
+        }
+        NVX_FOR_SEGMENTS({
+            // chunk G = cpt t1 + r: t1 is the tile that is finishing (its chunk index r + lead), t1 + 1 starts once r + lead >= cpt
+            int r = lead ? cpt - lead : 0;
+            int t1 = lead ? -1 : 0;                         // relative to ta
+            const int n_tiles = (int)(tb - ta);
+            const int n_chunks = cpt * n_tiles + lead;
+            for (int j = 0; j < n_chunks; ++j, ++gi) {
+                bar_wait(bar0 + 8 * (kBarAFull + s), ph);
+                NVX_TRACE(0, gi);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t at = tmem + kACol0 + s * kSetCols;
+#pragma unroll 1
+                for (int which = 0; which < 2; ++which) {
+                    const int t = t1 + which;
+                    const int c = which ? r + lead - cpt : r + lead;     // chunk index inside tile t's window, 0 .. chunks - 1
+                    if (c < 0 || t < 0 || t >= n_tiles) continue;
+                    const int q = q0 + t;
+                    const uint32_t slot = (uint32_t)(q & 1);
+                    if (c == 0) {                                       // first chunk of the tile: its accumulator slot must have been dumped
+                        bar_wait(bar0 + 8 * (kBarTmemFree + slot), (uint32_t)((q >> 1) & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                    }
+                    const uint32_t acc = tmem + slot * kSlotCols;
+                    // chunk c of B = copy c % kCopies of the band, moved up by whole atoms: the descriptors are those of the band's
+                    // first rows plus the offset in their 16-byte address field (shared memory is far below its 14-bit range)
+                    const uint32_t goff = (uint32_t)((a.chunks - 1) / kCopies - c / kCopies) * 1024 + (uint32_t)(c % kCopies) * (a.J * 128);
+                    const uint64_t dadd = goff >> 4;
+                    if (leader) {
+#pragma unroll
+                        for (int p = 0; p < 2; ++p)
+#pragma unroll
+                            for (int term = 0; term < 3; ++term)        // x_hi h_hi, x_lo h_hi, x_hi h_lo
+#pragma unroll
+                                for (int k = 0; k < kKB / kUmmaK; ++k)
+                                    umma_ts_tf32(acc + p * N, at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
+                                                 (term == 2 ? dl0[k] : dh0[k]) + dadd, idesc, (c | term | k) ? 1u : 0u);
+                        if (c == a.chunks - 1) umma_commit(bar0 + 8 * (kBarTile + slot));
+                    }
+                    __syncwarp();
+                }
+                if (leader) umma_commit(bar0 + 8 * (kBarAEmpty + s));
+                NVX_TRACE(1, gi);
+                if (++s == kSets) { s = 0; ph ^= 1; }
+                if (++r == cpt) { r = 0; ++t1; }
+            }
+            q0 += n_tiles;
+        })
+    } else if (warp < kConvWarps) {
+        const int q = warp & 3, kh = warp >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + kACol0 + kh * 16;
+        int slot = a.s16 ? 0 : kh;
+        uint32_t sph = 0, s = 0, ph = 0;
+        int gi = 0;
+        NVX_FOR_SEGMENTS({
+            for (long long G = cpt * ta - lead; G < cpt * tb; ++G, ++gi) {
+                bar_wait(bar0 + 8 * (kBarRawFull + slot), sph);
+                if (warp == 0) NVX_TRACE(2, gi);
+                const uint8_t* row = s_raw + slot * kSlotBytes + r * 128;
+                float ih[16], il[16], qh[16], ql[16];
+                if (a.dbg & 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ih[j] = il[j] = qh[j] = ql[j] = (float)gi;
+                } else if (G >= 0) {
+                    if (a.s16) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int4 v = *reinterpret_cast<const int4*>(row + (((4 * kh + u) ^ (r & 7)) << 4));
+                            const int wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                split_tf32((float)(short)(wv[j] & 0xFFFF), ih[4 * u + j], il[4 * u + j]);
+                                split_tf32((float)(wv[j] >> 16), qh[4 * u + j], ql[4 * u + j]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            float4 v = *reinterpret_cast<const float4*>(row + ((u ^ (r & 7)) << 4));
+                            if (kCS != kKB && kh * 16 + 2 * u >= kCS) v = make_float4(0.f, 0.f, 0.f, 0.f);     // zero columns
+                            split_tf32(v.x, ih[2 * u], il[2 * u]);
+                            split_tf32(v.y, qh[2 * u], ql[2 * u]);
+                            split_tf32(v.z, ih[2 * u + 1], il[2 * u + 1]);
+                            split_tf32(v.w, qh[2 * u + 1], ql[2 * u + 1]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float2 v = make_float2(0.f, 0.f);
+                        if (kh * 16 + j < kCS) v = tc_load(a, rb * kRows + r, G * kCS + kh * 16 + j);
+                        split_tf32(v.x, ih[j], il[j]);
+                        split_tf32(v.y, qh[j], ql[j]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) bar_arrive(bar0 + 8 * (kBarRawEmpty + slot));
+                if (warp == 0) NVX_TRACE(3, gi);
+                bar_wait(bar0 + 8 * (kBarAEmpty + s), ph ^ 1);
+                if (warp == 0) NVX_TRACE(4, gi);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t col = lane_base + s * kSetCols;
+                if (!(a.dbg & 4)) {
+                    tmem_st16(col + 0 * 32, ih);
+                    tmem_st16(col + 1 * 32, il);
+                    tmem_st16(col + 2 * 32, qh);
+                    tmem_st16(col + 3 * 32, ql);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) bar_arrive(bar0 + 8 * (kBarAFull + s));
+                if (warp == 0) NVX_TRACE(5, gi);
+                if (++s == kSets) { s = 0; ph ^= 1; }
+                slot += slots_per_chunk;
+                if (slot >= a.slots) { slot -= a.slots; sph ^= 1; }
+            }
+        })
+    } else {
+        // epilogue, as in fir_tc_kernel, on the accumulator slot of the tile
+        const int q = warp & 3;
+        const long long n_out = a.n_in / D;
+        float* my_row = s_dump + (q * 32 + lane) * kDumpPitch;
+        const float* rows0 = s_dump + (q * 32) * kDumpPitch;
+        long long tq = 0;                                   // tiles handled so far (all segments)
+        NVX_FOR_SEGMENTS({
+            for (long long t = ta; t < tb; ++t, ++tq) {
+                const uint32_t slot = (uint32_t)(tq & 1);
+                const long long n0 = t * N;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * kSlotCols;
+                bar_wait(bar0 + 8 * (kBarTile + slot), (uint32_t)((tq >> 1) & 1));
+                if (q == 0) NVX_TRACE(6, tq);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int row0 = rb * kRows + q * 32;
+                const int r_max = a.rows - row0 < 32 ? a.rows - row0 : 32;
+                if (a.dbg & 8) {
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(bar0 + 8 * (kBarTmemFree + slot));
+                    continue;
+                }
+#pragma unroll 1
+                for (int pass = 0; pass < N / NP; ++pass) {
+                    if (pass) __syncwarp();
+#pragma unroll 1
+                    for (int h = 0; h < 2 * NP / 32; ++h) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + (h < NP / 32 ? pass * NP + h * 32 : N + pass * NP + (h - NP / 32) * 32), v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(my_row + h * 32 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (pass == N / NP - 1) asm volatile("tcgen05.fence::before_thread_sync;");
+                    __syncwarp();
+                    if (pass == N / NP - 1 && lane == 0) bar_arrive(bar0 + 8 * (kBarTmemFree + slot));
+                    if (pass == N / NP - 1 && q == 0) NVX_TRACE(7, tq);
+#pragma unroll 1
+                    for (int h = 0; h < NP / 32; ++h) {
+                        const int m = h * 32 + lane;
+                        const int n = pass * NP + m;
+                        if (n0 + n >= n_out) continue;
+                        const long long tick = a.k_abs + n0 + n;
+                        if (!a.mix) {
+                            float2* dst1 = a.out + (size_t)row0 * a.out_pitch + a.out_off + n0 + n;
+#pragma unroll 4
+                            for (int rr = 0; rr < r_max; ++rr, dst1 += a.out_pitch)
+                                *dst1 = make_float2(rows0[rr * kDumpPitch + m], rows0[rr * kDumpPitch + NP + m]);
+                            continue;
+                        }
+                        float2* dst = a.out + (size_t)(2 * row0) * a.out_pitch + a.out_off + n0 + n;
+                        if (a.nco) {
+                            const long long rden = tick % kNcoDen;
+                            const long long kden = rden < 0 ? rden + kNcoDen : rden;
+#pragma unroll 2
+                            for (int rr = 0; rr < r_max; ++rr, dst += 2 * a.out_pitch) {
+                                const NcoParam np = a.nco[row0 + rr];
+                                const float2 y = make_float2(rows0[rr * kDumpPitch + m], rows0[rr * kDumpPitch + NP + m]);
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    const int phs = (int)((kden * np.num[c]) % kNcoDen);
+                                    float tt = (float)phs * (2.0f / kNcoDen);
+                                    if (tt > 1.0f) tt -= 2.0f;
+                                    float sn, cs;
+                                    sincospif(tt, &sn, &cs);
+                                    dst[c * a.out_pitch] = make_float2(fmaf(y.y, sn, y.x * cs), fmaf(-y.x, sn, y.y * cs));
+                                }
+                            }
+                        } else {
+                            const long long r9 = tick % kNcoPeriod;
+                            const float2 rot = s_nco[r9 < 0 ? r9 + kNcoPeriod : r9];
+#pragma unroll 4
+                            for (int rr = 0; rr < r_max; ++rr, dst += 2 * a.out_pitch) {
+                                const float2 y = make_float2(rows0[rr * kDumpPitch + m], rows0[rr * kDumpPitch + NP + m]);
+                                dst[0] = make_float2(fmaf(-y.y, rot.y, y.x * rot.x), fmaf(y.x, rot.y, y.y * rot.x));
+                                dst[a.out_pitch] = make_float2(fmaf(y.y, rot.y, y.x * rot.x), fmaf(-y.x, rot.y, y.y * rot.x));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        })
+    }
+#undef NVX_FOR_SEGMENTS
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -518,6 +920,10 @@ float tf32_rna(float x) {                  // round to nearest, ties away, 10-bi
 }
 
 int tc_chunks(int D, int N, int T) { return (D * (N - 1) + T + chunk_samples(D) - 1) / chunk_samples(D); }
+// streaming kernel geometry: chunks per tile advance, and the chunks a window leads its tile by for T_taps taps (the tap count is
+// padded to D + lead * chunk so that tile windows are whole chunks of ONE global grid)
+int tcs_cpt(int D) { return D * kSN / chunk_samples(D); }
+int tcs_lead(int D, int T_taps) { return T_taps <= D ? 0 : (T_taps - D + chunk_samples(D) - 1) / chunk_samples(D); }
 // rows of one copy of the band matrix: N plus one 8-row atom per further (group of) chunk(s)
 int tc_band_rows(int D, int N, int T) { return N + 8 * ((tc_chunks(D, N, T) - 1) / band_copies(D)); }
 size_t tc_smem(int D, int N, int T, int slots) {
@@ -534,6 +940,17 @@ int tc_slots(int D, int N, int T) {        // raw-input slots that fit beside th
     for (int slots = kMaxSlots; slots >= 4; slots -= 2)
         if (tc_smem(D, N, T, slots) <= (size_t)kSmemLimit) return slots;
     return 0;
+}
+
+template <int D>
+cudaError_t launch_tcs(TcArgs& a, int sms, cudaStream_t stream) {
+    a.slots = tc_slots(D, kSN, a.T);
+    const size_t smem = tc_smem(D, kSN, a.T, a.slots);
+    cudaError_t e = cudaFuncSetAttribute(fir_tcs_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long grid = a.work < sms ? a.work : sms;
+    fir_tcs_kernel<D><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 template <int D, int N>
@@ -563,8 +980,18 @@ int long_tc_tile(int D, int T) {
     return 0;
 }
 
+// the streaming kernel serves a stage when a window spans at most two tiles (lead <= chunks per tile) and its band fits;
+// NVX_TC_STREAM=0 keeps the tile-at-a-time kernel (A/B measurements)
+bool tcs_applies(int D, int T_taps) {
+    if (D != NVX_D1 && D != NVX_D2) return false;
+    if (getenv("NVX_TC_STREAM") && atoi(getenv("NVX_TC_STREAM")) == 0) return false;
+    const int lead = tcs_lead(D, T_taps);
+    return lead <= tcs_cpt(D) && tc_slots(D, kSN, D + lead * chunk_samples(D)) > 0;
+}
+
 struct LongTcStage {
     int D = 0, T = 0, N = 0, chunks = 0, J = 0, box_rows = 0;
+    bool streaming = false;
     float *d_gh = nullptr, *d_gl = nullptr;
     CUtensorMap map_gh, map_gl;
     EncodeTiledFn enc = nullptr;
@@ -578,7 +1005,14 @@ bool long_tc_band(int D, int T_taps, const double* h, TcBand* b) {
     // instead of 9
     int T = T_taps;
     while ((D - T) & 3) ++T;
-    const int N = long_tc_tile(D, T);
+    int N;
+    b->streaming = tcs_applies(D, T_taps);
+    if (b->streaming) {        // streaming kernel: windows are whole chunks of one global grid, T = D + lead * chunk
+        T = D + tcs_lead(D, T_taps) * chunk_samples(D);
+        N = kSN;
+    } else {
+        N = long_tc_tile(D, T);
+    }
     if (!N) return false;
     b->T = T; b->N = N;
     b->chunks = tc_chunks(D, N, T);
@@ -611,6 +1045,7 @@ LongTcStage* long_tc_prepare(int D, int T_taps, const double* h, cudaStream_t st
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
     LongTcStage* s = new LongTcStage();
     s->D = D; s->T = band.T; s->N = band.N;
+    s->streaming = band.streaming;
     s->chunks = band.chunks;
     s->J = band.J;
     s->box_rows = tc_box_rows(s->J);
@@ -659,7 +1094,9 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     // TMA boxes and 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by
     // construction).  The block as a 2-D tensor of 32-bit (float2 input) or 16-bit (short2 input) elements, two per sample:
     if (((uintptr_t)la.in & 15) || ((in_pitch * (la.s16 ? 4 : 8)) & 15)) return cudaErrorNotSupported;
-    if (chunk_samples(s->D) == kKB) {
+    a.cpt = tcs_cpt(s->D);
+    a.lead = s->chunks - a.cpt;
+    if (chunk_samples(s->D) == kKB || s->streaming) {
         const size_t esz = la.s16 ? 2 : 4;
         cuuint64_t dims[2] = {(cuuint64_t)(2 * la.n_in), (cuuint64_t)la.rows_in};
         cuuint64_t strides[1] = {(cuuint64_t)in_pitch * 2 * esz};
@@ -677,6 +1114,31 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (s->streaming) {
+        static long long* d_trace = nullptr;
+        static int traced = 0;
+        const char* tr = getenv("NVX_TC_TRACE");       // development aid: NVX_TC_TRACE=<decimation> dumps CTA 0's timeline of one launch to stderr
+        const bool want = tr && atoi(tr) == s->D && traced < 3;
+        if (want && !d_trace) cudaMalloc(&d_trace, sizeof(long long) * kTraceChunks * kTraceCols);
+        if (want) { cudaMemsetAsync(d_trace, 0, sizeof(long long) * kTraceChunks * kTraceCols, stream); a.trace = d_trace; }
+        a.dbg = (tr && getenv("NVX_TC_DBG")) ? atoi(getenv("NVX_TC_DBG")) : 0;      // knock-out experiments: only together with the trace
+        const cudaError_t e = s->D == NVX_D1 ? launch_tcs<NVX_D1>(a, sms, stream) : launch_tcs<NVX_D2>(a, sms, stream);
+        if (want && e == cudaSuccess && ++traced == 3) {
+            static long long h[kTraceChunks * kTraceCols];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "# tcs trace D=%d: chunk  AFull_seen issued | raw_full converted AEmpty_seen AFull_arrived | tile_done tmem_freed (cycles since first stamp)\n", s->D);
+            long long t0 = h[2];
+            fprintf(stderr, "# dbg=%d: cycles per chunk over chunks 24..88 = %.0f\n", a.dbg, (double)(h[88 * kTraceCols + 1] - h[24 * kTraceCols + 1]) / 64.0);
+            if (!getenv("NVX_TC_TRACE_FULL")) return e;
+            for (int k = 0; k < kTraceChunks; ++k) {
+                fprintf(stderr, "%3d", k);
+                for (int c = 0; c < kTraceCols; ++c) fprintf(stderr, " %8lld", h[k * kTraceCols + c] ? h[k * kTraceCols + c] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+        }
+        return e;
+    }
     if (s->D == NVX_D1)
         return s->N == 128 ? launch_tc<NVX_D1, 128>(a, sms, stream)
                            : s->N == 64 ? launch_tc<NVX_D1, 64>(a, sms, stream) : launch_tc<NVX_D1, 32>(a, sms, stream);

@@ -20,7 +20,12 @@ def test_band_gemm_equals_the_decimating_fir(D, T):
     geo, g_hi, g_lo = engine.long_tc_band(D, h)
     N, chunks, J, P, Tp = geo["n_tile"], geo["chunks"], geo["band_rows"], geo["copies"], geo["taps_padded"]
     cs = 32 // D * D                                            # samples per chunk
-    assert (D - Tp) % 4 == 0 and T <= Tp < T + 4                # tile windows start on whole 32-byte sectors
+    cpt = D * N // cs                                           # chunks a tile advances by
+    lead = -(-(T - D) // cs)
+    if lead <= cpt and N == 64:                                 # streaming kernel: windows are whole chunks of one global grid
+        assert Tp == D + lead * cs and chunks == cpt + lead and chunks * cs == D * (N - 1) + Tp
+    else:                                                       # tile-at-a-time kernel: windows start on whole 32-byte sectors
+        assert (D - Tp) % 4 == 0 and T <= Tp < T + 4
     assert chunks * cs >= D * (N - 1) + Tp and J == N + 8 * ((chunks - 1) // P) and P == 8 // (cs // D)
     g = g_hi.astype(np.float64) + g_lo.astype(np.float64)
     assert not g[:, :, cs:].any()                               # the zero columns of a 28-sample chunk
@@ -28,7 +33,7 @@ def test_band_gemm_equals_the_decimating_fir(D, T):
     assert np.all((g_hi.view(np.uint32) & 0x1FFF) == 0)
     n_tiles = 3
     x = rng.normal(size=D * N * n_tiles + 64)
-    hist = Tp + 8                                               # samples before the block (the carried history)
+    hist = Tp + 40                                              # samples before the block (the carried history)
     xx = np.concatenate([rng.normal(size=hist), x])
     for tile in range(n_tiles):
         n0 = tile * N
@@ -54,5 +59,9 @@ def test_band_is_refused_where_the_kernel_does_not_apply():
     assert geo["n_tile"] == 64
     geo, _, _ = engine.long_tc_band(4, np.ones(511))
     assert geo["n_tile"] == 128                                 # stage 1 from 384 taps on while the band fits
+    geo, _, _ = engine.long_tc_band(4, np.ones(255))
+    assert geo["n_tile"] == 64 and geo["taps_padded"] == 260 and geo["chunks"] == 16      # streaming: 8 + 8 chunks of 32 samples
+    geo, _, _ = engine.long_tc_band(7, np.ones(255))
+    assert geo["n_tile"] == 64 and geo["taps_padded"] == 259 and geo["chunks"] == 25      # streaming: 16 + 9 chunks of 28 samples
     geo, _, _ = engine.long_tc_band(7, np.ones(959))
     assert geo["n_tile"] == 64 and geo["copies"] == 2
