@@ -419,6 +419,10 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     ca.y3_pitch = nvx::kHistY + e->P_max;
     ca.y3_off = nvx::kHistY;
 
+    // this block's FIR output goes into the y3 buffer block (blocks - 3) used -- long drained, see wait_drained above -- whose
+    // last samples the feed-forward kernels of block (blocks - 2) read as their history: when those run on the demod stream
+    // nothing else orders them before this launch
+    if (!e->ff_on_main && e->blocks >= 2) CU_TRY(cudaStreamWaitEvent(e->stream, e->ff_done[(b + 1) % kBuf], 0));
     cudaEvent_t t0 = nullptr, t1 = nullptr, marks[8] = {};
     if (e->timing) {
         const int base = (int)e->ev_used;
@@ -432,10 +436,6 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         }
         CU_TRY(cudaEventRecord(t0, e->stream));
     }
-    // this block's FIR output goes into the y3 buffer block (blocks - 3) used -- long drained, see wait_drained above -- whose
-    // last samples the feed-forward kernels of block (blocks - 2) read as their history: when those run on the demod stream
-    // nothing else orders them before this launch
-    if (!e->ff_on_main && e->blocks >= 2) CU_TRY(cudaStreamWaitEvent(e->stream, e->ff_done[(b + 1) % kBuf], 0));
     if (e->long_taps) {
         const int cur = e->lcur, nx = cur ^ 1;
         const long long p1 = e->cfg.max_block / NVX_D1, p2 = e->cfg.max_block / (NVX_D1 * NVX_D2);
@@ -499,10 +499,10 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     da.n_new = n_super; da.channels = e->channels; da.seen = e->sb_abs;
     da.events = e->d_events[b]; da.ev_count = e->d_ev_count[b]; da.ev_cap = e->ev_cap;
     da.bits = e->d_bits; da.disc = e->d_disc; da.bit_count = e->d_bit_count; da.bit_cap = e->bit_cap;
-    // The feed-forward demod kernels are short whole-GPU kernels (0.25 ms of FP64 work per 10 s block of 2048 channels).
-    // By default they run on the demod stream beside the NEXT block's cascade: that costs the cascade ~3 % (it runs one warp
-    // per SM sub-partition with little latency slack) but takes their 0.25 ms off the step's critical path -- measured 3.69
-    // against 3.82 ms per step.  NVX_PIPELINE=main keeps them behind the cascade on the main stream.
+    // The feed-forward demod kernels are short whole-GPU kernels (0.25 ms of FP64 work per 10 s block of 2048 channels); beside
+    // the cascade (one warp per SM sub-partition, little latency slack) they cost it about what they take alone, so by default
+    // they follow it on the main stream and only the sequential symbol-clock / state-machine kernels (64 warps on the SMs the
+    // cascade grid leaves free) overlap the next block's cascade.  NVX_PIPELINE=overlap moves them to the demod stream too.
     cudaStream_t s_ff = e->ff_on_main ? e->stream : e->stream_demod;
     if (!e->ff_on_main) CU_TRY(cudaStreamWaitEvent(e->stream_demod, e->casc_done[b], 0));
     CU_TRY(demod_launch(da, s_ff, e->stream_demod, e->ff_done[b], e->timing > 1 ? marks : nullptr));
@@ -644,13 +644,14 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
             CREATE_TRY(cudaEventCreateWithFlags(&e->stage_free[k], cudaEventDisableTiming));
         }
         CREATE_TRY(cudaStreamCreateWithPriority(&e->stream_demod, cudaStreamNonBlocking, hi));
-        // tuning knob NVX_PIPELINE: default "overlap" = the whole demod chain of block i (feed-forward kernels included) runs on
-        // the demod stream beside the cascade of block i + 1; "main" = the feed-forward kernels follow the cascade on the main
-        // stream (the cascade then runs at its stand-alone speed, the step is ~4 % longer); "serial" = additionally the next
+        // tuning knob NVX_PIPELINE: default "main" = the feed-forward demod kernels follow the cascade on the main stream and only
+        // the sequential kernels run beside the next cascade; "overlap" = the whole demod chain of block i runs on the demod
+        // stream beside the cascade of block i + 1 (A/B on one box, 30 steps each, twice: 3.81 / 3.84 ms per step against 3.86 /
+        // 3.81 -- no difference beyond the noise, while the cascade itself slows from 3.48 to 3.71 ms); "serial" = the next
         // cascade waits for the whole demod
         const char* mode = getenv("NVX_PIPELINE");
         e->serial = mode && !strcmp(mode, "serial");
-        e->ff_on_main = e->serial || (mode && !strcmp(mode, "main"));
+        e->ff_on_main = !(mode && !strcmp(mode, "overlap"));
     }
     for (int k = 0; k < kBuf; ++k) {
         CREATE_TRY(cudaEventCreateWithFlags(&e->casc_done[k], cudaEventDisableTiming));
