@@ -638,6 +638,34 @@ def leg_config5(c, x, expect, taps_n, steps, warmup):
     }
 
 
+def leg_channels(c, x, expect):
+    """the cost of more channels per capture sharing stage 1.  The default captures through engines with 2 (the
+    reference's table NCO), 2, 3 and 4 channels on per-stream offsets (+14 / -14 kHz and two neighbours): kernel time of the one
+    pass against the HBM bound of the same bytes; the bulletins on the first two channels are checked as everywhere."""
+    import numpy as np
+    from navtex_b200 import engine
+
+    S = STREAMS_PER_GPU
+    peak, _ = measured_peak()
+    offsets, tags = [14000.0, -14000.0, 7000.0, -21000.0], [518, 490, 511, 483]
+    out = []
+    for n_ch, general in ((2, False), (2, True), (3, True), (4, True)):
+        kw = {}
+        if general:
+            kw = dict(nco_hz=np.tile(np.array(offsets[:n_ch]), (S, 1)), stream_freq_tag=np.tile(np.array(tags[:n_ch]), (S, 1)), n_channels=n_ch)
+        eng = engine.Engine(S, BLOCK, device=c.local, first_stream_id=c.rank * S, **kw)
+        ms, st, msgs, clocks, spans = timed_pushes(c, eng, x.data_ptr(), BLOCK, 5, 2)
+        ok, _ = count_exact(msgs, expect)
+        ok_all, = allreduce_sum(c, [ok])
+        eng.close()
+        k_ms = st.cascade_ms / max(1, st.cascade_launches)
+        bytes_alg = S * BLOCK * (8.0 + n_ch * 8.0 / 280)
+        out.append({"channels": n_ch, "nco": "per-stream offsets (exact integer phase)" if general else "reference 9-entry table",
+                    "kernel_ms": k_ms, **span_stats(spans), "ms_per_step": ms / 5, "value": c.world * S * BLOCK * 5 / (ms * 1e-3) / 1e6,
+                    "hbm_frac": bytes_alg / (k_ms * 1e-3) / 1e9 / peak, "decoded_exact_all_ranks": ok_all})
+    return {"unit": "Msamples/s", "what": "fused kernel with n channels per capture sharing stage 1, 5 timed steps each, same captures", "runs": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -651,7 +679,7 @@ def main():
                          "configs[3]) as the whole line; config5: the default captures through --taps-tap filters (configs[4])")
     ap.add_argument("--taps", type=int, default=255, help="config5: taps per stage")
     ap.add_argument("--seconds", type=float, default=60.0, help="--workload config4: traffic per stream")
-    ap.add_argument("--skip", default="", help="comma-separated legs to leave out of the default line: parity,int16,e2e,config4,config5,cpu")
+    ap.add_argument("--skip", default="", help="comma-separated legs to leave out of the default line: parity,int16,e2e,config4,config5,channels,cpu")
     ap.add_argument("--pinned", default="nvx", choices=["nvx", "wc"], help="e2e host buffer: cudaHostAlloc portable (nvx) or write-combined (wc)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -790,6 +818,7 @@ def main():
         e2e, n_e2e, e2e_exact, e2e_expected = leg_e2e(c, x, expect, args)
 
     # ---- BASELINE configs[4] and configs[3], short passes in front of the driver ------------------
+    channels = leg_channels(c, x, expect) if "channels" not in skip else None
     config5 = leg_config5(c, x, expect, args.taps, 5, 2) if "config5" not in skip else None
     del x
     torch.cuda.empty_cache()
@@ -834,7 +863,7 @@ def main():
                    "input": "float2 IQ resident in HBM, 21.2 GB per GPU per step (larger than L2; no flush needed)",
                    "parallelism": f"stream-sharded x{world}, no collectives"},
         "realtime_streams": value / 0.252,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "int16_input": int16_input, "config4": config4, "config5": config5,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "int16_input": int16_input, "config4": config4, "config5": config5, "channels": channels,
         "gpu_launches": int(st.cascade_launches + st.demod_launches + st.aux_launches),
         "clocks": clocks,
         "check": check,

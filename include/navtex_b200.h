@@ -72,6 +72,12 @@ typedef struct {
      * and 2 on the tensor cores (3xTF32, equal to the FP64 oracle to 1e-5; different blockings agree to rounding, not bit
      * for bit -- set NVX_LONG_TC=0 in the environment for the CUDA-core kernels if block-invariant bits matter) */
     int n1, n2, n3;
+    /* channels per capture sharing stage 1: 0 = 2 (the reference's pair, nav_sched.C:10-16).  1 .. 8 channels
+     * need nco_hz [n_streams][n_channels] (and stream_freq_tag [n_streams][n_channels] if the messages are to be told apart);
+     * up to four are computed in ONE pass over the input -- stage 1 runs once, the mix and stages 2 / 3 once per channel, all
+     * in registers -- five to eight in two passes.  Reference tap class only (up to 37 / 47 / 71 taps).  Results are laid out
+     * [stream][channel] everywhere (y3, bits, events, messages). */
+    int n_channels;
 } nvx_config;
 
 typedef struct {
@@ -120,7 +126,7 @@ int nvx_engine_try_poll_messages(nvx_engine *e, const nvx_message **msgs, size_t
  * from this call; cb = NULL goes back to queueing for poll. */
 int nvx_engine_set_message_callback(nvx_engine *e, nvx_message_cb cb, void *user);
 
-/* taps of the LAST pushed block (imply sync).  y3: [S][2][n/280] float pairs (I,Q) at 900 Hz */
+/* taps of the LAST pushed block (imply sync).  y3: [S][n_channels][n/280] float pairs (I,Q) at 900 Hz */
 int nvx_engine_read_y3(nvx_engine *e, float *out, size_t cap_floats, size_t *n_per_channel);
 /* bits decided during the last block for (stream, ch): 'B'/'Y'; sums = 4 floats per bit (BR BI YR YI), may be NULL */
 int nvx_engine_read_bits(nvx_engine *e, int stream, int ch, char *bits, float *sums, size_t cap, size_t *count);

@@ -30,8 +30,8 @@ int cascade_box_elems(bool s16);
 int cascade_tap_class(int n1, int n2, int n3);
 int cascade_warm_super(int tap_class);
 void cascade_fill_taps(int tap_class, const double* h1, int n1, const double* h2, int n2, const double* h3, int n3, CascadeTaps* out);
-cudaError_t cascade_launch(const CascadeArgs& a, const CascadeTaps& taps, int tap_class, bool custom_taps, bool s16, cudaStream_t stream);
-int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class);
+cudaError_t cascade_launch(const CascadeArgs& a, const CascadeTaps& taps, int tap_class, bool custom_taps, bool s16, int n_ch, cudaStream_t stream);
+int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class, bool heavy);
 }  // namespace nvx
 
 namespace {
@@ -106,6 +106,7 @@ constexpr int kBuf = 3;   // blocks in flight: cascade of block i+1/i+2 overlaps
 struct nvx_engine {
     nvx_config cfg;
     int S = 0, P_max = 0, channels = 0;
+    int C = 2;                            // channels per stream (nvx_config.n_channels)
     cudaStream_t stream = nullptr;        // cascade, tail carry, ingest copies / conversion
     cudaStream_t stream_demod = nullptr;  // demod kernels + event download, one block behind
     float2* y3buf[kBuf] = {};
@@ -136,7 +137,8 @@ struct nvx_engine {
     int last_P = 0;
     bool custom_taps = false;
     nvx::CascadeTaps taps;                // this engine's filter constants: passed in the parameter block of every cascade launch
-    nvx::NcoParam* d_nco = nullptr;       // per-stream NCO parameters (general-NCO kernel variant), else null
+    nvx::NcoParam* d_nco = nullptr;       // per-stream NCO parameters, two-channel layout of the long-tap path, else null
+    nvx::NcoChan* d_nco_ch = nullptr;     // per (stream, channel) NCO parameters of the fused kernel's general-NCO variants, else null
     // long-tap path (tap counts other than 37 / 47 / 71): per-stage kernels, intermediates and histories in HBM
     bool long_taps = false;
     nvx::LongStage lst[3];
@@ -200,6 +202,7 @@ int free_engine(nvx_engine* e) {
     }
     if (e->stream_copy) cudaStreamDestroy(e->stream_copy);
     cudaFree(e->d_nco);
+    cudaFree(e->d_nco_ch);
     for (int k = 0; k < 3; ++k) { cudaFree(e->lhist[k][0]); cudaFree(e->lhist[k][1]); }
     cudaFree(e->y1buf); cudaFree(e->y2buf);
     nvx::long_tc_free(e->ltc[0]); nvx::long_tc_free(e->ltc[1]);
@@ -284,7 +287,7 @@ int drain_events(nvx_engine* e, int b) {
         int n = e->h_ev_count[b][ch];
         if (n > e->ev_cap) { n = e->ev_cap; rc = NVX_ERR_OVERFLOW; }
         if (n > 0)
-            e->assembler.feed(ch, e->cfg.first_stream_id + ch / 2, e->stream_tag.empty() ? e->cfg.freq_tag[ch & 1] : e->stream_tag[ch],
+            e->assembler.feed(ch, e->cfg.first_stream_id + ch / e->C, e->stream_tag.empty() ? e->cfg.freq_tag[(ch % e->C) & 1] : e->stream_tag[ch],
                               e->h_events[b] + (size_t)ch * e->ev_cap,
                               (size_t)n, &out);
     }
@@ -415,9 +418,11 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
     ca.n_super = n_super;
     ca.sb_phase = (int)(e->sb_abs % kNcoPeriod);
     ca.sb_abs = e->sb_abs;
-    ca.nco = e->d_nco;
+    ca.nco = e->d_nco_ch;
     ca.y3_pitch = nvx::kHistY + e->P_max;
     ca.y3_off = nvx::kHistY;
+    ca.ch_total = e->C;
+    ca.ch0 = 0;
 
     // this block's FIR output goes into the y3 buffer block (blocks - 3) used -- long drained, see wait_drained above -- whose
     // last samples the feed-forward kernels of block (blocks - 2) read as their history: when those run on the demod stream
@@ -467,7 +472,15 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         e->lcur = nx;
         e->stats.aux_launches += 5;
     } else {
-        CU_TRY(cascade_launch(ca, e->taps, e->tap_class, e->custom_taps, s16, e->stream));
+        // up to four channels share one pass over the input (stage 1 computed once for all of them); five to eight take two
+        for (int c0 = 0; c0 < e->C;) {
+            const int left = e->C - c0;
+            const int n_ch = left <= nvx::kMaxFusedCh ? left : (left + 1) / 2;      // 5 = 3 + 2, 6 = 3 + 3, 7 = 4 + 3, 8 = 4 + 4
+            ca.ch0 = c0;
+            CU_TRY(cascade_launch(ca, e->taps, e->tap_class, e->custom_taps, s16, n_ch, e->stream));
+            if (c0) e->stats.aux_launches++;
+            c0 += n_ch;
+        }
     }
     if (e->timing) CU_TRY(cudaEventRecord(t1, e->stream));
 
@@ -585,11 +598,18 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
     e->cfg.h1 = e->cfg.h2 = e->cfg.h3 = nullptr;    // copied to the device below, not retained
     e->cfg.nco_hz = nullptr;
     e->cfg.stream_freq_tag = nullptr;
-    if (cfg->stream_freq_tag) e->stream_tag.assign(cfg->stream_freq_tag, cfg->stream_freq_tag + 2 * (size_t)cfg->n_streams);
+    const int C = cfg->n_channels ? cfg->n_channels : 2;
+    if (C < 1 || C > nvx::kMaxChannels) { delete e; return fail(NVX_ERR_ARG, "n_channels %d outside 1..%d", C, nvx::kMaxChannels); }
+    if (C != 2 && !cfg->nco_hz) { delete e; return fail(NVX_ERR_ARG, "n_channels = %d needs nco_hz (only the reference's two channels have default offsets)", C); }
+    if ((long long)C * cfg->n_streams > 65535) { delete e; return fail(NVX_ERR_ARG, "n_streams x n_channels = %lld exceeds 65535 channel rows per engine", (long long)C * cfg->n_streams); }
+    e->C = C;
+    if (cfg->stream_freq_tag) e->stream_tag.assign(cfg->stream_freq_tag, cfg->stream_freq_tag + (size_t)C * (size_t)cfg->n_streams);
     std::vector<nvx::NcoParam> nco;
+    std::vector<nvx::NcoChan> nco_ch;
     if (cfg->nco_hz) {
-        nco.resize((size_t)cfg->n_streams);
-        for (int k = 0; k < 2 * cfg->n_streams; ++k) {
+        nco_ch.resize((size_t)cfg->n_streams * C);
+        if (C == 2) nco.resize((size_t)cfg->n_streams);
+        for (int k = 0; k < C * cfg->n_streams; ++k) {
             const double f = cfg->nco_hz[k], twice = 2.0 * f;
             if (!(fabs(f) < 31500.0) || twice != nearbyint(twice)) {
                 delete e;
@@ -597,13 +617,15 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
             }
             long long num = (long long)twice % nvx::kNcoDen;
             if (num < 0) num += nvx::kNcoDen;
-            nco[(size_t)k / 2].num[k & 1] = (int)num;
             // same expression as fir2cpp.C:105-106 for table entry 1, rounded once to float
-            nco[(size_t)k / 2].step[k & 1] = make_float2((float)cos((2 * M_PI * 1 * f) / 63000), (float)-sin((2 * M_PI * 1 * f) / 63000));
+            const float2 step = make_float2((float)cos((2 * M_PI * 1 * f) / 63000), (float)-sin((2 * M_PI * 1 * f) / 63000));
+            nco_ch[(size_t)k].num = (int)num;
+            nco_ch[(size_t)k].step = step;
+            if (C == 2) { nco[(size_t)k / 2].num[k & 1] = (int)num; nco[(size_t)k / 2].step[k & 1] = step; }
         }
     }
     e->S = cfg->n_streams;
-    e->channels = 2 * e->S;
+    e->channels = C * e->S;
     e->P_max = (int)(cfg->max_block / nvx::kSuper);
     e->custom_taps = cfg->h1 || cfg->h2 || cfg->h3;
     // tap counts: reference lengths unless given; sets up to 37/47/71 and up to 61/75/111 run through the fused kernel
@@ -617,6 +639,10 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         if (n[k] < 1 || n[k] > nvx::kLongMaxTaps) { delete e; return fail(NVX_ERR_ARG, "tap count %d outside 1..%d", n[k], nvx::kLongMaxTaps); }
     e->tap_class = nvx::cascade_tap_class(n[0], n[1], n[2]);
     e->long_taps = e->tap_class < 0;
+    if (C != 2 && e->tap_class != 0) {
+        delete e;
+        return fail(NVX_ERR_ARG, "n_channels = %d is served by the fused kernel's reference tap class only (up to %d / %d / %d taps)", C, NVX_T1, NVX_T2, NVX_T3);
+    }
     e->halo = nvx::kSuper * nvx::cascade_warm_super(e->tap_class);
     if (e->long_taps) {
         const int D[3] = {NVX_D1, NVX_D2, NVX_D3};
@@ -715,11 +741,15 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
         CREATE_TRY(cudaMalloc(&e->d_nco, nco.size() * sizeof(nvx::NcoParam)));
         CREATE_TRY(cudaMemcpy(e->d_nco, nco.data(), nco.size() * sizeof(nvx::NcoParam), cudaMemcpyHostToDevice));
     }
+    if (!nco_ch.empty()) {
+        CREATE_TRY(cudaMalloc(&e->d_nco_ch, nco_ch.size() * sizeof(nvx::NcoChan)));
+        CREATE_TRY(cudaMemcpy(e->d_nco_ch, nco_ch.data(), nco_ch.size() * sizeof(nvx::NcoChan), cudaMemcpyHostToDevice));
+    }
 #undef CREATE_TRY
     for (int f = 0; f < 2; ++f)
         for (int k = 0; k < 2; ++k)
             if (int rc = encode_rows(&e->map_tail[f][k], e->tail[f][k], e->halo, e->S, f != 0)) { free_engine(e); return rc; }
-    for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels), f != 0, e->tap_class);
+    for (int f = 0; f < 2; ++f) e->target_warps[f] = nvx::cascade_target_warps(cfg->device, nvx::demod_reserved_sms(e->channels), f != 0, e->tap_class, C > 2);
     e->assembler.resize(e->channels);
     if (int rc = reset_state(e)) { free_engine(e); return rc; }
     e->worker = std::thread(worker_main, e);
@@ -842,10 +872,10 @@ int nvx_engine_read_y3(nvx_engine* e, float* out, size_t cap_floats, size_t* n_p
 }
 
 int nvx_engine_read_bits(nvx_engine* e, int stream, int ch, char* bits, float* sums, size_t cap, size_t* count) {
-    if (!e || !bits || !count || stream < 0 || stream >= e->S || ch < 0 || ch > 1) return fail(NVX_ERR_ARG, "bad argument");
+    if (!e || !bits || !count || stream < 0 || stream >= e->S || ch < 0 || ch >= e->C) return fail(NVX_ERR_ARG, "bad argument");
     if (!e->d_bits) return fail(NVX_ERR_ARG, "engine was created without keep_bits");
     int rc = sync_engine(e);
-    const int c = stream * 2 + ch;
+    const int c = stream * e->C + ch;
     int n = 0;
     CU_TRY(cudaMemcpy(&n, e->d_bit_count + c, sizeof n, cudaMemcpyDeviceToHost));
     if (n > e->bit_cap) { n = e->bit_cap; rc = fail(NVX_ERR_OVERFLOW, "bit buffer overflow"); }
@@ -859,9 +889,9 @@ int nvx_engine_read_bits(nvx_engine* e, int stream, int ch, char* bits, float* s
 }
 
 int nvx_engine_read_events(nvx_engine* e, int stream, int ch, char* ev, size_t cap, size_t* count) {
-    if (!e || !ev || !count || stream < 0 || stream >= e->S || ch < 0 || ch > 1) return fail(NVX_ERR_ARG, "bad argument");
+    if (!e || !ev || !count || stream < 0 || stream >= e->S || ch < 0 || ch >= e->C) return fail(NVX_ERR_ARG, "bad argument");
     int rc = sync_engine(e);
-    const int c = stream * 2 + ch;
+    const int c = stream * e->C + ch;
     int n = e->h_ev_count[e->last_buf][c];
     if (n > e->ev_cap) n = e->ev_cap;
     if ((size_t)n > cap) return fail(NVX_ERR_ARG, "event buffer too small (%d needed)", n);

@@ -7,10 +7,10 @@
 
 namespace nvx {
 
-template <bool kImm, bool kGenNco, bool kS16, int kClass>
-__global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeParams<kClass> prm) {
+template <bool kImm, bool kGenNco, bool kS16, int kClass, int kCh>
+__global__ void __launch_bounds__(InFmt<kS16, kClass, kCh>::kWarps * 32, kCtasPerSm) fir_cascade_kernel(const __grid_constant__ CascadeParams<kClass> prm) {
     const CascadeArgs& a = prm.a;
-    using F = InFmt<kS16, kClass>;
+    using F = InFmt<kS16, kClass, kCh>;
     using G = Geo<kClass>;
     constexpr int kWarmSuper = G::kWarm, kHalo = G::kWarm * kSuper, kLive1 = G::kLive1, kLive2 = G::kLive2, kLive3 = G::kLive3;
     constexpr int kWarpsPerCta = F::kWarps;
@@ -59,11 +59,11 @@ __global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) 
     for (int s = 0; s < kStages; ++s)
         if (s < warp_stages) issue(s, s);
 
-    CascadeState<kClass> st;
+    CascadeState<kClass, kCh> st;
 #pragma unroll
     for (int j = 0; j < kLive1; ++j) st.a1[j] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kCh; ++c) {
 #pragma unroll
         for (int j = 0; j < kLive2; ++j) st.a2[c][j] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -74,24 +74,27 @@ __global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) 
     // superblock index; identical for every lane (same time position, all streams share the chunk clock).
     int phase = (7 * ((a.sb_phase + first_sb + 9 * kWarmSuper - kWarmSuper) % kNcoPeriod)) % kNcoPeriod;
     // general NCO: exact phase numerators of this lane's two channels at the first stage-1 output of the warm-up
-    NcoLane nl = {};
-    int nco_idx[2] = {0, 0}, nco_adv[2] = {0, 0};
+    NcoLane<kCh> nl = {};
+    int nco_idx[kCh] = {}, nco_adv[kCh] = {};
     if (kGenNco) {
-        const NcoParam np = a.nco[strm < a.streams ? strm : a.streams - 1];
+        const NcoChan* np = a.nco + (size_t)(strm < a.streams ? strm : a.streams - 1) * a.ch_total + a.ch0;
         long long k0 = ((a.sb_abs + first_sb - kWarmSuper) * (long long)(kSuper / NVX_D1)) % kNcoDen;    // 70 outputs per superblock
         if (k0 < 0) k0 += kNcoDen;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            nco_idx[c] = (int)((k0 * np.num[c]) % kNcoDen);
-            nco_adv[c] = (int)(((long long)NVX_D2 * np.num[c]) % kNcoDen);
-            nl.step[c] = np.step[c];
+        for (int c = 0; c < kCh; ++c) {
+            const NcoChan pc = np[c];
+            nco_idx[c] = (int)((k0 * pc.num) % kNcoDen);
+            nco_adv[c] = (int)(((long long)NVX_D2 * pc.num) % kNcoDen);
+            nl.step[c] = pc.step;
         }
     }
     int stage = 0;
     uint32_t parity = 0;
-    float2* const y3row = a.y3 + (size_t)strm * 2 * a.y3_pitch + a.y3_off + first_sb;
+    float2* const y3row = a.y3 + ((size_t)strm * a.ch_total + a.ch0) * a.y3_pitch + a.y3_off + first_sb;
 
-    float2 y3[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float2 y3[kCh];
+#pragma unroll
+    for (int c = 0; c < kCh; ++c) y3[c] = make_float2(0.f, 0.f);
     int r10 = 0, out = -kWarmSuper;
     for (int t = 0; t < warp_stages; ++t) {
         mbar_wait(bar0 + 8 * stage, parity);
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) 
         for (int u = 0; u < kStepsPerStage; ++u) {
             if (kGenNco) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < kCh; ++c) {
                     float t = (float)nco_idx[c] * (2.0f / kNcoDen);      // turns * 2, in [0, 2)
                     if (t > 1.0f) t -= 2.0f;
                     float sn, cs;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) 
                     if (nco_idx[c] >= kNcoDen) nco_idx[c] -= kNcoDen;
                 }
             }
-            cascade_step<kImm, kGenNco, kS16, kClass>(prm.taps, prm.nco, st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3, nl);
+            cascade_step<kImm, kGenNco, kS16, kClass, kCh>(prm.taps, prm.nco, st, reinterpret_cast<const float4*>(rowb + u * kStepBytes), phase, r10 + u, y3, nl);
             phase += 7;
             if (phase >= kNcoPeriod) phase -= kNcoPeriod;
         }
@@ -125,8 +128,8 @@ __global__ void __launch_bounds__(InFmt<kS16, kClass>::kWarps * 32, kCtasPerSm) 
         if (r10 == kStepsPerSuper) {
             r10 = 0;
             if (out >= 0 && out < my_super) {
-                y3row[out] = y3[0];
-                y3row[a.y3_pitch + out] = y3[1];
+#pragma unroll
+                for (int c = 0; c < kCh; ++c) y3row[c * a.y3_pitch + out] = y3[c];
             }
             ++out;
         }
@@ -177,36 +180,42 @@ void cascade_fill_taps(int tap_class, const double* h1, int n1, const double* h2
 
 // warps that are resident at once across the device, leaving `reserved_sms` SMs to the sequential demod kernels:
 // the host sizes the grid to at most one full wave
-template <bool kS16, int kClass>
+template <bool kS16, int kClass, int kCh>
 static int target_warps_fmt(int device, int reserved_sms) {
-    using F = InFmt<kS16, kClass>;
+    using F = InFmt<kS16, kClass, kCh>;
     int sms = 148, per_sm = kCtasPerSm;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    auto kern = fir_cascade_kernel<false, false, kS16, kClass>;
+    auto kern = fir_cascade_kernel<false, true, kS16, kClass, kCh>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::kSmemBytes);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, F::kWarps * 32, F::kSmemBytes) != cudaSuccess || per_sm < 1)
         per_sm = kCtasPerSm;
     if (sms - reserved_sms >= 8) sms -= reserved_sms;
     return sms * per_sm * F::kWarps;
 }
-int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class) {
-    if (tap_class == 1) return s16 ? target_warps_fmt<true, 1>(device, reserved_sms) : target_warps_fmt<false, 1>(device, reserved_sms);
-    return s16 ? target_warps_fmt<true, 0>(device, reserved_sms) : target_warps_fmt<false, 0>(device, reserved_sms);
+// heavy = a launch carries three or four channels (different CTA shape for int16 input)
+int cascade_target_warps(int device, int reserved_sms, bool s16, int tap_class, bool heavy) {
+    if (tap_class == 1) return s16 ? target_warps_fmt<true, 1, 2>(device, reserved_sms) : target_warps_fmt<false, 1, 2>(device, reserved_sms);
+    if (heavy) return s16 ? target_warps_fmt<true, 0, 4>(device, reserved_sms) : target_warps_fmt<false, 0, 4>(device, reserved_sms);
+    return s16 ? target_warps_fmt<true, 0, 2>(device, reserved_sms) : target_warps_fmt<false, 0, 2>(device, reserved_sms);
 }
 
-template <bool kS16, int kClass>
+template <bool kS16, int kClass, int kCh>
 static cudaError_t launch_fmt(const CascadeArgs& a, const CascadeTaps& taps, bool custom_taps, cudaStream_t stream) {
-    const size_t smem = InFmt<kS16, kClass>::kSmemBytes;
+    const size_t smem = InFmt<kS16, kClass, kCh>::kSmemBytes;
+    // more than two channels always run the general (per-channel) NCO; two channels use the reference's table unless offsets were given
     const bool gen = a.nco != nullptr;
     // immediates only for the reference taps themselves; every other set (class 0 or 1) reads the constant bank
     constexpr bool kCanImm = kClass == 0;
-    auto kern = gen ? ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, true, kS16, kClass> : fir_cascade_kernel<kCanImm, true, kS16, kClass>)
-                    : ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, false, kS16, kClass> : fir_cascade_kernel<kCanImm, false, kS16, kClass>);
+    constexpr bool kTable = kCh == 2;          // the table variants exist for exactly two channels
+    auto kern = (gen || !kTable)
+                    ? ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, true, kS16, kClass, kCh> : fir_cascade_kernel<kCanImm, true, kS16, kClass, kCh>)
+                    : ((custom_taps || !kCanImm) ? fir_cascade_kernel<false, !kTable, kS16, kClass, kCh> : fir_cascade_kernel<kCanImm, !kTable, kS16, kClass, kCh>);
+    if (!gen && !kTable) return cudaErrorInvalidValue;
     {   // function attributes are per device: set on every launch (cheap) rather than cached process-wide
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    constexpr int kWarpsPerCta = InFmt<kS16, kClass>::kWarps;
+    constexpr int kWarpsPerCta = InFmt<kS16, kClass, kCh>::kWarps;
     const long long warps = (long long)((a.streams + 31) / 32) * a.segs;
     const unsigned grid = (unsigned)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
     CascadeParams<kClass> prm;
@@ -217,9 +226,19 @@ static cudaError_t launch_fmt(const CascadeArgs& a, const CascadeTaps& taps, boo
     return cudaGetLastError();
 }
 
-cudaError_t cascade_launch(const CascadeArgs& a, const CascadeTaps& taps, int tap_class, bool custom_taps, bool s16, cudaStream_t stream) {
-    if (tap_class == 1) return s16 ? launch_fmt<true, 1>(a, taps, true, stream) : launch_fmt<false, 1>(a, taps, true, stream);
-    return s16 ? launch_fmt<true, 0>(a, taps, custom_taps, stream) : launch_fmt<false, 0>(a, taps, custom_taps, stream);
+// n_ch = channels of this launch (a.ch0 .. a.ch0 + n_ch - 1): 2 in either tap class, 1 / 3 / 4 in the reference class
+cudaError_t cascade_launch(const CascadeArgs& a, const CascadeTaps& taps, int tap_class, bool custom_taps, bool s16, int n_ch, cudaStream_t stream) {
+    if (tap_class == 1) {
+        if (n_ch != 2) return cudaErrorInvalidValue;
+        return s16 ? launch_fmt<true, 1, 2>(a, taps, true, stream) : launch_fmt<false, 1, 2>(a, taps, true, stream);
+    }
+    switch (n_ch) {
+        case 1: return s16 ? launch_fmt<true, 0, 1>(a, taps, custom_taps, stream) : launch_fmt<false, 0, 1>(a, taps, custom_taps, stream);
+        case 2: return s16 ? launch_fmt<true, 0, 2>(a, taps, custom_taps, stream) : launch_fmt<false, 0, 2>(a, taps, custom_taps, stream);
+        case 3: return s16 ? launch_fmt<true, 0, 3>(a, taps, custom_taps, stream) : launch_fmt<false, 0, 3>(a, taps, custom_taps, stream);
+        case 4: return s16 ? launch_fmt<true, 0, 4>(a, taps, custom_taps, stream) : launch_fmt<false, 0, 4>(a, taps, custom_taps, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace nvx

@@ -84,7 +84,7 @@ constexpr int kCtasPerSm = NVX_CTAS_PER_SM;
 // instruction fetch from L2 is not hidden (measured: 5 steps per stage = 5.3 ms, 2 steps = 3.3 ms per block).  Being
 // issue-bound it also wants more warps per sub-partition: 12 warps x 2 stages = 2.77 ms, 8 x 3 = 2.90 ms, 16 x 1 = 2.81 ms,
 // 4 warps x 6 stages = 3.27 ms.
-template <bool kS16, int kClass = 0>
+template <bool kS16, int kClass = 0, int kCh = 2>
 struct InFmt {
     static constexpr int kSteps = kS16 ? NVX_S16_STEPS_PER_STAGE : NVX_STEPS_PER_STAGE;   // 28-sample steps per TMA box row
     static constexpr int kSampleBytes = kS16 ? 4 : 8;
@@ -94,9 +94,10 @@ struct InFmt {
     static constexpr int kBoxElems = kRowBytes / 4;                                       // TMA box width in 32-bit elements (pad over-fetched)
     static constexpr int kElemsPerSample = kSampleBytes / 4;
     static constexpr int kStageBytes = 32 * kRowBytes;                                    // per warp per stage
-    // the medium tap class needs ~250 registers per thread: 4 warps per CTA for either format
-    static constexpr int kStages = kS16 ? (kClass == 0 ? NVX_S16_STAGES : 6) : NVX_STAGES;
-    static constexpr int kWarps = kS16 ? (kClass == 0 ? NVX_S16_WARPS_PER_CTA : 4) : NVX_WARPS_PER_CTA;      // per CTA
+    // the medium tap class needs ~250 registers per thread: 4 warps per CTA for either format; three or four channels sharing
+    // stage 1 need ~200: at most 8 warps per CTA
+    static constexpr int kStages = kS16 ? (kClass != 0 ? 6 : kCh > 2 ? 3 : NVX_S16_STAGES) : NVX_STAGES;
+    static constexpr int kWarps = kS16 ? (kClass != 0 ? 4 : kCh > 2 ? 8 : NVX_S16_WARPS_PER_CTA) : NVX_WARPS_PER_CTA;      // per CTA
     static constexpr int kSmemBytes = kWarps * kStages * kStageBytes + kWarps * kStages * 8;
     static_assert(kStepsPerSuper % kSteps == 0, "a stage must not straddle superblocks");
     static_assert(kRowBytes % 16 == 0 && kStageBytes % 128 == 0 && kBoxElems <= 256, "TMA box alignment");
@@ -141,10 +142,17 @@ struct NcoTable { float2 w[kNcoPeriod + NVX_D2]; };
 // output k is k * f / 63000 turns, tracked exactly as an integer numerator over 126000 (f on a 0.5 Hz grid); every
 // 28-sample step re-seeds the phasor from that exact phase (sincospif) and advances it by six complex multiplies.
 constexpr int kNcoDen = 126000;
-struct NcoParam {
+struct NcoParam {      // two-channel layout of the long-tap path
     int num[2];        // (2 f) mod 126000, per channel
     float2 step[2];    // (cos, -sin)(2 pi f / 63000): rotation per stage-1 output
 };
+// fused kernel: one entry per (stream, channel), [S][channels]: any number of channels can share stage 1
+struct NcoChan {
+    int num;           // (2 f) mod 126000
+    float2 step;       // (cos, -sin)(2 pi f / 63000)
+};
+constexpr int kMaxFusedCh = 4;   // channels one pass of the fused kernel carries in registers (9 + 14 per channel complex partial sums)
+constexpr int kMaxChannels = 8;  // per capture: more than four take two passes over the input
 
 struct CascadeArgs {
     CUtensorMap map_x;    // 32-bit view [S][2 n] (float2 input) or [S][n] (short2 input) of this chunk, box InFmt::kBoxElems x 32
@@ -157,9 +165,11 @@ struct CascadeArgs {
     int n_super;          // n / kSuper
     int sb_phase;         // (absolute superblock index of chunk start) mod 9
     long long sb_abs;     // absolute superblock index of chunk start
-    const NcoParam* nco;  // [S] per-stream NCO (kernel variants with kGenNco), else null
+    const NcoChan* nco;   // [S][ch_total] per-stream NCO (kernel variants with kGenNco), else null
     long long y3_pitch;
     long long y3_off;
+    int ch_total;         // channels per stream (rows of y3 per stream)
+    int ch0;              // first channel this launch computes (it computes kCh of them)
 };
 
 // Everything a launch needs travels in the kernel parameter block (constant bank 0, __grid_constant__): the tap set and the NCO
@@ -211,20 +221,21 @@ template <bool kImm, int kClass> __device__ __forceinline__ float tap2(const Tap
 
 __device__ __forceinline__ float2 fma2(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
 
-template <int kClass>
+template <int kClass, int kCh>
 struct CascadeState {
     float2 a1[Geo<kClass>::kLive1];
-    float2 a2[2][Geo<kClass>::kLive2];
-    float2 a3[2][Geo<kClass>::kLive3];
+    float2 a2[kCh][Geo<kClass>::kLive2];
+    float2 a3[kCh][Geo<kClass>::kLive3];
 };
 
 // One step: 28 inputs of one row -> 7 stage-1 outputs -> mix -> one stage-2 output per channel ->
 // scattered into the stage-3 partial sums.  r10 = position of this step inside its superblock.
 // y3 is written when r10 == 9 completed a 900 Hz sample.
 // Per-lane phasors of the general NCO (unused by the reference-table variants)
+template <int kCh>
 struct NcoLane {
-    float2 w[2];      // current (cos, -sin) per channel
-    float2 step[2];
+    float2 w[kCh];    // current (cos, -sin) per channel
+    float2 step[kCh];
 };
 
 // (double)short of capt_sched.c:511, exact in float, without the quarter-rate I2F unit: flip the sign bits (offset
@@ -236,21 +247,22 @@ __device__ __forceinline__ float2 iq_of(int packed) {
     return __fadd2_rn(biased, make_float2(-8421376.0f, -8421376.0f));
 }
 
-template <bool kImm, bool kGenNco, bool kS16, int kClass>
-__device__ __forceinline__ void cascade_step(const TapSet<kClass>& ts, const NcoTable& nco, CascadeState<kClass>& st,
-                                             const float4* __restrict__ row, int nco_phase, const int r10, float2 (&y3)[2], NcoLane& nl) {
+template <bool kImm, bool kGenNco, bool kS16, int kClass, int kCh>
+__device__ __forceinline__ void cascade_step(const TapSet<kClass>& ts, const NcoTable& nco, CascadeState<kClass, kCh>& st,
+                                             const float4* __restrict__ row, int nco_phase, const int r10, float2 (&y3)[kCh], NcoLane<kCh>& nl) {
     using G = Geo<kClass>;
     constexpr int kLive1 = G::kLive1, kLive2 = G::kLive2, kLive3 = G::kLive3;
     static_assert(!kImm || kClass == 0, "immediate taps are the reference set");
+    static_assert(kGenNco || kCh == 2, "the reference's 9-entry table serves exactly its two channels (+14 kHz and its conjugate)");
     float2 w[kLive1 + NVX_D2];
 #pragma unroll
     for (int j = 0; j < kLive1; ++j) w[j] = st.a1[j];
 #pragma unroll
     for (int j = kLive1; j < kLive1 + NVX_D2; ++j) w[j] = make_float2(0.f, 0.f);
 
-    float2 b[2][kLive2 + 1];
+    float2 b[kCh][kLive2 + 1];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kCh; ++c) {
 #pragma unroll
         for (int j = 0; j < kLive2; ++j) b[c][j] = st.a2[c][j];
         b[c][kLive2] = make_float2(0.f, 0.f);
@@ -275,10 +287,10 @@ __device__ __forceinline__ void cascade_step(const TapSet<kClass>& ts, const Nco
         }
         const float2 y1 = w[q];
         // NCO mix (fir2cpp.C:115-124): ch0 = y1 * (re + j im), ch1 = y1 * (re - j im), (re, im) = (cos, -sin)
-        float2 m[2];
+        float2 m[kCh];
         if (kGenNco) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < kCh; ++c) {
                 const float2 rot = nl.w[c];
                 m[c] = make_float2(fmaf(-y1.y, rot.y, y1.x * rot.x), fmaf(y1.x, rot.y, y1.y * rot.x));
                 if (q + 1 < NVX_D2)     // advance the phasor: w *= step
@@ -288,10 +300,10 @@ __device__ __forceinline__ void cascade_step(const TapSet<kClass>& ts, const Nco
             const float2 rot = nco.w[nco_phase + q];
             const float ar = y1.x * rot.x, br = y1.y * rot.x;
             m[0] = make_float2(fmaf(-y1.y, rot.y, ar), fmaf(y1.x, rot.y, br));
-            m[1] = make_float2(fmaf(y1.y, rot.y, ar), fmaf(-y1.x, rot.y, br));
+            m[kCh - 1] = make_float2(fmaf(y1.y, rot.y, ar), fmaf(-y1.x, rot.y, br));
         }
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kCh; ++c) {
 #pragma unroll
             for (int j = 0; 7 * j + 6 - q < G::T2; ++j) b[c][j] = fma2(m[c], tap2<kImm, kClass>(ts, 7 * j + 6 - q), b[c][j]);
         }
@@ -300,7 +312,7 @@ __device__ __forceinline__ void cascade_step(const TapSet<kClass>& ts, const Nco
     for (int j = 0; j < kLive1; ++j) st.a1[j] = w[j + NVX_D2];
 
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kCh; ++c) {
         const float2 y2 = b[c][0];
 #pragma unroll
         for (int j = 0; j < kLive2; ++j) st.a2[c][j] = b[c][j + 1];
@@ -311,7 +323,7 @@ __device__ __forceinline__ void cascade_step(const TapSet<kClass>& ts, const Nco
     }
     if (r10 == NVX_D3 - 1) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kCh; ++c) {
             y3[c] = st.a3[c][0];
 #pragma unroll
             for (int j = 1; j < kLive3; ++j) st.a3[c][j - 1] = st.a3[c][j];

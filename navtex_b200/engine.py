@@ -26,7 +26,7 @@ class Config(C.Structure):
         ("h1", C.POINTER(C.c_double)), ("h2", C.POINTER(C.c_double)), ("h3", C.POINTER(C.c_double)),
         ("keep_bits", C.c_int), ("first_stream_id", C.c_int),
         ("nco_hz", C.POINTER(C.c_double)), ("stream_freq_tag", C.POINTER(C.c_int)),
-        ("n1", C.c_int), ("n2", C.c_int), ("n3", C.c_int),
+        ("n1", C.c_int), ("n2", C.c_int), ("n3", C.c_int), ("n_channels", C.c_int),
     ]
 
 
@@ -162,7 +162,7 @@ class Engine:
     """One GPU, S streams.  Mirrors the reference's init / per-sample push / add_message flow, batched."""
 
     def __init__(self, n_streams: int, max_block: int, device: int = 0, keep_bits: bool = False, taps=None,
-                 first_stream_id: int = 0, nco_hz=None, stream_freq_tag=None):
+                 first_stream_id: int = 0, nco_hz=None, stream_freq_tag=None, n_channels: int = 2):
         L = load_library()
         cfg = Config()
         L.nvx_default_config(C.byref(cfg))
@@ -174,15 +174,17 @@ class Engine:
             cfg.h1, cfg.h2, cfg.h3 = (t.ctypes.data_as(C.POINTER(C.c_double)) for t in self._taps)
             # up to 37/47/71 and up to 61/75/111 taps: fused kernel (zero-padded); longer: the long-tap path
             cfg.n1, cfg.n2, cfg.n3 = (len(t) for t in self._taps)
-        if nco_hz is not None:           # [S, 2] per-stream channel offsets in Hz
-            self._nco = np.ascontiguousarray(nco_hz, dtype=np.float64).reshape(n_streams, 2)
+        cfg.n_channels = n_channels
+        if nco_hz is not None:           # [S, n_channels] per-stream channel offsets in Hz
+            self._nco = np.ascontiguousarray(nco_hz, dtype=np.float64).reshape(n_streams, n_channels)
             cfg.nco_hz = self._nco.ctypes.data_as(C.POINTER(C.c_double))
         if stream_freq_tag is not None:
-            self._tags = np.ascontiguousarray(stream_freq_tag, dtype=np.int32).reshape(n_streams, 2)
+            self._tags = np.ascontiguousarray(stream_freq_tag, dtype=np.int32).reshape(n_streams, n_channels)
             cfg.stream_freq_tag = self._tags.ctypes.data_as(C.POINTER(C.c_int))
         self._h = C.c_void_p()
         _check(L.nvx_engine_create(C.byref(cfg), C.byref(self._h)))
         self.L, self.S, self.max_block, self.device = L, n_streams, max_block, device
+        self.C = n_channels
         self.last_n = 0
 
     def close(self):
@@ -230,9 +232,9 @@ class Engine:
                 for k in range(cnt.value)]
 
     def read_y3(self) -> np.ndarray:
-        """[S, 2, P] complex64 of the last block."""
+        """[S, n_channels, P] complex64 of the last block."""
         P = self.last_n // BLOCK_ALIGN
-        out = np.empty((self.S, 2, P, 2), dtype=np.float32)
+        out = np.empty((self.S, self.C, P, 2), dtype=np.float32)
         got = C.c_size_t()
         _check(self.L.nvx_engine_read_y3(self._h, out.ctypes.data_as(C.c_void_p), out.size, C.byref(got)))
         assert got.value == P

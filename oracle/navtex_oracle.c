@@ -3,7 +3,7 @@
  * Plain-C FP64 restatement of the reference receive chain, one sample per
  * call, same operation order as the reference so that results are bit-equal
  * to the compiled reference at the default parameters (checked by
- * tests/test_oracle_vs_ref.py).  Build with -ffp-contract=off and no -march
+ * tests/test_oracle.py).  Build with -ffp-contract=off and no -march
  * so that, like the reference build (-O3 only, receiver/configure.ac:3-4),
  * no multiply-add is fused.
  *
@@ -318,12 +318,13 @@ typedef struct nvo_bsm {
 
 struct nvo_chain {
     nvo_params prm;
-    fir_t f1, f2[2], f3[2];
-    nco_t nco[2];
-    nvo_decoder dec[2];
-    nvo_bsm bsm[2];
-    long n3[2];
-    bytes_t y1, y2[2], y3[2], bits[2], bitpos[2], disc[2], pickm[2];
+    int nch;
+    fir_t f1, f2[NVO_MAX_CH], f3[NVO_MAX_CH];
+    nco_t nco[NVO_MAX_CH];
+    nvo_decoder dec[NVO_MAX_CH];
+    nvo_bsm bsm[NVO_MAX_CH];
+    long n3[NVO_MAX_CH];
+    bytes_t y1, y2[NVO_MAX_CH], y3[NVO_MAX_CH], bits[NVO_MAX_CH], bitpos[NVO_MAX_CH], disc[NVO_MAX_CH], pickm[NVO_MAX_CH];
     msg_t *msgs; size_t n_msgs, cap_msgs;
 };
 
@@ -505,8 +506,9 @@ nvo_chain *nvo_new(const nvo_params *prm) {
     nvo_chain *c = (nvo_chain *)calloc(1, sizeof *c);
     if (prm) c->prm = *prm; else nvo_default_params(&c->prm);
     const nvo_params *p = &c->prm;
+    c->nch = p->n_channels > 0 && p->n_channels <= NVO_MAX_CH ? p->n_channels : 2;
     fir_init(&c->f1, p->h1 ? p->h1 : k_h1, p->h1 ? p->n1 : NVX_T1, NVX_D1, 4096);
-    for (int ch = 0; ch < 2; ++ch) {
+    for (int ch = 0; ch < c->nch; ++ch) {
         fir_init(&c->f2[ch], p->h2 ? p->h2 : k_h2, p->h2 ? p->n2 : NVX_T2, NVX_D2, 1024);
         fir_init(&c->f3[ch], p->h3 ? p->h3 : k_h3, p->h3 ? p->n3 : NVX_T3, NVX_D3, 1024);
         nco_init(&c->nco[ch], p->nco_hz[ch], p->nco_period[ch]);
@@ -519,7 +521,7 @@ nvo_chain *nvo_new(const nvo_params *prm) {
 void nvo_free(nvo_chain *c) {
     if (!c) return;
     fir_free(&c->f1);
-    for (int ch = 0; ch < 2; ++ch) {
+    for (int ch = 0; ch < c->nch; ++ch) {
         fir_free(&c->f2[ch]); fir_free(&c->f3[ch]); nco_free(&c->nco[ch]);
         regfree(&c->bsm[ch].re_som); regfree(&c->bsm[ch].re_eom);
         free(c->bsm[ch].events.p);
@@ -535,7 +537,7 @@ static void chain_sample(nvo_chain *c, double xi, double xq) {
     double ai, aq;
     if (!fir_push(&c->f1, xi, xq, &ai, &aq)) return;
     if (c->prm.record_taps) bytes_add_2d(&c->y1, ai, aq);
-    for (int ch = 0; ch < 2; ++ch) {
+    for (int ch = 0; ch < c->nch; ++ch) {
         /* ref: fir2cpp.C:115-124 */
         nco_t *n = &c->nco[ch];
         double re = n->re[n->at], im = n->im[n->at];

@@ -11,7 +11,7 @@
  * portable checker on the GPU box.
  *
  * PARITY PINNING: the reference ships no tests / golden vectors (SURVEY.md 4,
- * 8c).  This restatement is pinned by EXECUTION: tests/test_oracle_vs_ref.py
+ * 8c).  This restatement is pinned by EXECUTION: tests/test_oracle.py
  * runs the unmodified reference (oracle/_ref/ref_chain) and this library on the
  * same inputs and requires exact FP64 equality of every stage tap, exact bit
  * strings and exact messages; tests/golden/ holds fixtures generated from
@@ -27,18 +27,22 @@ extern "C" {
 #endif
 
 typedef struct nvo_chain nvo_chain;
+#define NVO_MAX_CH 8
 
 typedef struct {
     /* NULL taps = the reference's literal arrays (fir1cpp.C:10-49, fir2cpp.C:24-72, fir3cpp.h:17-89) */
     const double *h1; int n1;
     const double *h2; int n2;
     const double *h3; int n3;
-    /* channel 0 / 1 NCO shift in Hz at the 63 kHz rate; reference = +14000 ("518"), -14000 ("490") */
-    double nco_hz[2];
+    /* channel NCO shifts in Hz at the 63 kHz rate; reference = +14000 ("518"), -14000 ("490").  Channels beyond the
+     * reference's two (n_channels > 2: more channels of one capture sharing stage 1) repeat the per-channel
+     * half of fir2cpp.C:112-215 / nav_sched.C:10-16 with their own offset */
+    double nco_hz[NVO_MAX_CH];
     /* table period in 63 kHz samples; 0 = derive (9 for +-14 kHz, fir2cpp.C:12-14) */
-    int nco_period[2];
-    int freq_tag[2];          /* passed through to messages; reference 518 / 490 */
+    int nco_period[NVO_MAX_CH];
+    int freq_tag[NVO_MAX_CH]; /* passed through to messages; reference 518 / 490 */
     int record_taps;          /* keep y1/y2/y3 arrays (memory!) */
+    int n_channels;           /* 0 = 2 (the reference) */
 } nvo_params;
 
 void nvo_default_params(nvo_params *p);

@@ -15,6 +15,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libnavtex_oracle.so")
 REF_CHAIN = os.path.join(ORACLE_DIR, "_ref", "ref_chain")
 CHANNELS = ("518", "490")
+CHANNEL_KEYS = ("518", "490", "ch2", "ch3", "ch4", "ch5", "ch6", "ch7")     # result keys of channels 0 .. 7
 
 
 def build_oracle():
@@ -26,10 +27,11 @@ class Params(C.Structure):
         ("h1", C.POINTER(C.c_double)), ("n1", C.c_int),
         ("h2", C.POINTER(C.c_double)), ("n2", C.c_int),
         ("h3", C.POINTER(C.c_double)), ("n3", C.c_int),
-        ("nco_hz", C.c_double * 2),
-        ("nco_period", C.c_int * 2),
-        ("freq_tag", C.c_int * 2),
+        ("nco_hz", C.c_double * 8),
+        ("nco_period", C.c_int * 8),
+        ("freq_tag", C.c_int * 8),
         ("record_taps", C.c_int),
+        ("n_channels", C.c_int),
     ]
 
 
@@ -99,9 +101,12 @@ def run_oracle(iq, h1=None, h2=None, h3=None, nco_hz=(14000.0, -14000.0), nco_pe
             keep.append(arr)
             setattr(p, "h" + name, arr.ctypes.data_as(C.POINTER(C.c_double)))
             setattr(p, "n" + name, len(arr))
-    p.nco_hz[0], p.nco_hz[1] = nco_hz
-    p.nco_period[0], p.nco_period[1] = nco_period
-    p.freq_tag[0], p.freq_tag[1] = freq_tag
+    n_ch = len(nco_hz)
+    for k in range(n_ch):
+        p.nco_hz[k] = nco_hz[k]
+        p.nco_period[k] = nco_period[k] if k < len(nco_period) else 0
+        p.freq_tag[k] = freq_tag[k] if k < len(freq_tag) else 1000 + k
+    p.n_channels = n_ch
     p.record_taps = int(record_taps)
     ch = L.nvo_new(C.byref(p))
     iq = np.ascontiguousarray(iq)
@@ -116,7 +121,7 @@ def run_oracle(iq, h1=None, h2=None, h3=None, nco_hz=(14000.0, -14000.0), nco_pe
     r = Result()
     pd = C.POINTER(C.c_double)()
     r.y1 = _cplx(pd, L.nvo_y1(ch, C.byref(pd)))
-    for c, tag in enumerate(CHANNELS):
+    for c, tag in enumerate(CHANNEL_KEYS[:n_ch]):
         pd = C.POINTER(C.c_double)()
         r.y2[tag] = _cplx(pd, L.nvo_y2(ch, c, C.byref(pd)))
         pd = C.POINTER(C.c_double)()

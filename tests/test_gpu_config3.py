@@ -134,3 +134,73 @@ def test_snr_sweep_and_fading_match_oracle():
     # sanity of the sweep itself: strong levels decode verbatim, the weakest do not
     assert decoded >= 3 and decoded < len(meta)
     eng.close()
+
+
+# ---- more than two channels of one capture sharing stage 1 ------------------------------------------------
+def _multi_capture(plan, seconds, snr, seed):
+    """One capture carrying one emission per (offset, text) of plan -- 490 / 518 and neighbours on the same band."""
+    ems = [synth.Emission(text, off, start_s=0.2 + 0.15 * k, n_phasing=18, n_tail=5, amplitude=5000.0) for k, (off, text) in enumerate(plan)]
+    return synth.quantise_s16(synth.fsk_iq(ems, seconds, snr_db=snr, seed=seed))
+
+
+@pytest.mark.parametrize("n_ch,fmt", [(3, "s16"), (4, "f32"), (4, "s16"), (5, "f32"), (8, "s16"), (1, "f32")])
+def test_n_channels_share_stage_one_against_restated_oracle(n_ch, fmt):
+    """n_channels channels per capture: 518 / 490 plus neighbours, every channel carrying its own bulletin.  Stage 1 runs once per
+    pass (one pass up to four channels, two from five on), mix + stages 2 / 3 + demod + SITOR-B once per channel; the restated
+    oracle repeats the reference's per-channel half (fir2cpp.C:112-215, nav_sched.C:10-16) once per offset.  Same bar as
+    everywhere: 900 Hz samples within 1e-5 of the stream's peak, bits / events / messages exact on every occupied channel."""
+    offsets = [14000.0, -14000.0, 7000.0, -21000.0, 21000.5, -7000.5, 0.0, 28000.0][:n_ch]
+    tags = [518, 490, 511, 483, 525, 497, 504, 532][:n_ch]
+    seconds = 11.0
+    n = int(seconds * 252000)
+    rng = np.random.default_rng(100 + n_ch)
+    S = 3
+    iqs, want = [], []
+    for s in range(S):
+        texts = [synth.random_message(rng, n_lines=1, words_per_line=3) for _ in range(n_ch)]
+        # stream 2 leaves every second channel empty
+        plan = [(off, t[0]) for k, (off, t) in enumerate(zip(offsets, texts)) if not (s == 2 and k % 2)]
+        iqs.append(_multi_capture(plan, seconds, snr=2.0, seed=500 + 10 * n_ch + s))
+        want.append(sorted((tags[k], t[1], t[0]) for k, t in enumerate(texts) if not (s == 2 and k % 2)))
+    x = np.stack([iq.reshape(-1, 2) for iq in iqs])
+    if fmt == "f32":
+        x = x.astype(np.float32)
+    nco = np.tile(np.array(offsets), (S, 1))
+    tg = np.tile(np.array(tags), (S, 1))
+    eng = engine.Engine(S, n, keep_bits=True, nco_hz=nco, stream_freq_tag=tg, n_channels=n_ch)
+    eng.push_host(np.ascontiguousarray(x))
+    msgs = eng.poll_messages()
+    y3 = eng.read_y3()
+    assert y3.shape[:2] == (S, n_ch)
+    for s in range(S):
+        o = ol.run_oracle(iqs[s], nco_hz=tuple(offsets), freq_tag=tuple(tags))
+        keys = ol.CHANNEL_KEYS[:n_ch]
+        scale = max(np.abs(o.y3[k]).max() for k in keys)
+        for c, key in enumerate(keys):
+            err = np.abs(y3[s, c].astype(np.complex128) - o.y3[key]).max() / scale
+            assert err <= REL_TOL, (n_ch, s, key, err)
+            if not (s == 2 and c % 2):                         # occupied: every decision, every event
+                bits, _ = eng.read_bits(s, c)
+                assert bits == o.bits[key], (n_ch, s, key)
+            assert eng.read_events(s, c) == o.events[key], (n_ch, s, key)
+        assert sorted(o.messages) == want[s]
+        assert sorted(m[1:] for m in msgs if m[0] == s) == want[s]
+    # any blocking gives the same bits: exact integer NCO phase per channel, warm-up recomputed per segment
+    blk = 280 * 1000
+    eng2 = engine.Engine(S, blk, nco_hz=nco, stream_freq_tag=tg, n_channels=n_ch)
+    ys = []
+    for a in range(0, n - n % blk, blk):
+        eng2.push_host(np.ascontiguousarray(x[:, a:a + blk]))
+        ys.append(eng2.read_y3())
+    y = np.concatenate(ys, axis=2)
+    assert np.array_equal(y.view(np.uint64), y3[:, :, : y.shape[2]].view(np.uint64))
+    eng.close(); eng2.close()
+
+
+def test_n_channels_argument_errors():
+    with pytest.raises(engine.NvxError, match="nco_hz"):
+        engine.Engine(1, 2800, n_channels=3)                                         # no default offsets beyond the reference pair
+    with pytest.raises(engine.NvxError, match="n_channels"):
+        engine.Engine(1, 2800, n_channels=9, nco_hz=np.zeros((1, 9)))
+    with pytest.raises(engine.NvxError, match="reference tap class"):
+        engine.Engine(1, 2800, n_channels=3, nco_hz=np.zeros((1, 3)), taps=(np.ones(61) / 61, np.ones(75) / 75, np.ones(111) / 111))
