@@ -259,3 +259,40 @@ def test_two_engines_on_two_devices_in_one_process():
     assert np.array_equal(engs[0].read_y3().view(np.uint64), engs[1].read_y3().view(np.uint64))
     for e in engs:
         e.close()
+
+
+def test_pinned_host_pushes_fence_and_kernel_spans():
+    """nvx_pinned_alloc buffers (the e2e arm's input) give the same bits as a pageable push; nvx_engine_fence orders the engine's
+    main stream behind the demod stream; the per-launch kernel times are reported one per timed push."""
+    import torch
+
+    iq = cases.build("noisy490")
+    n = iq.size // 2 // 280 * 280 // 2
+    x = np.ascontiguousarray(iq[: 4 * n].reshape(1, 2 * n, 2))
+    ref = engine.Engine(1, n)
+    ys_ref = []
+    for k in range(2):
+        ref.push_host(np.ascontiguousarray(x[:, k * n:(k + 1) * n]))
+        ys_ref.append(ref.read_y3().copy())
+    msgs_ref = ref.poll_messages()
+    ref.close()
+    for wc in (False, True):
+        pin = engine.PinnedBuffer((2, 1, n, 2), np.int16, write_combined=wc)
+        pin.array[0], pin.array[1] = x[:, :n], x[:, n:]
+        eng = engine.Engine(1, n)
+        eng.enable_timing(1)
+        eng.stats()
+        es = torch.cuda.ExternalStream(eng.stream)
+        for k in range(2):
+            eng.push_host_ptr(pin.ptr + k * n * 4, n, s16=True)
+            eng.fence()
+            done = torch.cuda.Event()
+            done.record(es)
+            done.synchronize()                       # everything of block k, demod stream included, is over: its events are on the host
+            assert np.array_equal(eng.read_y3().view(np.uint64), ys_ref[k].view(np.uint64))
+        spans = eng.cascade_spans()
+        st = eng.stats()
+        assert len(spans) == 2 and abs(float(spans.sum()) - st.cascade_ms) < 1e-3 and st.cascade_ms_min <= st.cascade_ms_max
+        assert eng.poll_messages() == msgs_ref and len(msgs_ref) == 1
+        eng.close()
+        pin.close()
