@@ -723,16 +723,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                     // chunk c of B = copy c % kCopies of the band, moved up by whole atoms: the descriptors are those of the band's
                     // first rows plus the offset in their 16-byte address field (shared memory is far below its 14-bit range)
                     const uint32_t goff = (uint32_t)((a.chunks - 1) / kCopies - c / kCopies) * 1024 + (uint32_t)(c % kCopies) * (a.J * 128);
-                    const uint64_t dadd = goff >> 4;
+                    // The band is a parallelogram: the samples of chunk c only reach the outputs n with a tap index
+                    // D n + T - 1 - (chunk c + k) inside [0, T), i.e. n in [opc (c - lead), opc c + opc - 1] (opc = outputs per chunk);
+                    // every other row of the tile's B slice is all zero.  So the MMAs of a chunk only span those output columns,
+                    // rounded out to the instruction's N granularity of 16: D, the band rows and N move together.  Early and late
+                    // chunks of a window become N = 16 .. 48 instructions instead of 64: 37 % less tensor work at 255 taps, more
+                    // for shorter filters.  The first MMA of a tile still spans all 64 columns: it is the one that clears them.
+                    constexpr int kOpc = kCS / D;
+                    int n_lo = kOpc * (c - lead), n_hi = kOpc * c + kOpc - 1;
+                    n_lo = n_lo < 0 ? 0 : n_lo;
+                    n_hi = n_hi > N - 1 ? N - 1 : n_hi;
+                    const uint32_t off = (uint32_t)n_lo & ~15u, np = (((uint32_t)n_hi | 15u) + 1u) - off;
+                    const bool trim = !(a.dbg & 16);
+                    const uint32_t c_off = trim ? off : 0u;
+                    const uint32_t idesc_np = trim ? ((idesc & ~(0x3Fu << 17)) | ((np >> 3) << 17)) : idesc;
+                    const uint64_t dadd = (goff >> 4) + (uint64_t)c_off * 8;       // 16 rows of the band = two 1024-byte atoms
+                    const uint64_t dadd0 = goff >> 4;
                     if (leader) {
 #pragma unroll
                         for (int p = 0; p < 2; ++p)
 #pragma unroll
                             for (int term = 0; term < 3; ++term)        // x_hi h_hi, x_lo h_hi, x_hi h_lo
 #pragma unroll
-                                for (int k = 0; k < kKB / kUmmaK; ++k)
-                                    umma_ts_tf32(acc + p * N, at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
-                                                 (term == 2 ? dl0[k] : dh0[k]) + dadd, idesc, (c | term | k) ? 1u : 0u);
+                                for (int k = 0; k < kKB / kUmmaK; ++k) {
+                                    const bool clear = (c | term | k) == 0;         // c == 0: off == 0 anyway
+                                    umma_ts_tf32(acc + p * N + (clear ? 0u : c_off), at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
+                                                 (term == 2 ? dl0[k] : dh0[k]) + (clear ? dadd0 : dadd), clear ? idesc : idesc_np, clear ? 0u : 1u);
+                                }
                         if (c == a.chunks - 1) umma_commit(bar0 + 8 * (kBarTile + slot));
                     }
                     __syncwarp();
@@ -1122,6 +1139,7 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
         if (want && !d_trace) cudaMalloc(&d_trace, sizeof(long long) * kTraceChunks * kTraceCols);
         if (want) { cudaMemsetAsync(d_trace, 0, sizeof(long long) * kTraceChunks * kTraceCols, stream); a.trace = d_trace; }
         a.dbg = (tr && getenv("NVX_TC_DBG")) ? atoi(getenv("NVX_TC_DBG")) : 0;      // knock-out experiments: only together with the trace
+        if (getenv("NVX_TC_TRIM") && atoi(getenv("NVX_TC_TRIM")) == 0) a.dbg |= 16;  // A/B: full-width MMAs for every chunk (same results)
         const cudaError_t e = s->D == NVX_D1 ? launch_tcs<NVX_D1>(a, sms, stream) : launch_tcs<NVX_D2>(a, sms, stream);
         if (want && e == cudaSuccess && ++traced == 3) {
             static long long h[kTraceChunks * kTraceCols];
