@@ -618,7 +618,16 @@ def leg_config5(c, x, expect, taps_n, steps, warmup):
         except engine.NvxError:
             return 0.0           # the stage runs on CUDA cores
         tiles = -(-rows // 128) * -(-(n_in // D) // g["n_tile"])
-        return tiles * g["chunks"] * 24 * 2.0 * 128 * g["n_tile"] * 8 / 1e12
+        cs = 32 // D * D
+        cpt, lead = D * g["n_tile"] // cs, g["chunks"] - D * g["n_tile"] // cs
+        if g["n_tile"] == 64 and 0 <= lead <= cpt:        # streaming kernel: MMAs trimmed to the non-zero columns of the band, N = 16 .. 64
+            opc, cols = cs // D, 0
+            for c in range(g["chunks"]):
+                n_lo, n_hi = max(0, opc * (c - lead)), min(63, opc * c + opc - 1)
+                cols += ((n_hi | 15) + 1) - (n_lo & ~15)
+        else:
+            cols = g["chunks"] * g["n_tile"]
+        return tiles * cols * 24 * 2.0 * 128 * 8 / 1e12
     ex = executed_tflop(4, taps[0], S, BLOCK) + executed_tflop(7, taps[1], 2 * S, BLOCK // 4)
     return {
         "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
