@@ -346,6 +346,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
                 const uint32_t at = tmem + kACol0 + s * kSetCols;
                 // chunk c of B = copy c % kCopies of the band, moved up by whole atoms
                 const uint32_t goff = (uint32_t)((a.chunks - 1) / kCopies - c / kCopies) * 1024 + (uint32_t)(c % kCopies) * (a.J * 128);
+                // only the outputs n with a tap index D n + T - 1 - (chunk c + k) inside [0, T) see this chunk: the MMAs span those
+                // columns of the tile, rounded out to 16 (see fir_tcs_kernel); the first MMA of the tile clears all N columns
+                const int num = kCS * c - a.T + 1;
+                const int n_lo = num <= 0 ? 0 : (num + D - 1) / D;
+                int n_hi = (kCS * c + kCS - 1) / D;
+                n_hi = n_hi > N - 1 ? N - 1 : n_hi;
+                const bool trim = !(a.dbg & 16) && n_lo <= n_hi;
+                const uint32_t c_off = trim ? ((uint32_t)n_lo & ~15u) : 0u;
+                const uint32_t np = trim ? (((uint32_t)n_hi | 15u) + 1u) - c_off : (uint32_t)N;
+                const uint32_t idesc_np = (idesc & ~(0x3Fu << 17)) | ((np >> 3) << 17);
                 const uint32_t gh = s_u32(s_gh) + goff, gl = s_u32(s_gl) + goff;
                 if (leader) {
 #pragma unroll
@@ -353,9 +363,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int term = 0; term < 3; ++term)              // x_hi h_hi, x_lo h_hi, x_hi h_lo
 #pragma unroll
-                            for (int k = 0; k < kKB / kUmmaK; ++k)
-                                umma_ts_tf32(acc + p * N, at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
-                                             umma_desc((term == 2 ? gl : gh) + k * kUmmaK * 4), idesc, (c | term | k) ? 1u : 0u);
+                            for (int k = 0; k < kKB / kUmmaK; ++k) {
+                                const bool clear = (c | term | k) == 0;
+                                umma_ts_tf32(acc + p * N + (clear ? 0u : c_off), at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
+                                             umma_desc((term == 2 ? gl : gh) + (clear ? 0u : c_off * 128u) + k * kUmmaK * 4),
+                                             clear ? idesc : idesc_np, clear ? 0u : 1u);
+                            }
                     umma_commit(bar0 + 8 * (kBarAEmpty + s));
                     if (c == a.chunks - 1) umma_commit(bar0 + 8 * kBarTile);
                 }
@@ -1157,6 +1170,7 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
         }
         return e;
     }
+    if (getenv("NVX_TC_TRIM") && atoi(getenv("NVX_TC_TRIM")) == 0) a.dbg |= 16;
     if (s->D == NVX_D1)
         return s->N == 128 ? launch_tc<NVX_D1, 128>(a, sms, stream)
                            : s->N == 64 ? launch_tc<NVX_D1, 64>(a, sms, stream) : launch_tc<NVX_D1, 32>(a, sms, stream);
