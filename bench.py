@@ -232,6 +232,9 @@ def ref_binary():
     return None
 
 
+RATES = []      # Msamples/s of every timed wave-pass of the last run_reference_cpu calls (the host is a noisy VM: spread matters)
+
+
 def run_reference_cpu(samples_i16, passes_warm, passes_timed, cores, pin_core=None):
     """Time the unmodified reference chain: one process (= one stream: its state is global) per core, `cores` at a time,
     until every stream of the sample has been through; passes back to back on the same in-memory capture.  A pass of a wave
@@ -258,8 +261,10 @@ def run_reference_cpu(samples_i16, passes_warm, passes_timed, cores, pin_core=No
                                       stderr=subprocess.PIPE, text=True, preexec_fn=pre(k)) for k, p in enumerate(wave)]
             outs = [p.communicate()[1] for p in procs]
             per_pass = [json.loads(o.strip().splitlines()[-1])["pass_s"][passes_warm:] for o in outs]
-            wave_s += sum(max(pp[k] for pp in per_pass) for k in range(passes_timed))
+            wave_pass = [max(pp[k] for pp in per_pass) for k in range(passes_timed)]
+            wave_s += sum(wave_pass)
             total += len(wave) * n * passes_timed
+            RATES.extend(len(wave) * n / t / 1e6 for t in wave_pass)
     waves = (len(paths) + cores - 1) // cores
     return total / wave_s, wave_s / (waves * passes_timed), n
 
@@ -271,6 +276,7 @@ def cpu_reference_figures(sample, warm, timed):
     if ref_binary():
         one = sorted(os.sched_getaffinity(0))[0]
         sps1, _, n = run_reference_cpu(sample[:4], 1, max(3, timed // 2), 1, pin_core=one)
+        del RATES[:]
         sps, step_s, n = run_reference_cpu(sample, warm, timed, cores)
         kind, binary = "reference", os.path.relpath(ref_binary(), ROOT)
     else:   # the compiled reference did not travel: time the C port instead (single thread)
@@ -286,7 +292,8 @@ def cpu_reference_figures(sample, warm, timed):
             f"{cores} at a time, {warm} warm-up + {timed} timed passes each, a wave-pass ends with its slowest process")
     return {"value": sps / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": desc,
             "one_core_pinned_msamples_per_s": sps1 / 1e6, "nproc": os.cpu_count(), "cpu_model": cpu_model(), "binary": binary,
-            "streams_in_sample": len(sample), "samples_per_stream": n}, step_s
+            "streams_in_sample": len(sample), "samples_per_stream": n,
+            "wave_pass_msamples_per_s": {"min": min(RATES), "median": statistics.median(RATES), "max": max(RATES), "n": len(RATES)} if RATES else None}, step_s
 
 
 def reference_sample(np, synth, n_streams, seconds):
