@@ -275,7 +275,7 @@ def cpu_reference_figures(sample, warm, timed):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if ref_binary():
         one = sorted(os.sched_getaffinity(0))[0]
-        sps1, _, n = run_reference_cpu(sample[:4], 1, max(3, timed // 2), 1, pin_core=one)
+        sps1, _, n = run_reference_cpu(sample[:4], 1, timed, 1, pin_core=one)
         del RATES[:]
         sps, step_s, n = run_reference_cpu(sample, warm, timed, cores)
         kind, binary = "reference", os.path.relpath(ref_binary(), ROOT)
@@ -291,7 +291,8 @@ def cpu_reference_figures(sample, warm, timed):
     desc = (f"first {n / 252000:.1f} s of {len(sample)} of the workload's streams; one {os.path.basename(binary)} process per core, "
             f"{cores} at a time, {warm} warm-up + {timed} timed passes each, a wave-pass ends with its slowest process")
     return {"value": sps / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": desc,
-            "one_core_pinned_msamples_per_s": sps1 / 1e6, "nproc": os.cpu_count(), "cpu_model": cpu_model(), "binary": binary,
+            "one_core_pinned_msamples_per_s": sps1 / 1e6, "per_core_msamples_per_s": sps / 1e6 / max(1, cores),
+            "realtime_streams": sps / 252000.0, "nproc": os.cpu_count(), "cpu_model": cpu_model(), "binary": binary,
             "streams_in_sample": len(sample), "samples_per_stream": n,
             "wave_pass_msamples_per_s": {"min": min(RATES), "median": statistics.median(RATES), "max": max(RATES), "n": len(RATES)} if RATES else None}, step_s
 
