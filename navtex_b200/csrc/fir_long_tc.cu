@@ -710,67 +710,83 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
             dh0[k] = umma_desc(s_u32(s_gh) + k * kUmmaK * 4);
             dl0[k] = umma_desc(s_u32(s_gl) + k * kUmmaK * 4);
         }
+        // What one chunk contributes to one tile, worked out ahead of time (see below): chunk index c inside the tile's window,
+        // accumulator slot, and the trimmed extent of its MMAs.
+        // The band is a parallelogram: the samples of chunk c only reach the outputs n with a tap index D n + T - 1 - (chunk c + k)
+        // inside [0, T), i.e. n in [opc (c - lead), opc c + opc - 1] (opc = outputs per chunk); every other row of the tile's B
+        // slice is all zero.  So the MMAs of a chunk only span those output columns, rounded out to the instruction's N
+        // granularity of 16: D, the band rows and N move together.  Early and late chunks of a window become N = 16 .. 48
+        // instructions instead of 64: 37 % less tensor work at 255 taps, more for shorter filters.  The first MMA of a tile still
+        // spans all 64 columns: it is the one that clears them (its chunk has column offset 0 anyway).
+        struct Plan { uint32_t valid, c, slot, wait_par, d_off, idesc_np; uint64_t dadd; };
+        const bool trim = !(a.dbg & 16);
+        auto plan = [&](int r, int t1, int which, int q0_, int n_tiles) {
+            Plan p;
+            const int t = t1 + which;
+            const int c = which ? r + lead - cpt : r + lead;    // chunk index inside tile t's window, 0 .. chunks - 1
+            p.valid = !(c < 0 || t < 0 || t >= n_tiles);
+            const int q = q0_ + t;
+            p.c = (uint32_t)c;
+            p.slot = (uint32_t)(q & 1);
+            p.wait_par = (uint32_t)((q >> 1) & 1) ^ 1u;
+            // chunk c of B = copy c % kCopies of the band, moved up by whole atoms: the descriptors are those of the band's first
+            // rows plus the offset in their 16-byte address field (shared memory is far below its 14-bit range)
+            const uint32_t goff = (uint32_t)((a.chunks - 1) / kCopies - c / kCopies) * 1024 + (uint32_t)(c % kCopies) * (a.J * 128);
+            constexpr int kOpc = kCS / D;
+            int n_lo = kOpc * (c - lead), n_hi = kOpc * c + kOpc - 1;
+            n_lo = n_lo < 0 ? 0 : n_lo;
+            n_hi = n_hi > N - 1 ? N - 1 : n_hi;
+            const uint32_t off = trim ? ((uint32_t)n_lo & ~15u) : 0u;
+            const uint32_t np = trim ? (((uint32_t)n_hi | 15u) + 1u) - off : (uint32_t)N;
+            p.d_off = p.slot * kSlotCols + off;
+            p.idesc_np = (idesc & ~(0x3Fu << 17)) | ((np >> 3) << 17);
+            p.dadd = (goff >> 4) + (uint64_t)off * 8;           // 16 rows of the band = two 1024-byte atoms
+            return p;
+        };
+        auto issue = [&](const Plan& p, uint32_t at) {
+            if (p.c == 0) {                                     // first chunk of the tile: its accumulator slot must have been dumped
+                bar_wait(bar0 + 8 * (kBarTmemFree + p.slot), p.wait_par);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+            }
+            if (leader) {
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                    for (int term = 0; term < 3; ++term)        // x_hi h_hi, x_lo h_hi, x_hi h_lo
+#pragma unroll
+                        for (int k = 0; k < kKB / kUmmaK; ++k) {
+                            const bool clear = (p.c | (uint32_t)term | (uint32_t)k) == 0;     // c == 0: column offset 0
+                            umma_ts_tf32(tmem + p.d_off + pl * N, at + (2 * pl + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
+                                         (term == 2 ? dl0[k] : dh0[k]) + p.dadd, clear ? idesc : p.idesc_np, clear ? 0u : 1u);
+                        }
+                if (p.c == (uint32_t)(a.chunks - 1)) umma_commit(bar0 + 8 * (kBarTile + p.slot));
+            }
+            __syncwarp();
+        };
         NVX_FOR_SEGMENTS({
             // chunk G = cpt t1 + r: t1 is the tile that is finishing (its chunk index r + lead), t1 + 1 starts once r + lead >= cpt
             int r = lead ? cpt - lead : 0;
             int t1 = lead ? -1 : 0;                         // relative to ta
             const int n_tiles = (int)(tb - ta);
             const int n_chunks = cpt * n_tiles + lead;
+            // The contributions of chunk j + 1 are planned BETWEEN the two MMA batches of chunk j: the issuing thread's integer
+            // work (~300 cycles of dependent uniform-datapath instructions per chunk) then runs while the tensor core still has
+            // the first batch queued, instead of leaving it idle between chunks.
+            Plan pa = plan(r, t1, 0, q0, n_tiles), pb = plan(r, t1, 1, q0, n_tiles);
             for (int j = 0; j < n_chunks; ++j, ++gi) {
                 bar_wait(bar0 + 8 * (kBarAFull + s), ph);
                 NVX_TRACE(0, gi);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t at = tmem + kACol0 + s * kSetCols;
-#pragma unroll 1
-                for (int which = 0; which < 2; ++which) {
-                    const int t = t1 + which;
-                    const int c = which ? r + lead - cpt : r + lead;     // chunk index inside tile t's window, 0 .. chunks - 1
-                    if (c < 0 || t < 0 || t >= n_tiles) continue;
-                    const int q = q0 + t;
-                    const uint32_t slot = (uint32_t)(q & 1);
-                    if (c == 0) {                                       // first chunk of the tile: its accumulator slot must have been dumped
-                        bar_wait(bar0 + 8 * (kBarTmemFree + slot), (uint32_t)((q >> 1) & 1) ^ 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;");
-                    }
-                    const uint32_t acc = tmem + slot * kSlotCols;
-                    // chunk c of B = copy c % kCopies of the band, moved up by whole atoms: the descriptors are those of the band's
-                    // first rows plus the offset in their 16-byte address field (shared memory is far below its 14-bit range)
-                    const uint32_t goff = (uint32_t)((a.chunks - 1) / kCopies - c / kCopies) * 1024 + (uint32_t)(c % kCopies) * (a.J * 128);
-                    // The band is a parallelogram: the samples of chunk c only reach the outputs n with a tap index
-                    // D n + T - 1 - (chunk c + k) inside [0, T), i.e. n in [opc (c - lead), opc c + opc - 1] (opc = outputs per chunk);
-                    // every other row of the tile's B slice is all zero.  So the MMAs of a chunk only span those output columns,
-                    // rounded out to the instruction's N granularity of 16: D, the band rows and N move together.  Early and late
-                    // chunks of a window become N = 16 .. 48 instructions instead of 64: 37 % less tensor work at 255 taps, more
-                    // for shorter filters.  The first MMA of a tile still spans all 64 columns: it is the one that clears them.
-                    constexpr int kOpc = kCS / D;
-                    int n_lo = kOpc * (c - lead), n_hi = kOpc * c + kOpc - 1;
-                    n_lo = n_lo < 0 ? 0 : n_lo;
-                    n_hi = n_hi > N - 1 ? N - 1 : n_hi;
-                    const uint32_t off = (uint32_t)n_lo & ~15u, np = (((uint32_t)n_hi | 15u) + 1u) - off;
-                    const bool trim = !(a.dbg & 16);
-                    const uint32_t c_off = trim ? off : 0u;
-                    const uint32_t idesc_np = trim ? ((idesc & ~(0x3Fu << 17)) | ((np >> 3) << 17)) : idesc;
-                    const uint64_t dadd = (goff >> 4) + (uint64_t)c_off * 8;       // 16 rows of the band = two 1024-byte atoms
-                    const uint64_t dadd0 = goff >> 4;
-                    if (leader) {
-#pragma unroll
-                        for (int p = 0; p < 2; ++p)
-#pragma unroll
-                            for (int term = 0; term < 3; ++term)        // x_hi h_hi, x_lo h_hi, x_hi h_lo
-#pragma unroll
-                                for (int k = 0; k < kKB / kUmmaK; ++k) {
-                                    const bool clear = (c | term | k) == 0;         // c == 0: off == 0 anyway
-                                    umma_ts_tf32(acc + p * N + (clear ? 0u : c_off), at + (2 * p + (term == 1 ? 1 : 0)) * 32 + k * kUmmaK,
-                                                 (term == 2 ? dl0[k] : dh0[k]) + (clear ? dadd0 : dadd), clear ? idesc : idesc_np, clear ? 0u : 1u);
-                                }
-                        if (c == a.chunks - 1) umma_commit(bar0 + 8 * (kBarTile + slot));
-                    }
-                    __syncwarp();
-                }
+                if (pa.valid) issue(pa, at);
+                int r2 = r + 1, t2 = t1;
+                if (r2 == cpt) { r2 = 0; ++t2; }
+                const Plan na = plan(r2, t2, 0, q0, n_tiles), nb = plan(r2, t2, 1, q0, n_tiles);
+                if (pb.valid) issue(pb, at);
                 if (leader) umma_commit(bar0 + 8 * (kBarAEmpty + s));
                 NVX_TRACE(1, gi);
                 if (++s == kSets) { s = 0; ph ^= 1; }
-                if (++r == cpt) { r = 0; ++t1; }
+                r = r2; t1 = t2; pa = na; pb = nb;
             }
             q0 += n_tiles;
         })
