@@ -106,6 +106,8 @@ int nvx_engine_reset(nvx_engine *e);
 int nvx_engine_push_host_f32(nvx_engine *e, const float *iq, long long n);
 int nvx_engine_push_host_s16(nvx_engine *e, const int16_t *iq, long long n);   /* SDRplay / WAV sample format */
 int nvx_engine_wait_ingest(nvx_engine *e);                                      /* every host buffer pushed so far has been read */
+long long nvx_engine_host_pushes(nvx_engine *e);                                /* host pushes made so far (the next one has this index) */
+int nvx_engine_wait_ingest_of(nvx_engine *e, long long push_index);             /* the buffer of that host push (0-based) has been read */
 /* device-resident float2 block [S][n], 16-byte aligned; processed in place, asynchronously on the
  * engine's stream (ordered after everything previously queued on it) */
 int nvx_engine_push_device_f32(nvx_engine *e, const void *d_iq, long long n);

@@ -39,6 +39,7 @@ struct nvx_capture {
     // [S][n] staging, stream-major: two page-locked buffers (nvx_pinned_alloc), so that the engine's H2D copy of pump k is
     // asynchronous and overlaps the ring drain of pump k + 1
     int16_t* block[2] = {nullptr, nullptr};
+    long long block_push[2] = {-1, -1};    // index of the engine host push that last read each buffer
     unsigned pumps = 0;
     std::thread poller;
     std::atomic<bool> stop{false};
@@ -56,9 +57,12 @@ long long pump_locked(nvx_capture* c) {
     }
     n -= n % NVX_BLOCK_ALIGN;
     if (n <= 0) return 0;
-    int16_t* const blk = c->block[c->pumps++ & 1];
-    // the copy that last read this buffer was queued two pumps ago; make sure it is over before the buffer is refilled
-    if (const int rc = nvx_engine_wait_ingest(c->eng)) return rc;
+    const unsigned which = c->pumps++ & 1;
+    int16_t* const blk = c->block[which];
+    // the copy that last read this buffer was queued two pumps ago; make sure it is over before the buffer is refilled (the copy
+    // of the previous pump, out of the other buffer, keeps running meanwhile)
+    if (c->block_push[which] >= 0)
+        if (const int rc = nvx_engine_wait_ingest_of(c->eng, c->block_push[which])) return rc;
     for (int s = 0; s < c->S; ++s) {
         auto& r = c->rings[(size_t)s];
         int16_t* dst = blk + (size_t)s * 2 * (size_t)n;
@@ -70,8 +74,9 @@ long long pump_locked(nvx_capture* c) {
         std::lock_guard<std::mutex> lk(r.mu);
         r.tail += n;
     }
+    c->block_push[which] = nvx_engine_host_pushes(c->eng);
     const int rc = nvx_engine_push_host_s16(c->eng, blk, n);
-    if (rc != 0) return rc;
+    if (rc != 0) { c->block_push[which] = -1; return rc; }
     return n;
 }
 }  // namespace

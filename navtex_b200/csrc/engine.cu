@@ -801,6 +801,18 @@ int nvx_engine_wait_ingest(nvx_engine* e) {
     return 0;
 }
 
+long long nvx_engine_host_pushes(nvx_engine* e) { return e ? e->host_pushes : NVX_ERR_ARG; }
+
+int nvx_engine_wait_ingest_of(nvx_engine* e, long long push_index) {
+    if (!e || push_index < 0) return fail(NVX_ERR_ARG, "bad argument");
+    if (push_index >= e->host_pushes) return fail(NVX_ERR_ARG, "host push %lld has not been made yet (%lld so far)", push_index, e->host_pushes);
+    // copies run in order on one stream into two alternating staging slots: pushes older than the last two are necessarily over
+    if (push_index < e->host_pushes - 2) return 0;
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaEventSynchronize(e->copy_done[push_index % 2]));
+    return 0;
+}
+
 int nvx_engine_sync(nvx_engine* e) {
     if (!e) return fail(NVX_ERR_ARG, "null engine");
     return sync_engine(e);

@@ -34,8 +34,9 @@ __device__ __forceinline__ int slot(int f) { return f + f / (kLongR * D); }
 // grid (tiles, input rows).  STAGE 0 (the first stage) writes TWO output rows per input row: its 63 kHz outputs rotated by
 // each channel's NCO (fir2cpp.C:112-128), so that the second stage is a plain FIR over channel rows.
 template <int D, int STAGE>
-__global__ void __launch_bounds__(kLongThreads) fir_long_kernel(const LongArgs a, const int J, const long long in_pitch,
-                                                                const __grid_constant__ LongStageTaps tp) {
+__global__ void __launch_bounds__(long_threads(D)) fir_long_kernel(const LongArgs a, const int J, const long long in_pitch,
+                                                                   const __grid_constant__ LongStageTaps tp) {
+    constexpr int kLongThreads = long_threads(D), kLongTile = long_tile(D);
     extern __shared__ __align__(16) float2 s_x[];
     const int H = D * J;
     const int F = D * (kLongTile + J - 1);                    // inputs staged per tile
@@ -171,6 +172,7 @@ __global__ void long_carry_kernel(const float2* __restrict__ old_hist, const Sam
 
 template <int D, int STAGE>
 cudaError_t launch_one(const LongArgs& a, const LongStage& st, const LongStageTaps& tp, long long in_pitch, cudaStream_t stream) {
+    constexpr int kLongThreads = long_threads(D), kLongTile = long_tile(D);
     const int F = D * (kLongTile + st.J - 1);
     const size_t smem = (size_t)(F + F / (kLongR * D) + 2) * sizeof(float2);
     {   // per device: not cached

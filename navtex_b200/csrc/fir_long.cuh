@@ -27,8 +27,11 @@
 namespace nvx {
 
 constexpr int kLongR = 8;                       // outputs per thread
-constexpr int kLongThreads = 128;
-constexpr int kLongTile = kLongR * kLongThreads;   // outputs per CTA
+// threads per CTA (each owns kLongR outputs).  The tile a CTA stages is D (tile + J - 1) samples: at D = 10 a 1024-output tile is
+// 84 KB of shared memory, two CTAs = 8 warps per SM, and the kernel ran at 42 % FMA-pipe activity for lack of warps; 64 threads
+// (512 outputs, 43 KB) put five CTAs on an SM and also waste less on the ragged last tile of a 9250-output row.
+__host__ __device__ constexpr int long_threads(int D) { return D == NVX_D3 ? 64 : 128; }
+__host__ __device__ constexpr int long_tile(int D) { return kLongR * long_threads(D); }   // outputs per CTA
 constexpr int kLongMaxTaps = 1024;              // per stage
 
 struct LongStage {

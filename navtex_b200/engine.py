@@ -50,7 +50,7 @@ class SynthDesc(C.Structure):
 EXPORTS = (
     "nvx_default_config", "nvx_last_error", "nvx_engine_create", "nvx_engine_destroy", "nvx_engine_reset",
     "nvx_engine_push_host_f32", "nvx_engine_push_host_s16", "nvx_engine_push_device_f32", "nvx_engine_push_device_s16",
-    "nvx_engine_sync", "nvx_engine_wait_ingest", "nvx_engine_poll_messages", "nvx_engine_try_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
+    "nvx_engine_sync", "nvx_engine_wait_ingest", "nvx_engine_host_pushes", "nvx_engine_wait_ingest_of", "nvx_engine_poll_messages", "nvx_engine_try_poll_messages", "nvx_engine_set_message_callback", "nvx_engine_read_y3",
     "nvx_engine_read_bits", "nvx_engine_read_events", "nvx_engine_enable_timing", "nvx_engine_get_stats",
     "nvx_engine_stream", "nvx_engine_get_cascade_spans", "nvx_engine_fence", "nvx_pinned_alloc", "nvx_pinned_free", "nvx_synth_fill_device", "nvx_host_assemble", "nvx_debug_long_tc_band",
     "nvx_capture_create", "nvx_capture_destroy", "nvx_capture_write", "nvx_capture_pump", "nvx_capture_start", "nvx_capture_stop",
@@ -83,6 +83,9 @@ def load_library():
     L.nvx_engine_poll_messages.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Message)), C.POINTER(C.c_size_t)]
     L.nvx_engine_try_poll_messages.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Message)), C.POINTER(C.c_size_t)]
     L.nvx_engine_wait_ingest.argtypes = [C.c_void_p]
+    L.nvx_engine_host_pushes.argtypes = [C.c_void_p]
+    L.nvx_engine_host_pushes.restype = C.c_longlong
+    L.nvx_engine_wait_ingest_of.argtypes = [C.c_void_p, C.c_longlong]
     L.nvx_engine_read_y3.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.nvx_engine_read_bits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.nvx_engine_read_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
