@@ -122,16 +122,20 @@ __device__ __forceinline__ void fsm_byte(FsmState& s, Emit& e, int b) {
     }
 }
 
-// receive_bit, nav_b_sm.C:266-634.  is_y: 'Y' (=1) else 'B'.
-__device__ __forceinline__ void fsm_bit(FsmState& s, Emit& e, bool is_y) {
-    if (s.enabled) {
-        s.shift = ((s.shift << 1) | (is_y ? 1 : 0)) & 0x7f;
-        if (++s.nbits == 7) {
-            fsm_byte(s, e, s.shift);
-            s.nbits = 0;
-            s.shift = 0;
-        }
-    }
+// receive_bit, nav_b_sm.C:266-634, in two halves so that the lanes of a warp (32 channels with 32 different byte phases) can meet
+// at the expensive one.  First half (:269-286): shift the bit in; true = this bit completes a 7-bit byte, which the caller must
+// hand to fsm_byte() BEFORE the second half of the same bit.  is_y: 'Y' (=1) else 'B'.
+__device__ __forceinline__ bool fsm_bit_shift(FsmState& s, bool is_y, int& byte) {
+    if (!s.enabled) return false;
+    s.shift = ((s.shift << 1) | (is_y ? 1 : 0)) & 0x7f;
+    if (++s.nbits < 7) return false;
+    byte = s.shift;
+    s.nbits = 0;
+    s.shift = 0;
+    return true;
+}
+// second half (:288-633): detector hold-off and the 30-bit phasing pattern
+__device__ __forceinline__ void fsm_bit_phasing(FsmState& s, bool is_y) {
     if (s.holdoff != 0) { s.holdoff--; return; }
     // 30-bit phasing pattern BBBBBB YYYY BB YY BBBBBB YYYY BB YY BB, bit k of the mask = 1 for 'Y'
     // positions of 'Y': 6-9, 12-13, 20-23, 26-27
@@ -471,7 +475,48 @@ __global__ void __launch_bounds__(kSeqWarps * 32) fsm_kernel(const DemodArgs a) 
         const int c1 = min(nb_max, c0 + kSeqChunk);
         stage_rows(rows, a.b.bitval, pitch_b(a.b.p_max), ch0, a.channels, c0, c1 - c0, lane);
         const int mine = min(nb, c1);
-        for (int k = c0; k < mine; ++k) fsm_bit(s, em, my_row[k - c0] != 0);
+        // The lane's row of the chunk (one byte per bit) is packed into eight 32-bit words first -- 64 independent loads instead of
+        // one dependent byte load per bit -- and written back over the front of its own row.
+        {
+            uint32_t pk[kSeqChunk / 32];
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(my_row);
+#pragma unroll
+            for (int w = 0; w < kSeqChunk / 32; ++w) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4)      // four bytes holding 0 / 1 -> four bits
+                    acc |= ((((rw[w * 8 + q4] & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q4);
+                pk[w] = acc;
+            }
+            uint32_t* ww = reinterpret_cast<uint32_t*>(rows + lane * kSeqPitch);
+#pragma unroll
+            for (int w = 0; w < kSeqChunk / 32; ++w) ww[w] = pk[w];
+        }
+        const uint32_t* wrow = reinterpret_cast<const uint32_t*>(my_row);
+        // Every lane runs through at most seven of its bits, stopping at (the first half of) the one that completes a byte; then
+        // the whole warp does receive_rxdx_byte together and finishes that bit.  After the first round the byte phases of the 32
+        // channels of a warp are aligned, so the expensive byte path runs once per seven bits instead of at every bit.
+        int k = c0;
+        uint32_t word = k < mine ? wrow[0] : 0u;
+        for (;;) {
+            int byte = 0;
+            bool pending = false, y = false;
+#pragma unroll 1
+            for (int i = 0; i < 7 && k < mine; ++i) {
+                y = (word & 1u) != 0;
+                word >>= 1;
+                ++k;
+                if (((k - c0) & 31) == 0) word = wrow[(k - c0) >> 5];      // (index 8 at the end of a full chunk: the row's pad word)
+                pending = fsm_bit_shift(s, y, byte);
+                if (pending) break;
+                fsm_bit_phasing(s, y);
+            }
+            if (pending) {
+                fsm_byte(s, em, byte);
+                fsm_bit_phasing(s, y);
+            }
+            if (!__any_sync(0xffffffffu, k < mine)) break;       // every lane has used up the chunk
+        }
     }
     if (!live) return;
     a.b.fsm[ch] = s;
