@@ -61,14 +61,15 @@ def test_single_block_against_oracle_and_golden(batch):
     eng.push_host(x)
     msgs = eng.poll_messages()
     for k, nm in enumerate(names):
-        occupied = {"clean518": ["518"], "noisy490": ["490"], "weak518": ["518"], "dropout": ["518"], "noise": ["518", "490"]}[nm]
+        occupied = {"clean518": ["518"], "noisy490": ["490"], "weak518": ["518"], "dropout": ["518"], "noise": ["518", "490"],
+                    "both": ["518", "490"], "figures": ["490"], "twice": ["518"]}[nm]
         _check_stream(eng, k, oracle[k], occupied, where="golden case " + nm)
         want = [(k, f, b, t) for f, b, t in oracle[k].messages]
         assert [m for m in msgs if m[0] == k] == want
         g = np.load(os.path.join(GOLDEN, nm + ".npz"))
         gold = [(k, int(f), str(b), str(t)) for f, b, t in zip(g["msg_freq"], g["msg_bbbb"], g["msg_text"])]
         assert [m for m in msgs if m[0] == k] == gold               # the reference's own add_message calls
-    assert sum(len(o.messages) for o in oracle) == len(msgs) == 3
+    assert sum(len(o.messages) for o in oracle) == len(msgs) == 8
     eng.close()
 
 
