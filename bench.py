@@ -348,6 +348,30 @@ def allreduce_sum(c, values):
     return [int(round(v)) for v in t.tolist()]
 
 
+def verify_all_ranks(c, msgs, expect, steps):
+    """Every rank checks ITS OWN bulletins (how many of the expected ones came out verbatim; whether the multiset of what came
+    out is exactly `steps` copies of each expected one: nothing missing, nothing extra, nothing garbled); rank 0 additionally
+    gathers every rank's messages and expectations -- the job's only cross-rank data exchange, untimed -- and compares the
+    gathered multiset with the union.  Returns (exact count, multiset flag, rank-0 check record)."""
+    from navtex_b200 import sharding
+
+    decoded_ok, got = count_exact(msgs, expect)
+    multiset_ok = int(got == collections.Counter({e: steps for e in expect}))
+    check = {"bulletins_expected_per_step_per_gpu": len(expect), "decoded_exact_rank0": decoded_ok}
+    merged = sharding.gather_messages(msgs)
+    all_expect = [None] * c.world if c.rank == 0 else None
+    if c.world > 1:
+        c.dist.gather_object(expect, all_expect, dst=0)
+    else:
+        all_expect = [expect]
+    if c.rank == 0:
+        want = collections.Counter({e: steps for ex in all_expect for e in ex})
+        have = collections.Counter((m[0], m[1], m[2], m[3]) for m in merged)
+        check["messages_gathered_all_ranks"] = len(merged)
+        check["gathered_multiset_equals_union_of_expected"] = bool(want == have)
+    return decoded_ok, multiset_ok, check
+
+
 def timed_pushes(c, eng, ptr, n, steps, warmup, s16=False, reset=False):
     """warmup untimed pushes, then exactly `steps` pushes of the resident block bracketed by barrier + synchronize; device time
     by CUDA events on the engine's stream, max over ranks.  Returns (ms, stats, messages of the timed pushes, clocks, spans)."""
@@ -779,23 +803,9 @@ def main():
     eng.poll_messages()
     eng.close()
     # correctness of what was timed: each pass over the block re-decodes every stream's bulletin.  EVERY rank checks its own.
-    decoded_ok, got = count_exact(msgs, expect)
-    multiset_ok = int(got == collections.Counter({e: args.steps for e in expect}))      # nothing missing, nothing extra, nothing garbled
     total_samples = world * S * BLOCK * args.steps
     value = total_samples / (max_ms * 1e-3) / 1e6                     # Msamples/s
-    check = {"bulletins_expected_per_step_per_gpu": len(expect), "decoded_exact_rank0": decoded_ok}
-    # the only cross-rank data exchange of the job: final host gather of the decoded message records (untimed)
-    merged = sharding.gather_messages(msgs)
-    all_expect = [None] * world if rank == 0 else None
-    if world > 1:
-        dist.gather_object(expect, all_expect, dst=0)
-    else:
-        all_expect = [expect]
-    if rank == 0:
-        want = collections.Counter({e: args.steps for ex in all_expect for e in ex})
-        have = collections.Counter((m[0], m[1], m[2], m[3]) for m in merged)
-        check["messages_gathered_all_ranks"] = len(merged)
-        check["gathered_multiset_equals_union_of_expected"] = bool(want == have)
+    decoded_ok, multiset_ok, check = verify_all_ranks(c, msgs, expect, args.steps)
 
     # ---- same-run parity against the unmodified reference (rank 0's streams) ----------------------
     oracle_parity = None

@@ -66,3 +66,53 @@ def test_two_rank_gloo_gather_matches_single_process():
     single = sorted(decode_streams(0, len(NAMES)), key=lambda m: m[0])
     assert merged == single
     assert [m[2] for m in merged] == ["PA12", "QB07", "MK33", "PA12"]      # clean518 twice, dropout's partial message
+
+
+def _bench_check_main(rank, world, port, q):
+    """bench.py's all-rank verification (every rank checks its own bulletins, counts are summed, rank 0 compares the gathered
+    multiset with the union) under gloo: rank 1 loses one of its messages in the second case."""
+    import collections
+
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = bench.Ctx()
+    c.torch, c.dist, c.rank, c.world, c.device = torch, dist, rank, world, torch.device("cpu")
+    steps = 3
+    expect = [(rank * 4 + s, 518 if s % 2 == 0 else 490, "AB%02d" % (rank * 4 + s), "ZCZC AB%02d\nTEXT %d\nNNNN\n" % (rank * 4 + s, s)) for s in range(4)]
+    out = []
+    for drop in (False, True):
+        msgs = [e for _ in range(steps) for e in expect]
+        if drop and rank == 1:
+            msgs = msgs[:-1]
+        ok, multiset, check = bench.verify_all_ranks(c, msgs, expect, steps)
+        sums = bench.allreduce_sum(c, [ok, len(expect), multiset])
+        out.append((sums, check))
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_all_rank_verification_two_gloo_ranks():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bench_check_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    (sums_ok, check_ok), (sums_bad, check_bad) = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sums_ok == [8, 8, 2] and check_ok["gathered_multiset_equals_union_of_expected"] and check_ok["messages_gathered_all_ranks"] == 24
+    # one message missing on rank 1: every bulletin was still seen at least once, but that rank's multiset and the gathered one are off
+    assert sums_bad == [8, 8, 1] and not check_bad["gathered_multiset_equals_union_of_expected"] and check_bad["messages_gathered_all_ranks"] == 23
