@@ -73,7 +73,8 @@ constexpr int kMaxSlots = 8;
 constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 NP + 4] floats (row pitch = 4 words mod 32: conflict-free)
 // NP: outputs dumped per epilogue pass.  Stage 2 (D = 7) dumps 32 at a time: its two band copies leave little shared memory, and
 // two more raw-input slots are worth more than a one-pass epilogue
-__host__ __device__ constexpr int dump_outputs(int D, int N) { return D == NVX_D2 ? 32 : (N > 64 ? 64 : N); }
+// (the same holds for the streaming kernel with three live tiles, L = 3, whose band is long)
+__host__ __device__ constexpr int dump_outputs(int D, int N, int L = 2) { return (D == NVX_D2 || L == 3) ? 32 : (N > 64 ? 64 : N); }
 constexpr int kSmemLimit = 227 * 1024;
 // A K chunk is 32 columns holding the largest whole number of outputs' worth of samples: D = 4: 32 samples = 8 outputs; D = 7:
 // 28 samples = 4 outputs and 4 zero columns.  The band matrix moves 8 / 4 rows per chunk; descriptors can only move in whole
@@ -166,9 +167,9 @@ enum {
     kBarRawEmpty = kBarRawFull + kMaxSlots,
     kBarAFull = kBarRawEmpty + kMaxSlots,
     kBarAEmpty = kBarAFull + kMaxSets,
-    kBarTile = kBarAEmpty + kMaxSets,      // (streaming kernel: one per accumulator slot)
-    kBarTmemFree = kBarTile + 2,
-    kBars = kBarTmemFree + 2
+    kBarTile = kBarAEmpty + kMaxSets,      // (streaming kernel: one per accumulator slot, up to three)
+    kBarTmemFree = kBarTile + 3,
+    kBars = kBarTmemFree + 3
 };
 
 // round to TF32 (10-bit mantissa, nearest, ties away) with integer ops; the remainder is exact in FP32
@@ -554,15 +555,19 @@ constexpr int kTraceChunks = 96, kTraceCols = 8;
         if (a.trace && blockIdx.x == 0 && (idx) < kTraceChunks && lane == 0) a.trace[(idx) * kTraceCols + (col)] = clock64(); \
     } while (0)
 
-template <int D>
+// L = live tiles = accumulator slots: 2 while a window spans at most two tiles (lead <= cpt: two A sets), 3 up to three tiles
+// (cpt < lead <= 2 cpt, i.e. up to 516 taps at D = 4: the third slot takes the place of the second A set, so conversion and MMAs
+// of consecutive chunks no longer overlap -- still far ahead of loading and converting every window three times).
+template <int D, int L>
 __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_constant__ TcArgs a) {
     constexpr int N = kSN;
     constexpr int kCS = chunk_samples(D);
     constexpr int kCopies = band_copies(D);
-    constexpr int kSets = 2;
-    constexpr uint32_t kACol0 = 512 - kSets * kSetCols;      // 256: above the two accumulator slots
     constexpr uint32_t kSlotCols = 2 * N;
-    constexpr int NP = dump_outputs(D, N);
+    constexpr int kSets = (512 - L * (int)kSlotCols) / (int)kSetCols;
+    constexpr uint32_t kACol0 = L * kSlotCols;               // the A sets sit above the accumulator slots
+    static_assert(kSets >= 1 && L >= 2 && L <= 3, "tensor memory budget");
+    constexpr int NP = dump_outputs(D, N, L);
     constexpr int kDumpPitch = 2 * NP + kDumpPad;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int g_bytes = kCopies * a.J * 128;
@@ -723,12 +728,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
         auto plan = [&](int r, int t1, int which, int q0_, int n_tiles) {
             Plan p;
             const int t = t1 + which;
-            const int c = which ? r + lead - cpt : r + lead;    // chunk index inside tile t's window, 0 .. chunks - 1
+            const int c = r + lead - which * cpt;               // chunk index inside tile t's window, 0 .. chunks - 1
             p.valid = !(c < 0 || t < 0 || t >= n_tiles);
-            const int q = q0_ + t;
+            const int q = q0_ + (t < 0 ? 0 : t);
             p.c = (uint32_t)c;
-            p.slot = (uint32_t)(q & 1);
-            p.wait_par = (uint32_t)((q >> 1) & 1) ^ 1u;
+            p.slot = (uint32_t)(q % L);
+            p.wait_par = (uint32_t)((q / L) & 1) ^ 1u;
             // chunk c of B = copy c % kCopies of the band, moved up by whole atoms: the descriptors are those of the band's first
             // rows plus the offset in their 16-byte address field (shared memory is far below its 14-bit range)
             const uint32_t goff = (uint32_t)((a.chunks - 1) / kCopies - c / kCopies) * 1024 + (uint32_t)(c % kCopies) * (a.J * 128);
@@ -765,28 +770,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
         };
         NVX_FOR_SEGMENTS({
             // chunk G = cpt t1 + r: t1 is the tile that is finishing (its chunk index r + lead), t1 + 1 starts once r + lead >= cpt
-            int r = lead ? cpt - lead : 0;
-            int t1 = lead ? -1 : 0;                         // relative to ta
+            const int back = (lead + cpt - 1) / cpt;        // whole tiles the first chunk of the segment lies before tile ta
+            int r = back * cpt - lead;
+            int t1 = -back;                                 // relative to ta
             const int n_tiles = (int)(tb - ta);
             const int n_chunks = cpt * n_tiles + lead;
-            // The contributions of chunk j + 1 are planned BETWEEN the two MMA batches of chunk j: the issuing thread's integer
+            // The contributions of chunk j + 1 are planned BETWEEN the MMA batches of chunk j: the issuing thread's integer
             // work (~300 cycles of dependent uniform-datapath instructions per chunk) then runs while the tensor core still has
             // the first batch queued, instead of leaving it idle between chunks.
-            Plan pa = plan(r, t1, 0, q0, n_tiles), pb = plan(r, t1, 1, q0, n_tiles);
+            Plan pl[L];
+#pragma unroll
+            for (int w = 0; w < L; ++w) pl[w] = plan(r, t1, w, q0, n_tiles);
             for (int j = 0; j < n_chunks; ++j, ++gi) {
                 bar_wait(bar0 + 8 * (kBarAFull + s), ph);
                 NVX_TRACE(0, gi);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t at = tmem + kACol0 + s * kSetCols;
-                if (pa.valid) issue(pa, at);
+                if (pl[0].valid) issue(pl[0], at);
                 int r2 = r + 1, t2 = t1;
                 if (r2 == cpt) { r2 = 0; ++t2; }
-                const Plan na = plan(r2, t2, 0, q0, n_tiles), nb = plan(r2, t2, 1, q0, n_tiles);
-                if (pb.valid) issue(pb, at);
+                Plan nx[L];
+#pragma unroll
+                for (int w = 0; w < L; ++w) nx[w] = plan(r2, t2, w, q0, n_tiles);
+#pragma unroll
+                for (int w = 1; w < L; ++w)
+                    if (pl[w].valid) issue(pl[w], at);
                 if (leader) umma_commit(bar0 + 8 * (kBarAEmpty + s));
                 NVX_TRACE(1, gi);
                 if (++s == kSets) { s = 0; ph ^= 1; }
-                r = r2; t1 = t2; pa = na; pb = nb;
+                r = r2; t1 = t2;
+#pragma unroll
+                for (int w = 0; w < L; ++w) pl[w] = nx[w];
             }
             q0 += n_tiles;
         })
@@ -870,10 +884,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
         long long tq = 0;                                   // tiles handled so far (all segments)
         NVX_FOR_SEGMENTS({
             for (long long t = ta; t < tb; ++t, ++tq) {
-                const uint32_t slot = (uint32_t)(tq & 1);
+                const uint32_t slot = (uint32_t)(tq % L);
                 const long long n0 = t * N;
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * kSlotCols;
-                bar_wait(bar0 + 8 * (kBarTile + slot), (uint32_t)((tq >> 1) & 1));
+                bar_wait(bar0 + 8 * (kBarTile + slot), (uint32_t)((tq / L) & 1));
                 if (q == 0) NVX_TRACE(6, tq);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int row0 = rb * kRows + q * 32;
@@ -972,8 +986,8 @@ int tcs_cpt(int D) { return D * kSN / chunk_samples(D); }
 int tcs_lead(int D, int T_taps) { return T_taps <= D ? 0 : (T_taps - D + chunk_samples(D) - 1) / chunk_samples(D); }
 // rows of one copy of the band matrix: N plus one 8-row atom per further (group of) chunk(s)
 int tc_band_rows(int D, int N, int T) { return N + 8 * ((tc_chunks(D, N, T) - 1) / band_copies(D)); }
-size_t tc_smem(int D, int N, int T, int slots) {
-    return (size_t)2 * band_copies(D) * tc_band_rows(D, N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * dump_outputs(D, N) + kDumpPad) * 4 + 128 +
+size_t tc_smem(int D, int N, int T, int slots, int L = 2) {
+    return (size_t)2 * band_copies(D) * tc_band_rows(D, N, T) * 128 + (size_t)slots * kSlotBytes + (size_t)kRows * (2 * dump_outputs(D, N, L) + kDumpPad) * 4 + 128 +
            kBars * 8 + 16;
 }
 int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 rows, dividing J
@@ -982,20 +996,20 @@ int tc_box_rows(int J) {                   // whole swizzle atoms, at most 256 r
         if ((J / 8) % d == 0) best = d;
     return 8 * best;
 }
-int tc_slots(int D, int N, int T) {        // raw-input slots that fit beside the band matrix: even, >= 4 (0: the stage does not fit)
+int tc_slots(int D, int N, int T, int L = 2) {        // raw-input slots that fit beside the band matrix: even, >= 4 (0: the stage does not fit)
     for (int slots = kMaxSlots; slots >= 4; slots -= 2)
-        if (tc_smem(D, N, T, slots) <= (size_t)kSmemLimit) return slots;
+        if (tc_smem(D, N, T, slots, L) <= (size_t)kSmemLimit) return slots;
     return 0;
 }
 
-template <int D>
+template <int D, int L>
 cudaError_t launch_tcs(TcArgs& a, int sms, cudaStream_t stream) {
-    a.slots = tc_slots(D, kSN, a.T);
-    const size_t smem = tc_smem(D, kSN, a.T, a.slots);
-    cudaError_t e = cudaFuncSetAttribute(fir_tcs_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    a.slots = tc_slots(D, kSN, a.T, L);
+    const size_t smem = tc_smem(D, kSN, a.T, a.slots, L);
+    cudaError_t e = cudaFuncSetAttribute(fir_tcs_kernel<D, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long grid = a.work < sms ? a.work : sms;
-    fir_tcs_kernel<D><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
+    fir_tcs_kernel<D, L><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -1026,13 +1040,14 @@ int long_tc_tile(int D, int T) {
     return 0;
 }
 
-// the streaming kernel serves a stage when a window spans at most two tiles (lead <= chunks per tile) and its band fits;
+// the streaming kernel serves a stage when a window spans at most three tiles (lead <= 2 x chunks per tile) and its band fits;
 // NVX_TC_STREAM=0 keeps the tile-at-a-time kernel (A/B measurements)
 bool tcs_applies(int D, int T_taps) {
     if (D != NVX_D1 && D != NVX_D2) return false;
     if (getenv("NVX_TC_STREAM") && atoi(getenv("NVX_TC_STREAM")) == 0) return false;
     const int lead = tcs_lead(D, T_taps);
-    return lead <= tcs_cpt(D) && tc_slots(D, kSN, D + lead * chunk_samples(D)) > 0;
+    const int max_lead = (getenv("NVX_TC_LIVE") && atoi(getenv("NVX_TC_LIVE")) == 2 ? 1 : 2) * tcs_cpt(D);      // two or three live tiles
+    return lead <= max_lead && tc_slots(D, kSN, D + lead * chunk_samples(D), lead > tcs_cpt(D) ? 3 : 2) > 0;
 }
 
 struct LongTcStage {
@@ -1169,7 +1184,9 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
         if (want) { cudaMemsetAsync(d_trace, 0, sizeof(long long) * kTraceChunks * kTraceCols, stream); a.trace = d_trace; }
         a.dbg = (tr && getenv("NVX_TC_DBG")) ? atoi(getenv("NVX_TC_DBG")) : 0;      // knock-out experiments: only together with the trace
         if (getenv("NVX_TC_TRIM") && atoi(getenv("NVX_TC_TRIM")) == 0) a.dbg |= 16;  // A/B: full-width MMAs for every chunk (same results)
-        const cudaError_t e = s->D == NVX_D1 ? launch_tcs<NVX_D1>(a, sms, stream) : launch_tcs<NVX_D2>(a, sms, stream);
+        const bool three = a.lead > a.cpt;
+        const cudaError_t e = s->D == NVX_D1 ? (three ? launch_tcs<NVX_D1, 3>(a, sms, stream) : launch_tcs<NVX_D1, 2>(a, sms, stream))
+                                             : (three ? launch_tcs<NVX_D2, 3>(a, sms, stream) : launch_tcs<NVX_D2, 2>(a, sms, stream));
         if (want && e == cudaSuccess && ++traced == 3) {
             static long long h[kTraceChunks * kTraceCols];
             cudaStreamSynchronize(stream);

@@ -31,7 +31,9 @@ def _capture(text, offset, seconds, snr, seed):
 
 # (255, ...), (101, ...), (37, 47, 500): long-tap path; (61, 75, 111), (45, 47, 90): the fused kernel's medium class;
 # (21, 31, 51): shorter than the reference, zero-padded into the reference class
-@pytest.mark.parametrize("lengths", [(255, 255, 255), (101, 383, 129), (37, 47, 500), (61, 75, 111), (45, 47, 90), (21, 31, 51)])
+# (383, 511, 71) and (516, 900, 71): streaming kernel with three live tiles in both stages / tile-at-a-time stage 2
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (101, 383, 129), (37, 47, 500), (61, 75, 111), (45, 47, 90), (21, 31, 51), (383, 511, 71),
+                                     (516, 900, 71)])
 def test_long_taps_against_restated_oracle(lengths):
     taps = designs(*lengths)
     seconds = 11.0
@@ -75,7 +77,7 @@ def test_long_taps_cuda_core_stage1(cuda_core_stage1, lengths):
     test_long_taps_against_restated_oracle(lengths)
 
 
-@pytest.mark.parametrize("lengths", [(255, 255, 255), (127, 255, 90), (511, 255, 255), (1000, 47, 71)])
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (127, 255, 90), (511, 255, 255), (511, 511, 90), (1000, 47, 71)])
 def test_long_taps_tensor_core_stage1(monkeypatch, lengths):
     """tcgen05 3xTF32 Toeplitz GEMM for stage 1 (the default; 1000 taps loads the band matrix in many TMA boxes): same 1e-5 bar as the
     oracle tests above; here a ragged stream count (130 = one full 128-row tile + 2), float input, and blockings that move the

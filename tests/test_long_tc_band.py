@@ -22,7 +22,7 @@ def test_band_gemm_equals_the_decimating_fir(D, T):
     cs = 32 // D * D                                            # samples per chunk
     cpt = D * N // cs                                           # chunks a tile advances by
     lead = -(-(T - D) // cs)
-    if lead <= cpt and N == 64:                                 # streaming kernel: windows are whole chunks of one global grid
+    if lead <= 2 * cpt and N == 64:                             # streaming kernel (two or three live tiles): windows are whole chunks of one global grid
         assert Tp == D + lead * cs and chunks == cpt + lead and chunks * cs == D * (N - 1) + Tp
     else:                                                       # tile-at-a-time kernel: windows start on whole 32-byte sectors
         assert (D - Tp) % 4 == 0 and T <= Tp < T + 4
@@ -58,7 +58,9 @@ def test_band_is_refused_where_the_kernel_does_not_apply():
     geo, _, _ = engine.long_tc_band(4, np.ones(1000))
     assert geo["n_tile"] == 64
     geo, _, _ = engine.long_tc_band(4, np.ones(511))
-    assert geo["n_tile"] == 128                                 # stage 1 from 384 taps on while the band fits
+    assert geo["n_tile"] == 64 and geo["taps_padded"] == 516 and geo["chunks"] == 24       # streaming with three live tiles: 8 + 16 chunks
+    geo, _, _ = engine.long_tc_band(4, np.ones(540))
+    assert geo["n_tile"] == 128                                 # beyond 516 taps: tile at a time, N = 128 while the band fits (to 548)
     geo, _, _ = engine.long_tc_band(4, np.ones(255))
     assert geo["n_tile"] == 64 and geo["taps_padded"] == 260 and geo["chunks"] == 16      # streaming: 8 + 8 chunks of 32 samples
     geo, _, _ = engine.long_tc_band(7, np.ones(255))
