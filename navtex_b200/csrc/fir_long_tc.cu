@@ -21,25 +21,32 @@
 // in tensor memory -- the converters write it with tcgen05.st -- and shared memory only serves the band matrix reads, the
 // ring of raw input and the epilogue's dump.
 //
+// Two kernels share the machinery below.  fir_tcs_kernel<D, L> ("streaming", the default up to 516 taps at D = 4 and 903 at D = 7)
+// cuts the input into one global grid of chunks and multiplies every chunk, loaded and converted ONCE, into the two or three tiles
+// whose windows contain it (L live accumulator slots in tensor memory); its MMAs are trimmed to the non-zero columns of the band
+// parallelogram and the issuer plans the next chunk between the batches of the current one -- see the comment above it.
+// fir_tc_kernel<D, N> ("tile at a time") loads and converts each tile's whole window and serves the longer tap sets.
+//
 // One CTA = 16 warps, persistent over a contiguous range of (row block, output tile) work items:
-//   * warp 9 (one thread, TMA) and warps 10..11 (cp.async loaders): stream the raw input window of each tile through a
-//     ring of [128 rows x 128 B] slots, alternating chunks between one 2-D TMA box per slot (SWIZZLE_128B; D = 4 only) and
-//     16-byte cp.async copies written in the same XOR-swizzled layout, both completing on the slot's mbarrier; the swizzle
-//     lets a thread read ITS row conflict-free, and rows past the last stream / samples past the block end are zero-filled.
-//     (One 1-D bulk copy per row was measured at ~63 cycles of the TMA unit each, whatever its size: 2.8x slower end to
-//     end.)  Tiles that touch the carried history skip the copies and the converters call the general loader instead; the
-//     ring protocol is the same;
+//   * warp 9 (one thread, TMA) and warps 10..11 (cp.async loaders): stream the raw input through a ring of [128 rows x 128 B]
+//     slots, alternating chunks between one 2-D TMA box per slot (SWIZZLE_128B) and 16-byte cp.async copies written in the same
+//     XOR-swizzled layout, both completing on the slot's mbarrier; the swizzle lets a thread read ITS row conflict-free, and rows
+//     past the last stream / samples past the block end are zero-filled.  (One 1-D bulk copy per row was measured at ~63 cycles
+//     of the TMA unit each, whatever its size: 2.8x slower end to end.)  Chunks that lie in the carried history skip the copies
+//     and the converters call the general loader instead; the ring protocol is the same;
 //   * warps 0..7, converters: thread = row (TMEM lane) x half of the chunk; reads its 16 samples from the slot,
 //     de-interleaves I and Q, splits them into TF32 high and low parts and writes the four A tiles (I_hi, I_lo, Q_hi, Q_lo;
 //     32 columns each) of one of the A sets into tensor memory with tcgen05.st;
 //   * warp 8, issuer: the whole warp runs the loop, one elect.sync-elected lane issues the 2 planes x 3 terms x 4 k-steps
-//     tcgen05.mma.kind::tf32 (A in TMEM, B = band matrix in shared memory) per chunk and commits them to the A set's empty
-//     barrier; the last chunk of a tile also commits to the tile barrier.  (Issued from an "if (lane == 0)" branch, ptxas
-//     wraps every MMA in an R2UR waterfall loop -- ~80 cycles per MMA, which bounded the first versions of this kernel.);
-//   * warps 12..15, epilogue: dump the tile's accumulator columns to shared memory (tcgen05.ld, lane = row; 64 outputs per
-//     pass) and release the accumulators, then, lane = output, apply the NCO rotation of both channels (stage 1,
-//     fir2cpp.C:112-128) and store 256 contiguous bytes per instruction.
-// TMEM map (512 columns): [0, 2 N) accumulators (I | Q), A sets of 4 x 32 columns at the top: three at N <= 64, two at N = 128.
+//     tcgen05.mma.kind::tf32 (A in TMEM, B = band matrix in shared memory) per chunk and tile and commits them to the A set's
+//     empty barrier; the last chunk of a tile also commits to the tile barrier.  (Issued from an "if (lane == 0)" branch, ptxas
+//     wraps every MMA in an R2UR waterfall loop -- ~80 cycles per MMA, which bounded the first versions of this kernel; 64-bit
+//     divisions and per-MMA descriptor arithmetic on this thread bounded the next ones: everything it does per chunk is
+//     incremental 32-bit arithmetic now.);
+//   * warps 12..15, epilogue: dump the tile's accumulator columns to shared memory (tcgen05.ld, lane = row) and release the
+//     accumulators, then, lane = output, apply the NCO rotation of both channels (stage 1, fir2cpp.C:112-128) and store 256
+//     contiguous bytes per instruction.
+// TMEM map (512 columns): accumulators (I | Q per tile) at the bottom, A sets of 4 x 32 columns above them.
 // The accumulation order inside the tensor core is fixed per tile position, so results are deterministic for a given
 // blocking but not bit-identical across blockings (tile boundaries move); the tests hold this path to the 1e-5 bar.
 #include <cuda.h>
