@@ -411,7 +411,7 @@ def span_stats(spans):
     return {"kernel_ms_min": float(min(spans)), "kernel_ms_median": float(statistics.median(map(float, spans))), "kernel_ms_max": float(max(spans))}
 
 
-def leg_oracle_parity(c, x, expect):
+def leg_oracle_parity(c, x, expect, n_streams=PARITY_STREAMS):
     """Same-run parity: PARITY_STREAMS of this rank's streams, the full 10.28 s, through the UNMODIFIED
     reference (oracle/_ref/ref_chain --out: stage taps by ld --wrap) on the host cores, against one more pass of the GPU chain
     over the resident block with the bit taps switched on.  Rank 0 only.  Messages, events-to-text and bit decisions of the
@@ -427,7 +427,8 @@ def leg_oracle_parity(c, x, expect):
     eng.push_device(x.data_ptr(), BLOCK)
     msgs = eng.poll_messages()
     y3 = eng.read_y3()
-    pick = list(range(0, S, S // PARITY_STREAMS))[:PARITY_STREAMS]
+    n_streams = max(1, min(S, n_streams))
+    pick = list(range(0, S, S // n_streams))[:n_streams]
     caps = [x[s].round().to(c.torch.int16).cpu().numpy().reshape(-1) for s in pick]
     use_ref = ol.have_ref()
     t0 = time.time()
@@ -721,6 +722,8 @@ def main():
     ap.add_argument("--taps", type=int, default=255, help="config5: taps per stage")
     ap.add_argument("--seconds", type=float, default=60.0, help="--workload config4: traffic per stream")
     ap.add_argument("--skip", default="", help="comma-separated legs to leave out of the default line: parity,int16,e2e,config4,config5,channels,cpu")
+    ap.add_argument("--parity-streams", type=int, default=PARITY_STREAMS,
+                    help="streams of the workload compared against the unmodified reference in the same run (check.oracle_parity); up to 1024")
     ap.add_argument("--pinned", default="nvx", choices=["nvx", "wc"], help="e2e host buffer: cudaHostAlloc portable (nvx) or write-combined (wc)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -810,7 +813,7 @@ def main():
     # ---- same-run parity against the unmodified reference (rank 0's streams) ----------------------
     oracle_parity = None
     if rank == 0 and "parity" not in skip:
-        oracle_parity = leg_oracle_parity(c, x, expect)
+        oracle_parity = leg_oracle_parity(c, x, expect, args.parity_streams)
     barrier()
 
     # ---- secondary: the same captures resident as int16 I,Q (the radio's own format), fused-ingest kernel variant ----
