@@ -146,6 +146,7 @@ struct nvx_engine {
     float2 *y1buf = nullptr, *y2buf = nullptr;
     int lcur = 0;
     nvx::LongTcStage* ltc[2] = {nullptr, nullptr};   // tensor-core variants of stages 1 and 2 (null: CUDA-core kernel)
+    bool mix_on_load = false;             // long path, reference NCO table, streaming tensor-core stage 2: stage 1 writes ONE un-mixed row per stream
     bool ltc_wanted[2] = {false, false};  // the tensor-core kernel was asked for (NVX_LONG_TC mask) for that stage
     nvx::LongStageTaps ltaps[3];          // this engine's long-path taps: passed in the parameter block of every stage launch
     std::vector<int> stream_tag;          // optional [S][2] message tags
@@ -447,6 +448,7 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         LongArgs la = {};
         la.in = d_x; la.hist = e->lhist[0][cur]; la.out = e->y1buf; la.n_in = n; la.out_pitch = p1; la.out_off = 0;
         la.rows_in = e->S; la.stage = 0; la.s16 = s16; la.k_abs = e->sb_abs * (kSuper / NVX_D1); la.nco = e->d_nco;
+        la.plain = e->mix_on_load;                 // stage 2 mixes while it loads: one un-mixed 63 kHz row per stream
         cudaError_t tc = e->ltc[0] ? long_tc_launch(e->ltc[0], la, e->lst[0], n, e->stream) : cudaErrorNotSupported;
         if (tc == cudaErrorNotSupported) {         // 252 k -> 63 k, mixed: one row per channel
             if (e->ltc_wanted[0]) note_tc_fallback(e, 1, e->ltc[0] ? "this block cannot be described to the TMA unit (pointer or pitch not 16-byte aligned)"
@@ -457,14 +459,18 @@ int process_block(nvx_engine* e, const void* d_x, long long n, bool s16) {
         CU_TRY(long_carry(e->lhist[0][cur], d_x, n, e->lhist[0][nx], e->S, e->lst[0].H, n, s16, e->stream));
         la.in = e->y1buf; la.hist = e->lhist[1][cur]; la.out = e->y2buf; la.n_in = n / NVX_D1; la.out_pitch = p2;
         la.rows_in = e->channels; la.stage = 1; la.s16 = 0; la.nco = nullptr;
+        la.plain = 0; la.mix_in = e->mix_on_load;   // (k_abs: the block's first stage-2 INPUT sample sits at that 63 kHz tick)
         tc = e->ltc[1] ? long_tc_launch(e->ltc[1], la, e->lst[1], p1, e->stream) : cudaErrorNotSupported;
+        if (tc == cudaErrorNotSupported && e->mix_on_load)      // (cannot happen: y1buf and its pitch are 16-byte aligned)
+            return fail(NVX_ERR_CUDA, "long-tap stage 2: the tensor-core kernel refused the block and the stage-1 output is un-mixed");
         if (tc == cudaErrorNotSupported) {         // 63 k -> 9 k
             if (e->ltc_wanted[1]) note_tc_fallback(e, 2, e->ltc[1] ? "this block cannot be described to the TMA unit (pointer or pitch not 16-byte aligned)"
                                                                     : "the tap set does not fit the tensor-core tile");
             tc = long_launch(la, e->lst[1], e->ltaps[1], p1, e->stream);
         }
         CU_TRY(tc);
-        CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->channels, e->lst[1].H, n / NVX_D1, 0, e->stream));
+        CU_TRY(long_carry(e->lhist[1][cur], e->y1buf, p1, e->lhist[1][nx], e->mix_on_load ? e->S : e->channels, e->lst[1].H, n / NVX_D1, 0, e->stream));
+        la.mix_in = 0;
         la.in = e->y2buf; la.hist = e->lhist[2][cur]; la.out = e->y3buf[b]; la.n_in = n / (NVX_D1 * NVX_D2);
         la.out_pitch = ca.y3_pitch; la.out_off = ca.y3_off; la.stage = 2;
         CU_TRY(long_launch(la, e->lst[2], e->ltaps[2], p2, e->stream));                // 9 k -> 900
@@ -733,6 +739,11 @@ int nvx_engine_create(const nvx_config* cfg, nvx_engine** out) {
             if (e->ltc_wanted[k] && !e->ltc[k])
                 fail(0, "note: long-tap stage %d (%d taps) is not served by the tensor-core kernel and runs on the CUDA-core kernel", k + 1, e->lst[k].T);
         CREATE_TRY(cudaMalloc(&e->y1buf, (size_t)e->channels * (cfg->max_block / NVX_D1) * sizeof(float2)));
+        // "mix on load": with the reference offsets (no per-stream NCO) and stage 2 on the streaming tensor-core kernel, stage 1
+        // writes one un-mixed 63 kHz row per stream and stage 2 rotates while it converts: y1 crosses HBM once per stream instead
+        // of once per channel, in both directions.  NVX_LONG_MIX=stage1 keeps the rotation in the stage-1 epilogue (A/B measurements).
+        e->mix_on_load = nco.empty() && nvx::long_tc_mixes_on_load(e->ltc[1]) && (cfg->max_block / NVX_D1) % 2 == 0 &&
+                         !(getenv("NVX_LONG_MIX") && !strcmp(getenv("NVX_LONG_MIX"), "stage1"));
         CREATE_TRY(cudaMalloc(&e->y2buf, (size_t)e->channels * (cfg->max_block / (NVX_D1 * NVX_D2)) * sizeof(float2)));
     } else {
         nvx::cascade_fill_taps(e->tap_class, cfg->h1, n[0], cfg->h2, n[1], cfg->h3, n[2], &e->taps);

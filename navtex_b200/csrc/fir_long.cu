@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(long_threads(D)) fir_long_kernel(const LongArg
             }
         }
     }
-    if (STAGE == 0) {
+    if (STAGE == 0 && !a.plain) {
         // NCO mix: output k sits at 63 kHz clock tick k_abs + k; channel c gets y1 * (cos - j sin)(2 pi tick f_c / 63000)
         float2* out0 = a.out + (size_t)(2 * row_in) * a.out_pitch + a.out_off + k0 + (long long)kLongR * t;
         float2* out1 = out0 + a.out_pitch;

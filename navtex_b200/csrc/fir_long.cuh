@@ -14,7 +14,8 @@
 //     taps of that phase (warp-uniform constant-bank operands) as packed FFMA2 on (I, Q): R * R FFMA2 per R loads;
 //   * the stage-1 kernel applies the NCO rotation of both channels in its epilogue (9-entry table of the reference or
 //     the exact per-stream phase of the general NCO) and writes one 63 kHz row per channel, so stages 2 and 3 are
-//     plain FIRs over channel rows.
+//     plain FIRs over channel rows -- unless stage 2 runs on the streaming tensor-core kernel with the reference table:
+//     then stage 1 writes ONE un-mixed row per stream and stage 2 rotates while it loads (LongArgs.plain / mix_in).
 // History between blocks is carried per stage (last H inputs of each row), not recomputed.
 #pragma once
 #include <cuda_runtime.h>
@@ -52,6 +53,11 @@ struct LongArgs {
     int s16;                  // stage 1 only: input block is short2
     long long k_abs;          // stage 1: absolute index of the block's first OUTPUT sample (63 kHz clock), for the NCO
     const NcoParam* nco;      // stage 1: per-stream general NCO or null (reference table)
+    // "mix on load" (reference NCO table only): stage 1 leaves its output un-mixed, ONE 63 kHz row per stream (plain = 1), and the
+    // tensor-core stage 2 applies the rotation of its row's channel while it converts the samples (mix_in = 1: the input has
+    // rows_in / 2 rows, k_abs is the absolute index of the block's first INPUT sample) -- the same FP32 products in the same order
+    // as the stage-1 epilogue, with half the y1 traffic on both sides
+    int plain, mix_in;
 };
 
 // taps of one stage regrouped per decimation phase + the reference NCO table: passed by value in the kernel parameter block
@@ -79,6 +85,7 @@ bool long_tc_band(int D, int T_taps, const double* h, TcBand* out);
 // builds the Toeplitz operand of one stage (D = 4 or 7, T taps) on the device; nullptr when the stage does not fit the kernel
 LongTcStage* long_tc_prepare(int D, int T, const double* h, cudaStream_t stream);
 void long_tc_free(LongTcStage* s);
+bool long_tc_mixes_on_load(const LongTcStage* s);      // stage 2 served by the streaming kernel: LongArgs.mix_in is available
 cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& a, const LongStage& st, long long in_pitch, cudaStream_t stream);
 
 }  // namespace nvx

@@ -44,8 +44,9 @@
 //     divisions and per-MMA descriptor arithmetic on this thread bounded the next ones: everything it does per chunk is
 //     incremental 32-bit arithmetic now.);
 //   * warps 12..15, epilogue: dump the tile's accumulator columns to shared memory (tcgen05.ld, lane = row) and release the
-//     accumulators, then, lane = output, apply the NCO rotation of both channels (stage 1, fir2cpp.C:112-128) and store 256
-//     contiguous bytes per instruction.
+//     accumulators, then, lane = output, apply the NCO rotation of both channels (stage 1 with per-stream offsets,
+//     fir2cpp.C:112-128) and store 256 contiguous bytes per instruction.  With the reference offsets the rotation moves into
+//     the stage-2 converters instead ("mix on load", kMixIn below): stage 1 stores one plain row per stream.
 // TMEM map (512 columns): accumulators (I | Q per tile) at the bottom, A sets of 4 x 32 columns above them.
 // The accumulation order inside the tensor core is fixed per tile position, so results are deterministic for a given
 // blocking but not bit-identical across blockings (tile boundaries move); the tests hold this path to the 1e-5 bar.
@@ -75,6 +76,8 @@ constexpr int kLoaderWarp0 = kConvWarps + 2;
 constexpr int kLoaderWarps = 2;
 constexpr int kEpiWarp0 = kLoaderWarp0 + kLoaderWarps;
 constexpr int kTcThreads = 32 * (kConvWarps + 2 + kLoaderWarps + 4);
+// streaming kernel: 4 kCW converter warps (kCW per TMEM lane quarter) + issuer + TMA + loaders + 4 epilogue warps
+__host__ __device__ constexpr int tcs_threads(int kCW) { return 32 * (4 * kCW + 2 + kLoaderWarps + 4); }
 constexpr int kSlotBytes = kRows * 128;    // one raw-input slot: [128 rows x 128 B]
 constexpr int kMaxSlots = 8;
 constexpr int kDumpPad = 4;                // epilogue dump: [128 rows][2 NP + 4] floats (row pitch = 4 words mod 32: conflict-free)
@@ -100,12 +103,13 @@ struct TcArgs {
     long long n_in, in_pitch, out_pitch, out_off, k_abs;
     const NcoParam* nco;
     int rows, s16, T, H, chunks, J, slots, box_rows, mix;
+    int rows_src;                          // rows of the input: rows, or rows / 2 stream rows when the stage mixes on load
     int cpt, lead;                         // streaming kernel: chunks per tile advance (D N / chunk samples), chunks a window leads its tile by
     long long* trace;                      // development aid (NVX_TC_TRACE): clock64 stamps of CTA 0's first chunks, else null
     int dbg;                               // development aid (NVX_TC_DBG bit mask): leave parts of the pipeline out to find the limiter (results are garbage)
     long long tiles_per_block;             // output tiles per row block
     long long work;                        // row blocks * tiles_per_block
-    float2 nco_tab[kNcoPeriod];            // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107
+    float2 nco_tab[kNcoPeriod + 16];       // (cos, -sin)(2 pi k 14000 / 63000), fir2cpp.C:104-107, continued periodically (mix on load)
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,9 +146,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
                    "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[16]) { tmem_st16(taddr, v); }
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // general loader for tiles that touch the carried history
 __device__ __noinline__ float2 tc_load(const TcArgs& a, int row, long long g) {
-    if (row >= a.rows || g >= a.n_in || g < -(long long)a.H) return make_float2(0.f, 0.f);   // (older than the history: only zero-padded taps reach there)
+    if (row >= a.rows_src || g >= a.n_in || g < -(long long)a.H) return make_float2(0.f, 0.f);   // (older than the history: only zero-padded taps reach there)
     if (g < 0) return a.hist[(size_t)row * a.H + (a.H + g)];
     if (a.s16) {
         const short2 v = static_cast<const short2*>(a.in)[(size_t)row * a.in_pitch + g];
@@ -183,6 +193,13 @@ enum {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
     lo = x - hi;
+}
+
+// one sample times the NCO rotation rot = (cos, -sin) of its tick, or its conjugate for the "490" channel (fir2cpp.C:115-124):
+// exactly the two FP32 operations per component of the stage-1 epilogues
+__device__ __forceinline__ float2 mix_sample(float2 y, float2 rot, bool conj) {
+    const float sn = conj ? -rot.y : rot.y;
+    return make_float2(__fmaf_rn(-y.y, sn, __fmul_rn(y.x, rot.x)), __fmaf_rn(y.x, sn, __fmul_rn(y.y, rot.x)));
 }
 
 template <int D, int N>
@@ -565,9 +582,23 @@ constexpr int kTraceChunks = 96, kTraceCols = 8;
 // L = live tiles = accumulator slots: 2 while a window spans at most two tiles (lead <= cpt: two A sets), 3 up to three tiles
 // (cpt < lead <= 2 cpt, i.e. up to 516 taps at D = 4: the third slot takes the place of the second A set, so conversion and MMAs
 // of consecutive chunks no longer overlap -- still far ahead of loading and converting every window three times).
-template <int D, int L>
-__global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_constant__ TcArgs a) {
+// kMixIn ("mix on load", stage 2 with the reference NCO table): the input is the UN-mixed stage-1 output, one row per stream; a
+// row block is 64 streams, CTA row r = stream (r & 63) of the block, channel r >> 6 (uniform per converter warp), and the converters
+// rotate every sample by its channel's NCO phase (fir2cpp.C:112-128: "518" by (cos, -sin), "490" by the conjugate) before the
+// TF32 split -- the same two FP32 operations per component as the stage-1 epilogue's mix, so the products are bit-identical,
+// while y1 crosses HBM once per stream instead of once per channel on both sides.
+// kCW: converter warps per TMEM lane quarter, each converting 32 / kCW samples of a chunk per row.  Two is what ships.  The
+// converters are a latency-bound chain of ~300 instructions per chunk and warp and set the chunk period of stage 2 (in-kernel
+// trace, 65 taps: 1 470 cycles per chunk against 963 with conversion, loads and epilogue knocked out), so four per quarter were
+// built and measured: 24 warps per CTA cap the kernel at 80 registers per thread, every role spills, and the whole chain is
+// SLOWER (65 taps: 332 -> 315 Gsamples/s with stage 2 on four, 286 with both stages; 255 taps: 288 -> 276 / 260).
+template <int D, int L, bool kMixIn = false, int kCW = 2>
+__global__ void __launch_bounds__(tcs_threads(kCW), 1) fir_tcs_kernel(const __grid_constant__ TcArgs a) {
     constexpr int N = kSN;
+    constexpr int kConvWarps = 4 * kCW, kIssuerWarp = kConvWarps, kTmaWarp = kConvWarps + 1, kLoaderWarp0 = kConvWarps + 2;
+    constexpr int kPer = kKB / kCW;                          // samples (A columns) per converter thread and chunk
+    constexpr int kInRows = kMixIn ? kRows / 2 : kRows;      // input rows per row block
+    static_assert(!kMixIn || chunk_samples(D) % kNcoPeriod == 1, "mix on load: a chunk advances the NCO phase index by one");
     constexpr int kCS = chunk_samples(D);
     constexpr int kCopies = band_copies(D);
     constexpr uint32_t kSlotCols = 2 * N;
@@ -587,7 +618,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars);
     const uint32_t bar0 = s_u32(bars);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const int slots_per_chunk = a.s16 ? 1 : 2;
+    // a chunk is one 128-byte piece per row (int16 input) or two (float2 input): two ring slots -- except when mixing on load, where
+    // a row block has only 64 input rows and both pieces share ONE slot (second piece at kHalfBytes), so the ring holds twice as
+    // many chunks and as many bytes in flight as the 128-row layout
+    const int pieces = a.s16 ? 1 : 2;
+    const int slots_per_chunk = kMixIn ? 1 : pieces;
+    constexpr int kHalfBytes = kInRows * 128;
     const int cpt = a.cpt, lead = a.lead;
 
     if (threadIdx.x == 0) {
@@ -641,6 +677,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                     if (++ring_at == ring_chunks) { ring_at = 0; ring_ph ^= 1; }
                     if (!mine) continue;
                     const bool fast = G >= 0 && !(a.dbg & 1);   // chunks before the block come from the carried history
+                    if (kMixIn) {
+                        const uint32_t full = bar0 + 8 * (kBarRawFull + slot);
+                        bar_wait(bar0 + 8 * (kBarRawEmpty + slot), ph ^ 1);
+                        if (fast) {
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(pieces * kHalfBytes) : "memory");
+                            for (int h = 0; h < pieces; ++h)
+                                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                             ::"r"(s_u32(s_raw + slot * kSlotBytes + h * kHalfBytes)), "l"(&a.map_x), "r"((int)(2 * (G * kCS + h * 16))),
+                                               "r"(rb * kInRows), "r"(full) : "memory");
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps - 1) : "memory");
+                        } else {
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps) : "memory");
+                        }
+                        continue;
+                    }
                     for (int h = 0; h < slots_per_chunk; ++h) {
                         const uint32_t full = bar0 + 8 * (kBarRawFull + slot + h);
                         bar_wait(bar0 + 8 * (kBarRawEmpty + slot + h), ph ^ 1);
@@ -649,9 +700,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                             // 28-sample chunk over-fetches 4 samples of the next chunk (the converters zero those columns); rows past
                             // the last stream and samples past the block end are zero-filled by the TMA unit
                             const int x0 = (int)(2 * (G * kCS + h * 16));
-                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(kSlotBytes) : "memory");
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(kInRows * 128) : "memory");
                             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                         ::"r"(s_u32(s_raw + (slot + h) * kSlotBytes)), "l"(&a.map_x), "r"(x0), "r"(rb * kRows), "r"(full) : "memory");
+                                         ::"r"(s_u32(s_raw + (slot + h) * kSlotBytes)), "l"(&a.map_x), "r"(x0), "r"(rb * kInRows), "r"(full) : "memory");
                             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps - 1) : "memory");
                         } else {
                             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(32 * kLoaderWarps) : "memory");
@@ -663,7 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
     } else if (warp >= kLoaderWarp0 && warp < kLoaderWarp0 + kLoaderWarps) {
         const int tid = (warp - kLoaderWarp0) * 32 + lane;
         constexpr int kLoaders = 32 * kLoaderWarps;
-        const int units = 8 * slots_per_chunk;
+        const int units = 8 * pieces;
         const int u16 = tid % units, r0 = tid / units, r_step = kLoaders / units;
         const int esz = a.s16 ? 4 : 8;
         const int per_piece = 16 / esz;
@@ -682,13 +733,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                 if (G >= 0 && !(a.dbg & 1)) {
                     const long long t = G * kCS + u16 * per_piece;
                     const bool t_ok = t + per_piece <= a.n_in && u16 * per_piece < kCS;
-                    const uint8_t* src = static_cast<const uint8_t*>(a.in) + ((size_t)(rb * kRows + r0) * a.in_pitch + t) * esz;
+                    const uint8_t* src = static_cast<const uint8_t*>(a.in) + ((size_t)(rb * kInRows + r0) * a.in_pitch + t) * esz;
                     const size_t src_step = (size_t)r_step * a.in_pitch * esz;
-                    const uint32_t dst0 = s_u32(s_raw + (slot + (u16 >> 3)) * kSlotBytes);
+                    const uint32_t dst0 = s_u32(s_raw + (kMixIn ? slot * kSlotBytes + (u16 >> 3) * kHalfBytes : (slot + (u16 >> 3)) * kSlotBytes));
 #pragma unroll 4
-                    for (int r = r0; r < kRows; r += r_step, src += src_step) {
+                    for (int r = r0; r < kInRows; r += r_step, src += src_step) {
                         const uint32_t dst = dst0 + r * 128 + (((u16 & 7) ^ (r & 7)) << 4);
-                        const int bytes = (t_ok && rb * kRows + r < a.rows) ? 16 : 0;
+                        const int bytes = (t_ok && rb * kInRows + r < a.rows_src) ? 16 : 0;
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(bytes ? src : static_cast<const uint8_t*>(a.in)), "r"(bytes) : "memory");
                     }
                     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * (kBarRawFull + slot)) : "memory");
@@ -812,26 +863,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
             q0 += n_tiles;
         })
     } else if (warp < kConvWarps) {
-        const int q = warp & 3, kh = warp >> 2;
+        const int q = warp & 3, kh = warp >> 2;              // TMEM lane quarter, column group of the chunk
         const int r = q * 32 + lane;
-        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + kACol0 + kh * 16;
-        int slot = a.s16 ? 0 : kh;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + kACol0 + kh * kPer;
+        // where this thread's kPer samples sit: float2 input = two 128-byte pieces of 16 samples per row (two slots, or -- mix on
+        // load -- two halves of one slot), int16 input = one piece of 32 samples
+        const int piece = a.s16 ? 0 : (kh * kPer) / 16;
+        const int in_piece = a.s16 ? kh * kPer : (kh * kPer) % 16;     // first sample inside the piece
+        int slot = kMixIn ? 0 : piece;
         uint32_t sph = 0, s = 0, ph = 0;
         int gi = 0;
+        const int r_in = r & (kInRows - 1);                  // this thread's input row inside the row block
+        const bool conj = kMixIn && q >= 2;                  // mix on load: rows 64..127 are the "490" channel (conjugate rotation)
         NVX_FOR_SEGMENTS({
+            // mix on load: phase index of this thread's first sample of the chunk in the periodically continued NCO table; the
+            // input sample at block index t sits at 63 kHz tick k_abs + t, and a chunk advances the phase by 28 mod 9 = 1
+            int p9 = 0;
+            if (kMixIn) {
+                const long long t0 = (a.k_abs + (cpt * ta - lead) * kCS + kh * kPer) % kNcoPeriod;
+                p9 = (int)(t0 < 0 ? t0 + kNcoPeriod : t0);
+            }
             for (long long G = cpt * ta - lead; G < cpt * tb; ++G, ++gi) {
                 bar_wait(bar0 + 8 * (kBarRawFull + slot), sph);
                 if (warp == 0) NVX_TRACE(2, gi);
-                const uint8_t* row = s_raw + slot * kSlotBytes + r * 128;
-                float ih[16], il[16], qh[16], ql[16];
+                const uint8_t* row = s_raw + slot * kSlotBytes + (kMixIn ? piece * kHalfBytes : 0) + r_in * 128;
+                float ih[kPer], il[kPer], qh[kPer], ql[kPer];
                 if (a.dbg & 2) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) ih[j] = il[j] = qh[j] = ql[j] = (float)gi;
+                    for (int j = 0; j < kPer; ++j) ih[j] = il[j] = qh[j] = ql[j] = (float)gi;
                 } else if (G >= 0) {
                     if (a.s16) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int4 v = *reinterpret_cast<const int4*>(row + (((4 * kh + u) ^ (r & 7)) << 4));
+                        for (int u = 0; u < kPer / 4; ++u) {
+                            const int4 v = *reinterpret_cast<const int4*>(row + (((in_piece / 4 + u) ^ (r & 7)) << 4));
                             const int wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -841,9 +905,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                         }
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            float4 v = *reinterpret_cast<const float4*>(row + ((u ^ (r & 7)) << 4));
-                            if (kCS != kKB && kh * 16 + 2 * u >= kCS) v = make_float4(0.f, 0.f, 0.f, 0.f);     // zero columns
+                        for (int u = 0; u < kPer / 2; ++u) {
+                            float4 v = *reinterpret_cast<const float4*>(row + (((in_piece / 2 + u) ^ (r & 7)) << 4));
+                            if (kCS != kKB && kh * kPer + 2 * u >= kCS) v = make_float4(0.f, 0.f, 0.f, 0.f);     // zero columns
+                            if (kMixIn) {
+                                const float2 m0 = mix_sample(make_float2(v.x, v.y), a.nco_tab[p9 + 2 * u], conj);
+                                const float2 m1 = mix_sample(make_float2(v.z, v.w), a.nco_tab[p9 + 2 * u + 1], conj);
+                                v = make_float4(m0.x, m0.y, m1.x, m1.y);
+                            }
                             split_tf32(v.x, ih[2 * u], il[2 * u]);
                             split_tf32(v.y, qh[2 * u], ql[2 * u]);
                             split_tf32(v.z, ih[2 * u + 1], il[2 * u + 1]);
@@ -852,13 +921,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < kPer; ++j) {
                         float2 v = make_float2(0.f, 0.f);
-                        if (kh * 16 + j < kCS) v = tc_load(a, rb * kRows + r, G * kCS + kh * 16 + j);
+                        if (kh * kPer + j < kCS) v = tc_load(a, rb * kInRows + r_in, G * kCS + kh * kPer + j);
+                        if (kMixIn) v = mix_sample(v, a.nco_tab[p9 + j], conj);
                         split_tf32(v.x, ih[j], il[j]);
                         split_tf32(v.y, qh[j], ql[j]);
                     }
                 }
+                if (kMixIn && ++p9 == kNcoPeriod) p9 = 0;
                 __syncwarp();
                 if (lane == 0) bar_arrive(bar0 + 8 * (kBarRawEmpty + slot));
                 if (warp == 0) NVX_TRACE(3, gi);
@@ -867,10 +938,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t col = lane_base + s * kSetCols;
                 if (!(a.dbg & 4)) {
-                    tmem_st16(col + 0 * 32, ih);
-                    tmem_st16(col + 1 * 32, il);
-                    tmem_st16(col + 2 * 32, qh);
-                    tmem_st16(col + 3 * 32, ql);
+                    tmem_st(col + 0 * 32, ih);
+                    tmem_st(col + 1 * 32, il);
+                    tmem_st(col + 2 * 32, qh);
+                    tmem_st(col + 3 * 32, ql);
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;");
@@ -897,8 +968,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                 bar_wait(bar0 + 8 * (kBarTile + slot), (uint32_t)((tq / L) & 1));
                 if (q == 0) NVX_TRACE(6, tq);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const int row0 = rb * kRows + q * 32;
-                const int r_max = a.rows - row0 < 32 ? a.rows - row0 : 32;
+                // mix on load: this warp's 32 rows are the streams rb 64 + (q & 1) 32 .. of channel q >> 1; output rows are
+                // channel rows, 2 stream + channel
+                const int row0 = kMixIn ? rb * kInRows + (q & 1) * 32 : rb * kRows + q * 32;
+                const int rows_left = (kMixIn ? a.rows_src : a.rows) - row0;
+                const int r_max = rows_left < 32 ? rows_left : 32;
                 if (a.dbg & 8) {
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     __syncwarp();
@@ -928,9 +1002,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fir_tcs_kernel(const __grid_con
                         if (n0 + n >= n_out) continue;
                         const long long tick = a.k_abs + n0 + n;
                         if (!a.mix) {
-                            float2* dst1 = a.out + (size_t)row0 * a.out_pitch + a.out_off + n0 + n;
+                            const long long out_step = kMixIn ? 2 * a.out_pitch : a.out_pitch;
+                            float2* dst1 = a.out + (size_t)(kMixIn ? 2 * row0 + (q >> 1) : row0) * a.out_pitch + a.out_off + n0 + n;
 #pragma unroll 4
-                            for (int rr = 0; rr < r_max; ++rr, dst1 += a.out_pitch)
+                            for (int rr = 0; rr < r_max; ++rr, dst1 += out_step)
                                 *dst1 = make_float2(rows0[rr * kDumpPitch + m], rows0[rr * kDumpPitch + NP + m]);
                             continue;
                         }
@@ -1009,15 +1084,20 @@ int tc_slots(int D, int N, int T, int L = 2) {        // raw-input slots that fi
     return 0;
 }
 
-template <int D, int L>
-cudaError_t launch_tcs(TcArgs& a, int sms, cudaStream_t stream) {
+template <int D, int L, bool kMixIn, int kCW>
+cudaError_t launch_tcs_w(TcArgs& a, int sms, cudaStream_t stream) {
     a.slots = tc_slots(D, kSN, a.T, L);
     const size_t smem = tc_smem(D, kSN, a.T, a.slots, L);
-    cudaError_t e = cudaFuncSetAttribute(fir_tcs_kernel<D, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fir_tcs_kernel<D, L, kMixIn, kCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long grid = a.work < sms ? a.work : sms;
-    fir_tcs_kernel<D, L><<<(unsigned)grid, kTcThreads, smem, stream>>>(a);
+    fir_tcs_kernel<D, L, kMixIn, kCW><<<(unsigned)grid, tcs_threads(kCW), smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+template <int D, int L, bool kMixIn = false>
+cudaError_t launch_tcs(TcArgs& a, int sms, cudaStream_t stream) {
+    return launch_tcs_w<D, L, kMixIn, 2>(a, sms, stream);
 }
 
 template <int D, int N>
@@ -1150,15 +1230,21 @@ void long_tc_free(LongTcStage* s) {
 
 // same contract as long_launch (fir_long.cu) for stages 0 and 1; cudaErrorNotSupported = this block cannot be described to the TMA
 // unit (misaligned pointer or pitch): the caller falls back to long_launch
+bool long_tc_mixes_on_load(const LongTcStage* s) { return s && s->D == NVX_D2 && s->streaming; }
+
 cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongStage& st, long long in_pitch, cudaStream_t stream) {
+    if (la.mix_in && !long_tc_mixes_on_load(s)) return cudaErrorInvalidValue;
     TcArgs a = {};
     a.map_gh = s->map_gh; a.map_gl = s->map_gl;
     a.in = la.in; a.hist = la.hist; a.out = la.out;
     a.n_in = la.n_in; a.in_pitch = in_pitch; a.out_pitch = la.out_pitch; a.out_off = la.out_off; a.k_abs = la.k_abs;
     a.nco = la.nco; a.rows = la.rows_in; a.s16 = la.s16; a.T = s->T; a.H = st.H; a.chunks = s->chunks; a.J = s->J; a.slots = 4; a.box_rows = s->box_rows;
-    a.mix = la.stage == 0;
-    for (int k = 0; k < kNcoPeriod; ++k)       // same expression as fir2cpp.C:105-106, rounded once to float
-        a.nco_tab[k] = make_float2((float)cos((2 * M_PI * k * 14000) / 63000), (float)-sin((2 * M_PI * k * 14000) / 63000));
+    a.mix = la.stage == 0 && !la.plain;
+    a.rows_src = la.mix_in ? la.rows_in / 2 : la.rows_in;
+    for (int k = 0; k < kNcoPeriod + 16; ++k) {      // same expression as fir2cpp.C:105-106, rounded once to float
+        const int k9 = k % kNcoPeriod;
+        a.nco_tab[k] = make_float2((float)cos((2 * M_PI * k9 * 14000) / 63000), (float)-sin((2 * M_PI * k9 * 14000) / 63000));
+    }
     // TMA boxes and 16-byte cp.async pieces: the block and its rows must start on 16-byte boundaries (tile windows do by
     // construction).  The block as a 2-D tensor of 32-bit (float2 input) or 16-bit (short2 input) elements, two per sample:
     if (((uintptr_t)la.in & 15) || ((in_pitch * (la.s16 ? 4 : 8)) & 15)) return cudaErrorNotSupported;
@@ -1166,9 +1252,9 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
     a.lead = s->chunks - a.cpt;
     if (chunk_samples(s->D) == kKB || s->streaming) {
         const size_t esz = la.s16 ? 2 : 4;
-        cuuint64_t dims[2] = {(cuuint64_t)(2 * la.n_in), (cuuint64_t)la.rows_in};
+        cuuint64_t dims[2] = {(cuuint64_t)(2 * la.n_in), (cuuint64_t)a.rows_src};
         cuuint64_t strides[1] = {(cuuint64_t)in_pitch * 2 * esz};
-        cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)kRows};
+        cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)(la.mix_in ? kRows / 2 : kRows)};
         cuuint32_t es[2] = {1, 1};
         if (s->enc(&a.map_x, la.s16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(la.in), dims, strides,
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1193,6 +1279,7 @@ cudaError_t long_tc_launch(const LongTcStage* s, const LongArgs& la, const LongS
         if (getenv("NVX_TC_TRIM") && atoi(getenv("NVX_TC_TRIM")) == 0) a.dbg |= 16;  // A/B: full-width MMAs for every chunk (same results)
         const bool three = a.lead > a.cpt;
         const cudaError_t e = s->D == NVX_D1 ? (three ? launch_tcs<NVX_D1, 3>(a, sms, stream) : launch_tcs<NVX_D1, 2>(a, sms, stream))
+                              : la.mix_in    ? (three ? launch_tcs<NVX_D2, 3, true>(a, sms, stream) : launch_tcs<NVX_D2, 2, true>(a, sms, stream))
                                              : (three ? launch_tcs<NVX_D2, 3>(a, sms, stream) : launch_tcs<NVX_D2, 2>(a, sms, stream));
         if (want && e == cudaSuccess && ++traced == 3) {
             static long long h[kTraceChunks * kTraceCols];

@@ -107,6 +107,40 @@ def test_long_taps_tensor_core_stage1(monkeypatch, lengths):
     cc.close()
 
 
+@pytest.mark.parametrize("lengths", [(255, 255, 255), (383, 511, 71)])
+def test_mix_on_load_equals_the_stage1_epilogue_mix(monkeypatch, lengths):
+    """With the reference offsets the streaming tensor-core stage 2 rotates each sample by its channel's NCO phase while it
+    converts it ("mix on load", the default: stage 1 writes ONE un-mixed 63 kHz row per stream); NVX_LONG_MIX=stage1 keeps the
+    rotation in the stage-1 epilogue (one row per channel).  Same FP32 products, same MMA order per row: the 900 Hz samples are
+    bit-identical -- over two pushes (carried, un-mixed history), a ragged stream count (130 = two 64-stream row blocks + 2) and
+    a block that does not start at tick 0.  NVX_LONG_TC=2 puts the CUDA-core stage 1 (plain rows) in front of the same stage 2."""
+    taps = designs(*lengths)
+    blk = 2520 * 70
+    rng = np.random.default_rng(29)
+    x = np.rint(rng.normal(0, 3000, size=(130, 2 * blk + 280 * 37, 2))).astype(np.float32)
+
+    def run():
+        eng = engine.Engine(130, blk, taps=taps)
+        ys = []
+        for a, b in ((0, 280 * 37), (280 * 37, 280 * 37 + blk), (280 * 37 + blk, 280 * 37 + 2 * blk)):
+            eng.push_host(np.ascontiguousarray(x[:, a:b]))
+            ys.append(eng.read_y3())
+        st = eng.stats()
+        eng.close()
+        assert st.long_tc_fallbacks == 0
+        return np.concatenate(ys, axis=2)
+
+    on_load = run()
+    monkeypatch.setenv("NVX_LONG_MIX", "stage1")
+    in_stage1 = run()
+    assert np.abs(in_stage1).max() > 0
+    assert np.array_equal(on_load.view(np.uint64), in_stage1.view(np.uint64))
+    monkeypatch.delenv("NVX_LONG_MIX")
+    monkeypatch.setenv("NVX_LONG_TC", "2")
+    cc1 = run()
+    assert np.abs(cc1 - on_load).max() <= REL_TOL * np.abs(on_load).max()
+
+
 @pytest.mark.parametrize("lengths", [(255, 255, 255), (61, 75, 111)])
 def test_long_taps_blocking_and_format_invariance(cuda_core_stage1, lengths):
     """Histories are carried per stage (long path, CUDA-core kernels) / recomputed from a longer input tail (medium class):
