@@ -592,6 +592,11 @@ constexpr int kTraceChunks = 96, kTraceCols = 8;
 // trace, 65 taps: 1 470 cycles per chunk against 963 with conversion, loads and epilogue knocked out), so four per quarter were
 // built and measured: 24 warps per CTA cap the kernel at 80 registers per thread, every role spills, and the whole chain is
 // SLOWER (65 taps: 332 -> 315 Gsamples/s with stage 2 on four, 286 with both stages; 255 taps: 288 -> 276 / 260).
+// Also built, measured and removed: one issuer warp per plane (I / Q: independent accumulators and A tiles) so that one thread's
+// per-batch operand set-up (~130 instructions of moves into uniform registers, ~300 cycles in which the short MMA queue runs dry:
+// 573 cycles of MMAs per 980-cycle chunk with every other role knocked out) overlaps the other's MMAs -- two interleaved MMA
+// streams are slower than one (that floor rose to 1 204 cycles per chunk; 65 / 255 taps: 330 / 280 -> 278 / 249 Gsamples/s);
+// and a host-built per-chunk plan table in the kernel parameters with 32-bit descriptor arithmetic (no measurable change).
 template <int D, int L, bool kMixIn = false, int kCW = 2>
 __global__ void __launch_bounds__(tcs_threads(kCW), 1) fir_tcs_kernel(const __grid_constant__ TcArgs a) {
     constexpr int N = kSN;
