@@ -597,6 +597,10 @@ constexpr int kTraceChunks = 96, kTraceCols = 8;
 // 573 cycles of MMAs per 980-cycle chunk with every other role knocked out) overlaps the other's MMAs -- two interleaved MMA
 // streams are slower than one (that floor rose to 1 204 cycles per chunk; 65 / 255 taps: 330 / 280 -> 278 / 249 Gsamples/s);
 // and a host-built per-chunk plan table in the kernel parameters with 32-bit descriptor arithmetic (no measurable change).
+// And: two converter groups taking ALTERNATE chunks (each thread all 32 columns, one A set per group, so that a chunk's chain of
+// hand-overs has two chunk periods to complete) -- correct only with two A sets and an even number of chunks in the ring (a parity
+// wait cannot tell phase k from phase k + 2), and slower where it applies (65 taps: 328 -> 319 Gsamples/s): the converters are
+// bound by their instruction throughput, not by the latency of the hand-overs.
 template <int D, int L, bool kMixIn = false, int kCW = 2>
 __global__ void __launch_bounds__(tcs_threads(kCW), 1) fir_tcs_kernel(const __grid_constant__ TcArgs a) {
     constexpr int N = kSN;
