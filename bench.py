@@ -643,25 +643,47 @@ def leg_config5(c, x, expect, taps_n, steps, warmup):
         peak, peak_src = 1125.0, "fallback: nominal dense TF32 = 2250 / 2 TFLOP/s (B200_PROFILING.md)"
     ach = S * BLOCK * flop / (fir_ms * 1e-3) / 1e12
 
-    def executed_tflop(D, h, rows, n_in):
-        # what the tensor cores execute for one stage (fir_long_tc.cu geometry, from the library's own band builder): per 128-row
-        # tile of n_tile outputs, `chunks` K chunks of 2 planes x 3 TF32 terms x 4 k-steps of M128 x n_tile x K8
+    def streaming(D, h):
+        # (geometry of the stage's band, served by the streaming kernel?)  Its signature: 64-output tiles and a tap count padded to
+        # D + lead chunks, lead <= two tiles' worth of chunks (fir_long_tc.cu: tcs_applies)
         try:
             g, _, _ = engine.long_tc_band(D, h)
         except engine.NvxError:
-            return 0.0           # the stage runs on CUDA cores
+            return None, False   # the stage runs on CUDA cores
+        cs = 32 // D * D
+        cpt, lead = D * g["n_tile"] // cs, g["chunks"] - D * g["n_tile"] // cs
+        return g, g["n_tile"] == 64 and 0 <= lead <= 2 * cpt and g["taps_padded"] == D + lead * cs
+
+    def executed_tflop(D, h, rows, n_in):
+        # what the tensor cores execute for one stage (fir_long_tc.cu geometry, from the library's own band builder): per 128-row
+        # tile of n_tile outputs, `chunks` K chunks of 2 planes x 3 TF32 terms x 4 k-steps of M128 x n_tile x K8
+        g, is_streaming = streaming(D, h)
+        if g is None:
+            return 0.0
         tiles = -(-rows // 128) * -(-(n_in // D) // g["n_tile"])
         cs = 32 // D * D
         cpt, lead = D * g["n_tile"] // cs, g["chunks"] - D * g["n_tile"] // cs
-        if g["n_tile"] == 64 and 0 <= lead <= cpt:        # streaming kernel: MMAs trimmed to the non-zero columns of the band, N = 16 .. 64
+        if is_streaming:         # streaming kernel (two or three live tiles): MMAs trimmed to the non-zero columns of the band, N = 16 .. 64
             opc, cols = cs // D, 0
             for c in range(g["chunks"]):
                 n_lo, n_hi = max(0, opc * (c - lead)), min(63, opc * c + opc - 1)
                 cols += ((n_hi | 15) + 1) - (n_lo & ~15)
-        else:
-            cols = g["chunks"] * g["n_tile"]
+        else:                    # tile-at-a-time kernel: the same trimming from its own window geometry (fir_tc_kernel)
+            N, Tp, cols = g["n_tile"], g["taps_padded"], 0
+            for c in range(g["chunks"]):
+                num = cs * c - Tp + 1
+                n_lo, n_hi = (0 if num <= 0 else -(-num // D)), min(N - 1, (cs * c + cs - 1) // D)
+                cols += ((n_hi | 15) + 1) - (n_lo & ~15) if n_lo <= n_hi else N
         return tiles * cols * 24 * 2.0 * 128 * 8 / 1e12
     ex = executed_tflop(4, taps[0], S, BLOCK) + executed_tflop(7, taps[1], 2 * S, BLOCK // 4)
+    # the HBM side of the same three kernels: input once, y1 (63 kHz) and y2 (9 kHz) written and read back once each.  y1 is ONE
+    # un-mixed row per stream when stage 2 mixes while it loads (reference offsets + streaming tensor-core stage 2, the default:
+    # engine.cu mix_on_load), else one row per channel
+    tc_mask = int(os.environ.get("NVX_LONG_TC", "3"))
+    mix_on_load = bool(tc_mask & 2) and streaming(7, taps[1])[1] and os.environ.get("NVX_LONG_MIX") != "stage1"
+    hbm_bytes = 8.0 + (1 if mix_on_load else 2) * 2 * 8.0 / 4 + 2 * 2 * 8.0 / 28 + 2 * 8.0 / 280
+    hbm_peak, hbm_src = measured_peak()
+    hbm_ach = S * BLOCK * hbm_bytes / (fir_ms * 1e-3) / 1e9
     return {
         "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
         "workload": "configs[4]: long-tap FIR stress, %d-tap Kaiser designs in all three stages, 1024 synthetic IQ streams per GPU resident in HBM "
@@ -674,7 +696,11 @@ def leg_config5(c, x, expect, taps_n, steps, warmup):
                      "kernel": "nvx::fir_tc_kernel<4,.> + <7,.> + fir_long_kernel<10,2>", "kernel_ms": fir_ms, **span_stats(spans),
                      "note": "achieved = ALGORITHMIC FP32 flops (%.0f per input sample) / time of the three stage kernels; the tensor cores "
                              "execute 3x that for the TF32 split plus the structural zeros of the Toeplitz band" % flop,
-                     "executed_tensor_tflops": ex / (fir_ms * 1e-3), "executed_frac": ex / (fir_ms * 1e-3) / peak},
+                     "executed_tensor_tflops": ex / (fir_ms * 1e-3), "executed_frac": ex / (fir_ms * 1e-3) / peak,
+                     "hbm": {"algorithmic_bytes_per_sample": hbm_bytes, "y1_rows_per_stream": 1 if mix_on_load else 2,
+                             "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src,
+                             "note": "the three stage kernels' compulsory HBM traffic (input + y1 and y2 written and read back once) / "
+                                     "their time: the bound that matters for short filters, the tensor figure for long ones"}},
         "gpu_launches": int(st.cascade_launches + st.demod_launches + st.aux_launches), "clocks": clocks,
         "check": {"bulletins_in_capture_all_ranks": exp_all, "decoded_exact_all_ranks": ok_all, "messages_total_all_ranks": n_all},
     }
