@@ -31,9 +31,10 @@ def _capture(text, offset, seconds, snr, seed):
 
 # (255, ...), (101, ...), (37, 47, 500): long-tap path; (61, 75, 111), (45, 47, 90): the fused kernel's medium class;
 # (21, 31, 51): shorter than the reference, zero-padded into the reference class
-# (383, 511, 71) and (516, 900, 71): streaming kernel with three live tiles in both stages / tile-at-a-time stage 2
+# (383, 511, 71) and (516, 900, 71): streaming kernel with three live tiles in both stages; (255, 930, 71): stage 2 beyond the
+# streaming kernel's 903 taps on the tile-at-a-time tensor-core kernel (and therefore the NCO mix in the stage-1 epilogue)
 @pytest.mark.parametrize("lengths", [(255, 255, 255), (101, 383, 129), (37, 47, 500), (61, 75, 111), (45, 47, 90), (21, 31, 51), (383, 511, 71),
-                                     (516, 900, 71)])
+                                     (516, 900, 71), (255, 930, 71)])
 def test_long_taps_against_restated_oracle(lengths):
     taps = designs(*lengths)
     seconds = 11.0
